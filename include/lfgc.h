@@ -1,0 +1,221 @@
+/*
+ * lfgc.h -- C ABI of liblfgc.so, the sm_100a implementation of the fV-SRN
+ * latent-feature-grid hot path of Bussler/Latent_Feature_Grid_Compression.
+ *
+ * The reference has no FFI layer: its operator API for this path is the Python
+ * nn.Module surface (model/Feature_Grid_Model.py, model/model_utils.py, ...).
+ * The Python modules in latent_feature_grid_compression_b200/ keep that surface
+ * and reach the GPU only through the entry points below (ctypes).  Each entry
+ * point names the reference code it replaces (file:line relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions (all functions):
+ *   - extern "C", plain pointers and sizes, no torch / C++ types;
+ *   - return 0 on success or a negative LFGC_E* code; never throw; the message
+ *     of the last failure on the calling thread is lfgc_last_error();
+ *   - every pointer is a caller-owned DEVICE pointer (fp32 unless stated) that
+ *     must stay valid until the work is complete in stream order;
+ *   - the last argument is the cudaStream_t to launch on (as void*); the
+ *     functions never synchronise and never allocate device memory, so they are
+ *     CUDA-graph capturable; host-side descriptor structs are read at call time;
+ *   - re-entrant across host threads and streams.
+ */
+#ifndef LFGC_H
+#define LFGC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFGC_ABI_VERSION 1
+#define LFGC_MAX_LEVELS 12 /* coefficient tensors per model (1 low-pass + up to 11 detail levels) */
+#define LFGC_MAX_TAPS 16   /* longest supported 1-D reconstruction filter */
+#define LFGC_MAX_LAYERS 8  /* hidden layers of the decoder MLP */
+
+enum {
+    LFGC_OK = 0,
+    LFGC_E_INVALID = -1,     /* bad argument (null pointer, bad size, unsupported shape) */
+    LFGC_E_UNSUPPORTED = -2, /* configuration outside what the kernels are built for */
+    LFGC_E_CUDA = -3,        /* a CUDA runtime call failed; see lfgc_last_error() */
+    LFGC_E_WORKSPACE = -4    /* caller-provided workspace too small */
+};
+
+/* mask-layer kinds (model/Smallify_Dropout.py, model/Variational_Dropout_Layer.py,
+ * model/Straight_Through_Dropout.py) */
+enum {
+    LFGC_MASK_IDENTITY = 0,
+    LFGC_MASK_DIRECT = 1,      /* m = p0                (Smallify betas, Smallify_Dropout.py:57; baked d_mask, :59) */
+    LFGC_MASK_VARIATIONAL = 2, /* m = exp(p0) + exp(p1/2) * noise  (Variational_Dropout_Layer.py:104-110) */
+    LFGC_MASK_STE_SIGMOID = 3, /* m = [sigmoid(p0) >= thr], aux = sigmoid(p0)  (Straight_Through_Dropout.py:55-58) */
+    LFGC_MASK_BERNOULLI = 4    /* m = [noise < p0]      (Straight_Through_Dropout.py:28-29) */
+};
+
+/* flags for lfgc_forward / lfgc_reconstruct / lfgc_train_step */
+enum {
+    LFGC_F_CLAMP = 1,        /* clamp output to [-1, 1] (eval mode, Feature_Grid_Model.py:78) */
+    LFGC_F_FAST_SIN = 2      /* range-reduced MUFU sin/cos instead of the precise path (not used for fp32 parity) */
+};
+
+/* Static shape of one model instance: what model_utils.setup_model fixes (model/model_utils.py:23-59). */
+typedef struct lfgc_model_desc {
+    int32_t C;      /* grid_features */
+    int32_t Cp;     /* channel stride of the channels-last grid, multiple of 4, >= C (pad channels are zero) */
+    int32_t G[3];   /* decoded grid extents (D, H, W) = (z, y, x); the reference uses G,G,G */
+    int32_t H;      /* n_hidden_size */
+    int32_t L;      /* n_layers (hidden layers, each followed by SnakeAlt) */
+    int32_t F;      /* n_embedding_freq; input width = 3 + 6F + C */
+} lfgc_model_desc;
+
+/* Wavelet synthesis chain: Feature_Grid_Model.decode_volume (model/Feature_Grid_Model.py:102-108) over
+ * _WaveletFilterNd.decode (wavelet_transform/Torch_Wavelet_Transform.py:91-104). */
+typedef struct lfgc_wavelet_desc {
+    int32_t n_coeff;                    /* number of coefficient tensors: 1 + number of synthesis levels */
+    int32_t C;                          /* channels */
+    int32_t n_taps;                     /* reconstruction filter length (even) */
+    float rec_lo[LFGC_MAX_TAPS];        /* pywt rec_lo, rounded to fp32 as the reference stores it (:41) */
+    float rec_hi[LFGC_MAX_TAPS];
+    int32_t dims[LFGC_MAX_LEVELS][3];   /* spatial extent of coefficient tensor l: level 0 is (C,d,d,d), l>=1 (C,7,d,d,d) */
+    int32_t target[LFGC_MAX_LEVELS][3]; /* output extent of synthesis level l (l>=1), = shape_array[l-1] */
+} lfgc_wavelet_desc;
+
+int lfgc_abi_version(void);
+const char* lfgc_last_error(void);
+/* number of SMs of the current device (grid sizing); negative on error */
+int lfgc_sm_count(void);
+
+/* ---- mask layers ------------------------------------------------------------------------------------------- */
+
+/* Mask multiplier of one mask tensor (n elements).  Replaces the forward of SmallifyDropout /
+ * VariationalDropout / MaskedWavelet_Straight_Through_Dropout / Straight_Through_Dropout
+ * (Smallify_Dropout.py:54-61, Variational_Dropout_Layer.py:101-113, Straight_Through_Dropout.py:26-30,53-61).
+ * mult_out[n] is the value multiplier; aux_out[n] (nullable) is the gradient multiplier (sigmoid for the STE,
+ * otherwise equal to mult).  noise is the caller-drawn xi ~ N(0,1) or u ~ U[0,1) (same torch generator order
+ * as the reference). */
+int lfgc_mask_multiplier(int mode, int64_t n, const float* p0, const float* p1, const float* noise,
+                         float threshold, float* mult_out, float* aux_out, void* stream);
+
+/* d mult -> d mask parameters (autograd of the above).  g0/g1 receive (accumulate != 0: +=) the gradients of
+ * p0/p1.  For LFGC_MASK_BERNOULLI and LFGC_MASK_IDENTITY nothing is written. */
+int lfgc_mask_param_grad(int mode, int64_t n, const float* p0, const float* p1, const float* noise,
+                         const float* gmult, float* g0, float* g1, int accumulate, void* stream);
+
+/* Smallify sign-variance tracker, device side: replaces SmallifySignVarianceTracker.sign_variance_pruning_onlyVar
+ * (Smallify_Dropout.py:103-112), which round-trips through the host every step. */
+int lfgc_smallify_ema(const float* betas, float* ema, float* emavar, int64_t n, float momentum, void* stream);
+
+/* ---- wavelet synthesis ------------------------------------------------------------------------------------- */
+
+/* One analysis level, used at model construction only: _WaveletFilterNd.encode
+ * (wavelet_transform/Torch_Wavelet_Transform.py:75-89) as called by Feature_Grid_Model.encode_volume
+ * (model/Feature_Grid_Model.py:83-99).  x (C,d0,d1,d2) -> out (C,8,e0,e1,e2); dec_lo/dec_hi are HOST arrays of the
+ * pywt decomposition taps (the flip of :56 is applied inside).  e_out receives the output extents; with x or out
+ * NULL only e_out is computed. */
+int lfgc_dwt_level(const float* x, int C, const int32_t d[3], int n_taps, const float* dec_lo, const float* dec_hi,
+                   float* out, int32_t e_out[3], void* stream);
+
+/* bytes of scratch lfgc_decode_fwd / lfgc_decode_bwd need for this chain */
+size_t lfgc_decode_scratch_bytes(const lfgc_wavelet_desc* w);
+
+/* grid_cl[z][y][x][Cp] = synthesis of (coeff[l] * mult[l]); mult[l] may be NULL (identity).
+ * coeff / mult are HOST arrays of n_coeff DEVICE pointers.  Pad channels [C, Cp) are written as zero.
+ * With n_coeff == 1 this is a masked NCDHW -> channels-last transpose. */
+int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* coeff, const float* const* mult,
+                    float* scratch, float* grid_cl, int Cp, void* stream);
+
+/* Adjoint of lfgc_decode_fwd (autograd of conv_transpose3d + mul, training/training.py:137).
+ * grad_coeff[l] (+)= d(coeff*mult) * gmul[l]  where gmul[l] is the gradient multiplier (aux of the mask; NULL = 1)
+ * grad_mult[l]  (+)= sum_c coeff[l][c] * d(coeff*mult)[c]      (NULL entries are skipped) */
+int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_grid_cl, int Cp, const float* const* coeff,
+                    const float* const* gmul, float* scratch, float* const* grad_coeff, float* const* grad_mult,
+                    int accumulate, void* stream);
+
+/* ---- per-sample path ----------------------------------------------------------------------------------------- */
+
+/* number of fp32 values in the packed MLP parameter block:
+ * [W0 (H x in) | b0 (H) | W1 (H x H) | b1 | ... | Wf (1 x H) | bf (1)], nn.Linear (out,in) row-major,
+ * i.e. net_layers.i.weight/.bias then final_layer.weight/.bias in state_dict order. */
+int64_t lfgc_mlp_param_count(const lfgc_model_desc* m);
+
+/* out[n] = MLP([xyz | Fourier(xyz) | trilinear(grid_cl, xyz)]).  Replaces Feature_Grid_Model.forward after
+ * decode_volume (model/Feature_Grid_Model.py:62-78): F.grid_sample(bilinear, zeros, align_corners=False),
+ * FourierEmbedding.embed (model/Feature_Embedding.py:14-16), 4 x SnakeAlt(Linear), final Linear, optional clamp. */
+int lfgc_forward(const lfgc_model_desc* m, const float* coords, int64_t n, const float* grid_cl,
+                 const float* mlp, float* out, int flags, void* stream);
+
+/* workspace (bytes) for lfgc_backward / lfgc_train_step: per-CTA partial sums of the MLP gradient */
+size_t lfgc_backward_workspace_bytes(const lfgc_model_desc* m);
+
+/* Backward of lfgc_forward for d(loss)/d(out) = grad_out[n] (recomputes the forward; nothing is saved):
+ *   grad_grid_cl[z][y][x][Cp] += trilinear scatter of d(features)       (L2 vector atomics)
+ *   grad_mlp[P]               (+)= MLP weight/bias gradients             (deterministic two-stage reduction)
+ *   grad_coords[n][3]          = d(loss)/d(coords) if non-NULL (the reference computes it, training.py:99, and
+ *                                never reads it)
+ * Replaces the autograd backward of grid_sampler_3d, cat, addmm, sin/pow (training/training.py:137). */
+int lfgc_backward(const lfgc_model_desc* m, const float* coords, int64_t n, const float* grad_out,
+                  const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
+                  float* grad_coords, int accumulate_mlp, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused training step core: in-kernel Philox voxel sampler (IndexDataset.__getitem__, data/IndexDataset.py:90-96),
+ * exact ground-truth lookup (data/Interpolation.py:8-44 at integer positions), forward, MSE loss
+ * (training/training.py:130,201) and backward, in one launch.
+ *   volume[R0][R1][R2] normalised volume; sample i of the step uses Philox(seed, counter = sample_offset + i)
+ *   loss_scale: d(loss)/d(pred) = loss_scale * 2 * (pred - gt); pass 1/N_global for the mean over the global batch
+ *   loss_sum[0] += sum (pred-gt)^2 over this call's samples (fp32 atomic, caller zeroes it)
+ *   explicit_idx (nullable, int64[n]): use these flat voxel indices instead of Philox (parity tests) */
+int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
+                    uint64_t seed, uint64_t sample_offset, const int64_t* explicit_idx, float loss_scale,
+                    const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
+                    float* loss_sum, int accumulate_mlp, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- sampler / ground truth ---------------------------------------------------------------------------------- */
+
+/* Random voxel sampler: replaces IndexDataset.__getitem__ + DataLoader collation (data/IndexDataset.py:90-96) and
+ * the ground-truth lookup trilinear_f_interpolation at integer positions (training/training.py:107-109).
+ * raw_out[n][3] = (i,j,k) as fp32, norm_out[n][3] = scales * (2*raw/max_idx - 1) with the reference's fp32
+ * operation order, gt_out[n] = volume[i][j][k].  Any output may be NULL.  explicit_idx as above. */
+int lfgc_sample(const float* volume, const int32_t R[3], int64_t n, uint64_t seed, uint64_t sample_offset,
+                const int64_t* explicit_idx, float* raw_out, float* norm_out, float* gt_out, void* stream);
+
+/* General trilinear_f_interpolation(p, f, min_bb, max_bb, res) (data/Interpolation.py:8-44): fp32 lattice
+ * coordinates, fp64 alphas, f[x][y][z] indexing, lerp order x -> y -> z. min_bb/max_bb are HOST float[3]. */
+int lfgc_trilinear(const float* p, int64_t n, const float* volume, const int32_t R[3], const float min_bb[3],
+                   const float max_bb[3], float* out, void* stream);
+
+/* ---- reconstruction ------------------------------------------------------------------------------------------ */
+
+/* Full-volume reconstruction of the slab [slab_begin, slab_end) along volume dim 0: replaces field_from_net
+ * (visualization/OutputToVTK.py:7-47): eval forward with clamp over every voxel of the slab.
+ * axis0[R0], axis1[R1], axis2[R2] are the normalised coordinates of each voxel index along the three volume
+ * dims (the host builds them with the reference's per-tile fp32 linspace * 2 - 1, times scales, so the
+ * coordinates are bit-identical to the reference's); sample (i,j,k) is evaluated at (axis0[i], axis1[j], axis2[k]).
+ * out_slab[(slab_end-slab_begin)][R1][R2]. */
+int lfgc_reconstruct(const lfgc_model_desc* m, const float* grid_cl, const float* mlp, const int32_t R[3],
+                     const float* axis0, const float* axis1, const float* axis2, int32_t slab_begin,
+                     int32_t slab_end, float* out_slab, int flags, void* stream);
+
+/* Deviation statistics (visualization/OutputToVTK.py:53-60), accumulated in fp64 on the device:
+ * acc[0] += sum (gt-pred)^2, acc[1] += sum |gt-pred|, acc[2] = max(acc[2], max gt), acc[3] = min(acc[3], min gt).
+ * The caller initialises acc = {0, 0, -inf, +inf} and finishes PSNR = 10 log10((max-min)^2 / (acc[0]/n)). */
+int lfgc_deviation_stats(const float* pred, const float* gt, int64_t n, double* acc, void* stream);
+
+/* ---- optimiser ----------------------------------------------------------------------------------------------- */
+
+/* torch.optim.Adam (training/training.py:199,232) on flat buffers, one launch.  step_count is a DEVICE int32
+ * holding the number of steps taken so far (incremented by the kernel, so the call is graph-replayable);
+ * lr is a DEVICE float (the host decay strategies write it).  grad_scale multiplies the gradient first
+ * (1/world for data parallel means).  l2[n] (nullable) adds 2*l2_weight*p (the Sum coeff^2 regulariser of
+ * SmallifyLoss / VariationalDropoutLoss) and l1 similarly adds l1_weight*sign(p) where the flags say so. */
+int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+              float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* p-gradient of the sample-independent regularisers added in place: g += w_l2 * 2 * p (n_l2 leading elements) */
+int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream);
+int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFGC_H */

@@ -1,0 +1,48 @@
+// Library-level entry points and per-device caches.
+#include "lfgc_common.cuh"
+
+namespace lfgc {
+
+char* last_error_buffer() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+
+static int g_sm_count[64];
+static int g_smem_optin[64];
+static bool g_have[64];
+
+static bool query_device(int& dev) {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        cudaGetLastError();
+        return false;
+    }
+    if (!g_have[dev]) {
+        int sms = 0, smem = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        g_sm_count[dev] = sms;
+        g_smem_optin[dev] = smem;
+        g_have[dev] = true;
+    }
+    return true;
+}
+
+int sm_count() {
+    int dev;
+    return query_device(dev) ? g_sm_count[dev] : -1;
+}
+
+int max_smem_optin() {
+    int dev;
+    return query_device(dev) ? g_smem_optin[dev] : 0;
+}
+
+}  // namespace lfgc
+
+extern "C" int lfgc_abi_version(void) { return LFGC_ABI_VERSION; }
+extern "C" const char* lfgc_last_error(void) { return lfgc::last_error_buffer(); }
+extern "C" int lfgc_sm_count(void) { return lfgc::sm_count(); }

@@ -1,0 +1,107 @@
+// Shared host/device helpers for liblfgc (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "lfgc.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "liblfgc is written for sm_100a (B200) only"
+#endif
+
+namespace lfgc {
+
+// ---- error plumbing ---------------------------------------------------------------------------------------------
+char* last_error_buffer();  // thread-local, defined in api.cu
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define LFGC_CUDA_OK(expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return ::lfgc::fail(LFGC_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                __FILE__, __LINE__);                                                \
+    } while (0)
+
+#define LFGC_LAUNCH_OK()                                                                           \
+    do {                                                                                            \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess)                                                                      \
+            return ::lfgc::fail(LFGC_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                                __FILE__, __LINE__);                                                \
+    } while (0)
+
+int sm_count();            // cached per device
+int max_smem_optin();      // cached per device (bytes)
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---- device helpers ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    // vectorised fp32 reduction straight into L2 (sm_90+): one 16-byte atomic per 4 channels
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// SnakeAlt(x) = 0.5 x + sin^2 x and its derivative 0.5 + sin 2x (model/Feature_Grid_Model.py:12-13).
+// Precise path: sincosf (full-range reduction, <= 2 ulp) so that fp32 parity (1e-5 rel) holds for any argument.
+__device__ __forceinline__ float snake_precise(float z) {
+    float s = sinf(z);
+    return fmaf(s, s, 0.5f * z);
+}
+__device__ __forceinline__ void snake_and_grad_precise(float z, float& h, float& g) {
+    float s, c;
+    sincosf(z, &s, &c);
+    h = fmaf(s, s, 0.5f * z);
+    g = fmaf(2.0f * s, c, 0.5f);
+}
+
+// Philox4x32-10 counter-based generator (Salmon et al. 2011), one call per sample.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+// uniform voxel index in [0, n_voxels) from one Philox draw (multiply-high mapping of a 64-bit random)
+__device__ __forceinline__ unsigned long long philox_voxel(uint64_t seed, uint64_t counter,
+                                                           unsigned long long n_voxels) {
+    uint4 r = philox4x32_10(make_uint4((uint32_t)counter, (uint32_t)(counter >> 32), 0x6c666763u, 0u),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    unsigned long long r64 = ((unsigned long long)r.x << 32) | r.y;
+    return __umul64hi(r64, n_voxels);
+}
+
+// Normalised coordinate of voxel index i along an axis with max_idx = R-1 and scale = max_idx / max(max_idx):
+// scales * ((1 - -1) * ((raw - 0) / (max_idx - 0)) + -1), fp32, one rounding per operation as in
+// data/IndexDataset.py:7-8,92-95 (no FMA contraction).
+__device__ __forceinline__ float normalized_coord(float raw, float max_idx, float scale) {
+    float q = __fdiv_rn(raw, max_idx);
+    float v = __fadd_rn(__fmul_rn(2.0f, q), -1.0f);
+    return __fmul_rn(scale, v);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lfgc

@@ -1,0 +1,75 @@
+// Flat-buffer optimiser pieces: Adam (torch.optim.Adam semantics, training/training.py:199,232) and the
+// sample-independent regulariser gradients of SmallifyLoss (model/Smallify_Dropout.py:22-40).
+#include "lfgc_common.cuh"
+
+namespace lfgc {
+
+__global__ void adam_tick_kernel(int32_t* step) { *step += 1; }
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, const float* __restrict__ lr_ptr,
+                            const int32_t* __restrict__ step_ptr, float b1, float b2, float eps, float gscale) {
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        const int step = *step_ptr;  // already incremented by adam_tick_kernel
+        const double bc1 = 1.0 - pow((double)b1, (double)step);
+        const double bc2 = 1.0 - pow((double)b2, (double)step);
+        s_step_size = (float)((double)*lr_ptr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * gscale;
+    float mi = m[i], vi = v[i];
+    mi = mi + (gi - mi) * (1.0f - b1);              // exp_avg.lerp_(grad, 1 - beta1)
+    vi = vi * b2 + (1.0f - b2) * gi * gi;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(vi) / s_bc2_sqrt + eps;
+    p[i] = p[i] - s_step_size * (mi / denom);       // param.addcdiv_(exp_avg, denom, value=-step_size)
+    m[i] = mi;
+    v[i] = vi;
+}
+
+__global__ void add_l2_grad_kernel(float* __restrict__ g, const float* __restrict__ p, int64_t n, float w2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g[i] = fmaf(w2, p[i], g[i]);
+}
+__global__ void add_l1_grad_kernel(float* __restrict__ g, const float* __restrict__ p, int64_t n, float w) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float x = p[i];
+        g[i] += w * ((x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f));
+    }
+}
+
+}  // namespace lfgc
+
+using namespace lfgc;
+
+extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+                         float beta1, float beta2, float eps, float grad_scale, void* stream) {
+    if (!p || !g || !m || !v || !lr || !step_count || n < 0) return fail(LFGC_E_INVALID, "adam: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    adam_tick_kernel<<<1, 1, 0, st>>>(step_count);
+    LFGC_LAUNCH_OK();
+    if (n == 0) return LFGC_OK;
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
+
+extern "C" int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream) {
+    if (!g || !p || n < 0) return fail(LFGC_E_INVALID, "add_l2_grad: bad arguments");
+    if (n == 0) return LFGC_OK;
+    add_l2_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, p, n, 2.0f * weight);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
+
+extern "C" int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* stream) {
+    if (!g || !p || n < 0) return fail(LFGC_E_INVALID, "add_l1_grad: bad arguments");
+    if (n == 0) return LFGC_OK;
+    add_l1_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, p, n, weight);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
