@@ -85,6 +85,9 @@ int lfgc_abi_version(void);
 const char* lfgc_last_error(void);
 /* number of SMs of the current device (grid sizing); negative on error */
 int lfgc_sm_count(void);
+/* kernels launched by this library so far in this process (host-side counter; a CUDA-graph replay re-issues the
+ * launches recorded during capture without passing through here) */
+long long lfgc_launch_count(void);
 
 /* ---- mask layers ------------------------------------------------------------------------------------------- */
 
@@ -161,12 +164,15 @@ int lfgc_backward(const lfgc_model_desc* m, const float* coords, int64_t n, cons
 /* Fused training step core: in-kernel Philox voxel sampler (IndexDataset.__getitem__, data/IndexDataset.py:90-96),
  * exact ground-truth lookup (data/Interpolation.py:8-44 at integer positions), forward, MSE loss
  * (training/training.py:130,201) and backward, in one launch.
- *   volume[R0][R1][R2] normalised volume; sample i of the step uses Philox(seed, counter = sample_offset + i)
+ *   volume[R0][R1][R2] normalised volume; sample i of the step uses Philox(seed, counter = sample_offset + i
+ *   + *step_dev * step_stride); step_dev (nullable) is a DEVICE int32 step counter (the one lfgc_adam increments),
+ *   which lets a captured CUDA graph draw fresh samples on every replay
  *   loss_scale: d(loss)/d(pred) = loss_scale * 2 * (pred - gt); pass 1/N_global for the mean over the global batch
  *   loss_sum[0] += sum (pred-gt)^2 over this call's samples (fp32 atomic, caller zeroes it)
  *   explicit_idx (nullable, int64[n]): use these flat voxel indices instead of Philox (parity tests) */
 int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
-                    uint64_t seed, uint64_t sample_offset, const int64_t* explicit_idx, float loss_scale,
+                    uint64_t seed, uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
+                    const int64_t* explicit_idx, float loss_scale,
                     const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
                     float* loss_sum, int accumulate_mlp, void* workspace, size_t workspace_bytes, void* stream);
 

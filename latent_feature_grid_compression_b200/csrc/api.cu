@@ -1,12 +1,18 @@
 // Library-level entry points and per-device caches.
 #include "lfgc_common.cuh"
 
+#include <atomic>
+
 namespace lfgc {
 
 char* last_error_buffer() {
     static thread_local char buf[512] = {0};
     return buf;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 static int g_sm_count[64];
 static int g_smem_optin[64];
@@ -46,3 +52,4 @@ int max_smem_optin() {
 extern "C" int lfgc_abi_version(void) { return LFGC_ABI_VERSION; }
 extern "C" const char* lfgc_last_error(void) { return lfgc::last_error_buffer(); }
 extern "C" int lfgc_sm_count(void) { return lfgc::sm_count(); }
+extern "C" long long lfgc_launch_count(void) { return lfgc::launch_count(); }

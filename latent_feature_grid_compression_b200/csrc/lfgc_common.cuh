@@ -16,6 +16,7 @@ namespace lfgc {
 
 // ---- error plumbing ---------------------------------------------------------------------------------------------
 char* last_error_buffer();  // thread-local, defined in api.cu
+void count_launch();        // host-side counter of kernel launches issued by this library (api.cu)
 
 inline int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -39,6 +40,7 @@ inline int fail(int code, const char* fmt, ...) {
         if (_e != cudaSuccess)                                                                      \
             return ::lfgc::fail(LFGC_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
                                 __FILE__, __LINE__);                                                \
+        ::lfgc::count_launch();                                                                     \
     } while (0)
 
 int sm_count();            // cached per device

@@ -30,7 +30,8 @@ struct BwdArgs {
     int R[3];
     float max_idx[3], scales[3];
     unsigned long long n_voxels;
-    uint64_t seed, sample_offset;
+    uint64_t seed, sample_offset, step_stride;
+    const int32_t* step_dev;
     const int64_t* explicit_idx;
     float loss_scale2;          // 2 * loss_scale
     float* loss_sum;
@@ -148,6 +149,9 @@ __global__ void __launch_bounds__(kThreads, 1) sample_backward_kernel(const __gr
     for (int o = 0; o < NO; ++o) accWf[o] = 0.0f;
     float accbf = 0.0f, loss_part = 0.0f;
 
+    uint64_t sample_base = A.sample_offset;
+    if (FUSED && A.step_dev) sample_base += (uint64_t)(*A.step_dev) * A.step_stride;
+
     const int64_t ntiles = (A.n + kTile - 1) / kTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---- G: input stage -------------------------------------------------------------------------------------
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) sample_backward_kernel(const __gr
             if (valid) {
                 if (FUSED) {
                     unsigned long long v = A.explicit_idx ? (unsigned long long)A.explicit_idx[s]
-                                                          : philox_voxel(A.seed, A.sample_offset + (uint64_t)s, A.n_voxels);
+                                                          : philox_voxel(A.seed, sample_base + (uint64_t)s, A.n_voxels);
                     const unsigned long long r12 = (unsigned long long)A.R[1] * A.R[2];
                     const int i = (int)(v / r12);
                     const int j = (int)((v / A.R[2]) % A.R[1]);
@@ -451,7 +455,8 @@ extern "C" int lfgc_backward(const lfgc_model_desc* m, const float* coords, int6
     A.explicit_idx = nullptr;
     A.loss_sum = nullptr;
     A.loss_scale2 = 0.0f;
-    A.seed = A.sample_offset = 0;
+    A.seed = A.sample_offset = A.step_stride = 0;
+    A.step_dev = nullptr;
     A.n_voxels = 1;
     for (int a = 0; a < 3; ++a) { A.R[a] = 1; A.max_idx[a] = 1.0f; A.scales[a] = 1.0f; }
     A.n = n;
@@ -462,7 +467,8 @@ extern "C" int lfgc_backward(const lfgc_model_desc* m, const float* coords, int6
 }
 
 extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
-                               uint64_t seed, uint64_t sample_offset, const int64_t* explicit_idx, float loss_scale,
+                               uint64_t seed, uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
+                               const int64_t* explicit_idx, float loss_scale,
                                const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
                                float* loss_sum, int accumulate_mlp, void* workspace, size_t workspace_bytes,
                                void* stream) {
@@ -485,6 +491,8 @@ extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, co
     A.loss_scale2 = 2.0f * loss_scale;
     A.seed = seed;
     A.sample_offset = sample_offset;
+    A.step_dev = step_dev;
+    A.step_stride = step_stride;
     A.n_voxels = (unsigned long long)R[0] * R[1] * R[2];
     float mx = 0.0f;
     for (int a = 0; a < 3; ++a) {

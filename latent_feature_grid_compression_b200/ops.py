@@ -5,7 +5,7 @@ raises ``LfgcError`` on failure.  There is no CPU path.
 """
 from __future__ import annotations
 
-import ctypes as C
+import ctypes as ct
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -71,9 +71,9 @@ class Geometry:
                 w.target[l][a] = int(self.shape_array[l - 1][a]) if l >= 1 else 0
         self.wavelet_desc = w
         lib = L.load()
-        self.mlp_param_count = int(lib.lfgc_mlp_param_count(C.byref(m)))
-        self.decode_scratch_bytes = int(lib.lfgc_decode_scratch_bytes(C.byref(w)))
-        self.backward_workspace_bytes = int(lib.lfgc_backward_workspace_bytes(C.byref(m)))
+        self.mlp_param_count = int(lib.lfgc_mlp_param_count(ct.byref(m)))
+        self.decode_scratch_bytes = int(lib.lfgc_decode_scratch_bytes(ct.byref(w)))
+        self.backward_workspace_bytes = int(lib.lfgc_backward_workspace_bytes(ct.byref(m)))
 
     def coeff_shape(self, l):
         d = self.coeff_dims[l]
@@ -133,9 +133,9 @@ def dwt_level(x: torch.Tensor, wavelet: str):
     _req(x, 'x')
     dec_lo, dec_hi, _, _ = wavelets.filter_bank(wavelet)
     n = len(dec_lo)
-    lo = (C.c_float * n)(*[np.float32(v) for v in dec_lo])
-    hi = (C.c_float * n)(*[np.float32(v) for v in dec_hi])
-    e = (C.c_int32 * 3)()
+    lo = (ct.c_float * n)(*[np.float32(v) for v in dec_lo])
+    hi = (ct.c_float * n)(*[np.float32(v) for v in dec_hi])
+    e = (ct.c_int32 * 3)()
     d = L.int3(x.shape[1:])
     L.check(lib.lfgc_dwt_level(None, x.shape[0], d, n, lo, hi, None, e, None), 'lfgc_dwt_level(size)')
     out = torch.empty((x.shape[0], 8, e[0], e[1], e[2]), device=x.device, dtype=torch.float32)
@@ -158,7 +158,7 @@ def decode_fwd(geom: Geometry, coeffs: Sequence[torch.Tensor], mults: Sequence[O
         scratch = torch.empty(max(geom.decode_scratch_bytes // 4, 4), device=dev, dtype=torch.float32)
     if out is None:
         out = torch.empty((*geom.G, geom.Cp), device=dev, dtype=torch.float32)
-    L.check(lib.lfgc_decode_fwd(C.byref(geom.wavelet_desc), L.ptr_array([_p(c) for c in coeffs]),
+    L.check(lib.lfgc_decode_fwd(ct.byref(geom.wavelet_desc), L.ptr_array([_p(c) for c in coeffs]),
                                 L.ptr_array([_p(m) for m in mults]), _p(scratch), _p(out), geom.Cp, _stream()),
             'lfgc_decode_fwd')
     return out
@@ -176,7 +176,7 @@ def decode_bwd(geom: Geometry, grad_grid_cl, coeffs, gmuls, want_gmult: Sequence
     if grad_mults is None:
         grad_mults = [torch.empty(geom.mask_shape(i), device=dev, dtype=torch.float32) if w else None
                       for i, w in enumerate(want_gmult)]
-    L.check(lib.lfgc_decode_bwd(C.byref(geom.wavelet_desc), _p(grad_grid_cl), geom.Cp,
+    L.check(lib.lfgc_decode_bwd(ct.byref(geom.wavelet_desc), _p(grad_grid_cl), geom.Cp,
                                 L.ptr_array([_p(c) for c in coeffs]), L.ptr_array([_p(m) for m in gmuls]),
                                 _p(scratch), L.ptr_array([_p(g) for g in grad_coeffs]),
                                 L.ptr_array([_p(g) for g in grad_mults]), 0, _stream()), 'lfgc_decode_bwd')
@@ -193,7 +193,7 @@ def sample_forward(geom: Geometry, coords, grid_cl, mlp_flat, clamp=False, out=N
     n = coords.numel() // 3
     if out is None:
         out = torch.empty(n, device=coords.device, dtype=torch.float32)
-    L.check(lib.lfgc_forward(C.byref(geom.model_desc), _p(coords), n, _p(_req(grid_cl, 'grid_cl')),
+    L.check(lib.lfgc_forward(ct.byref(geom.model_desc), _p(coords), n, _p(_req(grid_cl, 'grid_cl')),
                              _p(_req(mlp_flat, 'mlp')), _p(out), L.F_CLAMP if clamp else 0, _stream()), 'lfgc_forward')
     return out
 
@@ -209,7 +209,7 @@ def sample_backward(geom: Geometry, coords, grad_out, grid_cl, mlp_flat, grad_gr
         grad_mlp = torch.empty(geom.mlp_param_count, device=dev, dtype=torch.float32)
     if workspace is None:
         workspace = torch.empty(geom.backward_workspace_bytes // 4, device=dev, dtype=torch.float32)
-    L.check(lib.lfgc_backward(C.byref(geom.model_desc), _p(_req(coords, 'coords')), n, _p(_req(grad_out, 'grad_out')),
+    L.check(lib.lfgc_backward(ct.byref(geom.model_desc), _p(_req(coords, 'coords')), n, _p(_req(grad_out, 'grad_out')),
                               _p(_req(grid_cl, 'grid_cl')), _p(_req(mlp_flat, 'mlp')), _p(grad_grid_cl), _p(grad_mlp),
                               None, 1 if accumulate_mlp else 0, _p(workspace), workspace.numel() * 4, _stream()),
             'lfgc_backward')
@@ -217,13 +217,15 @@ def sample_backward(geom: Geometry, coords, grad_out, grid_cl, mlp_flat, grad_gr
 
 
 def train_step(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl, mlp_flat,
-               grad_grid_cl, grad_mlp, loss_sum, workspace, explicit_idx=None, accumulate_mlp=False):
+               grad_grid_cl, grad_mlp, loss_sum, workspace, explicit_idx=None, accumulate_mlp=False, step_dev=None,
+               step_stride: int = 0):
     lib = L.load()
     _req(volume, 'volume')
     if explicit_idx is not None:
         _req(explicit_idx, 'explicit_idx', torch.int64)
-    L.check(lib.lfgc_train_step(C.byref(geom.model_desc), _p(volume), L.int3(volume.shape), int(n), int(seed),
-                                int(sample_offset), _p(explicit_idx), float(loss_scale), _p(_req(grid_cl, 'grid_cl')),
+    L.check(lib.lfgc_train_step(ct.byref(geom.model_desc), _p(volume), L.int3(volume.shape), int(n), int(seed),
+                                int(sample_offset), _p(step_dev), int(step_stride), _p(explicit_idx), float(loss_scale),
+                                _p(_req(grid_cl, 'grid_cl')),
                                 _p(_req(mlp_flat, 'mlp')), _p(grad_grid_cl), _p(grad_mlp), _p(loss_sum),
                                 1 if accumulate_mlp else 0, _p(workspace), workspace.numel() * 4, _stream()),
             'lfgc_train_step')
@@ -270,7 +272,7 @@ def reconstruct(geom: Geometry, grid_cl, mlp_flat, vol_shape, axes, slab_begin: 
         _req(a, 'axis')
         if a.numel() != R:
             raise L.LfgcError('axis table length %d != extent %d' % (a.numel(), R))
-    L.check(lib.lfgc_reconstruct(C.byref(geom.model_desc), _p(_req(grid_cl, 'grid_cl')), _p(_req(mlp_flat, 'mlp')),
+    L.check(lib.lfgc_reconstruct(ct.byref(geom.model_desc), _p(_req(grid_cl, 'grid_cl')), _p(_req(mlp_flat, 'mlp')),
                                  L.int3(vol_shape), _p(axes[0]), _p(axes[1]), _p(axes[2]), int(slab_begin),
                                  int(slab_end), _p(out), L.F_CLAMP if clamp else 0, _stream()), 'lfgc_reconstruct')
     return out
@@ -282,6 +284,11 @@ def deviation_stats_accumulate(pred, gt, acc):
     _req(acc, 'acc', torch.float64)
     L.check(lib.lfgc_deviation_stats(_p(_req(pred, 'pred')), _p(_req(gt, 'gt')), pred.numel(), _p(acc), _stream()),
             'lfgc_deviation_stats')
+
+
+def launch_count() -> int:
+    """Kernels launched through the C ABI so far in this process."""
+    return int(L.load().lfgc_launch_count())
 
 
 def adam(p, g, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):

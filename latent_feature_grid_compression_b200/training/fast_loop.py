@@ -1,0 +1,277 @@
+"""Graph-captured, data-parallel training loop on flat buffers.
+
+This is the B200-first counterpart of ``solve_model`` / ``training`` (reference training/training.py:71-243).  The
+unchanged reference loop is launch- and sync-bound (DataLoader workers, H2D copies, three ``.item()`` calls and
+a host round trip of the Smallify tracker per step); here one training step is
+
+    mask multipliers (+ Smallify EMA)            lfgc_mask_multiplier / lfgc_smallify_ema
+    wavelet synthesis -> channels-last grid      lfgc_decode_fwd
+    sampler + GT + forward + MSE + backward      lfgc_train_step          (one fused kernel)
+    synthesis adjoint + mask gradients           lfgc_decode_bwd / lfgc_mask_param_grad
+    [ one NCCL all-reduce of the flat gradient ] torch.distributed (only collective of the path)
+    regulariser gradients + Adam                 lfgc_add_l1/l2_grad, lfgc_adam
+
+captured once in a CUDA graph and replayed; the sample stream advances through the device-side step counter, the
+learning rate is a device scalar the host decay strategy writes.  All parameters, gradients and Adam moments live
+in single flat fp32 buffers; the model's ``nn.Parameter`` objects are views into them, so ``state_dict``,
+``save_dropvalues_on_grid`` and the reconstruction path keep working.
+
+Data parallelism: every rank draws ``batch`` samples of the same global Philox stream at its own
+offset, the flat gradient is summed with one all-reduce (the loss is pre-scaled by 1/global batch), the
+sample-independent regulariser gradients are added after the reduction, and Adam runs redundantly on every rank.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .. import ops
+from ..model.Dropout_Layer import DropoutLayer
+from ..model.Feature_Grid_Model import Feature_Grid_Model, _multipliers
+from ..model.Smallify_Dropout import SmallifyDropout
+from ..model.Straight_Through_Dropout import MaskedWavelet_Straight_Through_Dropout, Straight_Through_Dropout
+from ..model.Variational_Dropout_Layer import VariationalDropout
+
+
+class FastTrainer:
+
+    def __init__(self, model: Feature_Grid_Model, volume: torch.Tensor, batch: int, lr: float = 0.008, seed: int = 0,
+                 rank: int = 0, world_size: int = 1, process_group=None, weight_l1: float = 0.0,
+                 weight_l2: float = 0.0, use_graph: bool = True, betas=(0.9, 0.999), eps: float = 1e-8):
+        if not volume.is_cuda:
+            raise L.LfgcError('FastTrainer needs the volume on the GPU')
+        if any(isinstance(d, VariationalDropout) and d.d_mask is None for d in model.drop):
+            raise NotImplementedError('variational dropout trains through the nn.Module path (its likelihood loss is '
+                                      'not fused yet); FastTrainer covers no-mask, Smallify and straight-through masks')
+        self.model = model
+        self.volume = volume.contiguous().float()
+        self.batch = int(batch)
+        self.rank, self.world = int(rank), int(world_size)
+        self.group = process_group
+        self.seed = int(seed)
+        self.weight_l1, self.weight_l2 = float(weight_l1), float(weight_l2)
+        self.betas, self.eps = betas, eps
+        self.device = self.volume.device
+        model.train()
+        self.geom = model.geometry()
+
+        # ---- flat buffers: [coefficients | trainable mask parameters | MLP] --------------------------------------
+        self.coeff_params = [p for p in model.feature_grid]
+        self.mask_params = []
+        for d in model.drop:
+            if isinstance(d, DropoutLayer):
+                self.mask_params += [p for p in d.parameters()]
+        self.mlp_params = model._mlp_params()
+        every = self.coeff_params + self.mask_params + self.mlp_params
+        with torch.no_grad():
+            self.flat_p = torch.cat([p.detach().reshape(-1).to(self.device, torch.float32) for p in every])
+            self._slices = []
+            off = 0
+            for p in every:
+                n = p.numel()
+                p.data = self.flat_p[off:off + n].view(p.shape)
+                self._slices.append((off, n))
+                off += n
+        self.n_coeff_elems = sum(p.numel() for p in self.coeff_params)
+        self.n_mask_elems = sum(p.numel() for p in self.mask_params)
+        self.mlp_off = self.n_coeff_elems + self.n_mask_elems
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.flat_m = torch.zeros_like(self.flat_p)
+        self.flat_v = torch.zeros_like(self.flat_p)
+        # keep the model's own MLP pack coherent with the shared buffer
+        pack = model._mlp_pack
+        pack.flat = self.flat_p[self.mlp_off:]
+        pack._layout = []
+        o = 0
+        for p in self.mlp_params:
+            pack._layout.append((o, p.numel()))
+            o += p.numel()
+        self.mlp_flat = pack.flat
+        self._grad_view = {}
+        for p, (o, n) in zip(every, self._slices):
+            self._grad_view[id(p)] = self.flat_g[o:o + n].view(p.shape)
+
+        self.lr_dev = torch.tensor([lr], device=self.device, dtype=torch.float32)
+        self.step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.loss_sum = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self.grid_cl = torch.empty((*self.geom.G, self.geom.Cp), device=self.device, dtype=torch.float32)
+        self.grad_grid = torch.zeros_like(self.grid_cl)
+        self.scratch = torch.empty(max(self.geom.decode_scratch_bytes // 4, 4), device=self.device)
+        self.workspace = torch.empty(self.geom.backward_workspace_bytes // 4, device=self.device)
+        self.steps_done = 0
+        self.launches_per_step = None
+        self._graph = None
+        self._use_graph = use_graph
+
+    # ------------------------------------------------------------------------------------------------------------
+    def grad_of(self, p):
+        return self._grad_view[id(p)]
+
+    def _step_body(self):
+        model, geom = self.model, self.geom
+        specs = model.mask_specs()
+        mults, auxs = _multipliers(specs)
+        coeffs = [p.data for p in self.coeff_params]
+        ops.decode_fwd(geom, coeffs, mults, scratch=self.scratch, out=self.grid_cl)
+        self.grad_grid.zero_()
+        self.loss_sum.zero_()
+        n_global = self.batch * self.world
+        ops.train_step(geom, self.volume, self.batch, self.seed, self.rank * self.batch, 1.0 / n_global, self.grid_cl,
+                       self.mlp_flat, self.grad_grid, self.flat_g[self.mlp_off:], self.loss_sum, self.workspace,
+                       step_dev=self.step_dev, step_stride=n_global)
+        want = [s is not None and len(s.grad_params) > 0 for s in specs]
+        _, gmults = ops.decode_bwd(geom, self.grad_grid, coeffs, auxs, want, scratch=self.scratch,
+                                   grad_coeffs=[self.grad_of(p) for p in self.coeff_params])
+        for spec, gm in zip(specs, gmults):
+            if spec is None or not spec.grad_params:
+                continue
+            g0, g1 = ops.mask_param_grad(spec.mode, spec.p0.detach(), None if spec.p1 is None else spec.p1.detach(),
+                                         spec.noise, gm)
+            self.grad_of(spec.grad_params[0]).copy_(g0)
+            if len(spec.grad_params) == 2:
+                self.grad_of(spec.grad_params[1]).copy_(g1)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.group)
+        # sample-independent regularisers (SmallifyLoss): added once, after the reduction
+        if self.weight_l2 > 0.0 and self.n_coeff_elems:
+            ops.add_l2_grad(self.flat_g[:self.n_coeff_elems], self.flat_p[:self.n_coeff_elems], self.weight_l2)
+        if self.weight_l1 > 0.0 and self.n_mask_elems:
+            ops.add_l1_grad(self.flat_g[self.n_coeff_elems:self.mlp_off], self.flat_p[self.n_coeff_elems:self.mlp_off],
+                            self.weight_l1)
+        ops.adam(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_dev, self.step_dev, self.betas[0],
+                 self.betas[1], self.eps)
+
+    def capture(self):
+        """Warm up eagerly (counts launches), then record the step into a CUDA graph."""
+        state = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.step_dev.clone())
+        trackers = [(d.tracker.EMA.clone(), d.tracker.EMAVar.clone()) for d in self.model.drop
+                    if isinstance(d, SmallifyDropout)]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                before = ops.launch_count()
+                self._step_body()
+                self.launches_per_step = ops.launch_count() - before
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if self._use_graph:
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._step_body()
+        # undo the warm-up / capture side effects so that training starts from the initial state
+        with torch.no_grad():
+            self.flat_p.copy_(state[0])
+            self.flat_m.copy_(state[1])
+            self.flat_v.copy_(state[2])
+            self.step_dev.copy_(state[3])
+            it = iter(trackers)
+            for d in self.model.drop:
+                if isinstance(d, SmallifyDropout):
+                    ema, var = next(it)
+                    d.tracker.EMA.copy_(ema)
+                    d.tracker.EMAVar.copy_(var)
+        torch.cuda.synchronize()
+
+    def step(self):
+        """One optimiser step over ``batch`` fresh samples per rank (asynchronous)."""
+        if self.launches_per_step is None:
+            self.capture()
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._step_body()
+        self.steps_done += 1
+
+    def set_lr(self, lr: float):
+        self.lr_dev.fill_(float(lr))
+
+    def last_loss(self) -> float:
+        """Mean squared error of the last step's local batch (device -> host read)."""
+        return float(self.loss_sum.item()) / self.batch
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole training run: the reference's ``training(args)`` flow on the fast loop
+# ---------------------------------------------------------------------------------------------------------------------
+
+class NeurcompDecay:
+    """x ``lr_decay`` whenever a pass boundary is crossed and (pass + 1) % pass_decay == 0
+    (reference training/learning_rate_decay.py:24-34)."""
+
+    def __init__(self, trainer: FastTrainer, lr: float, pass_decay: int, lr_decay: float):
+        self.trainer, self.lr, self.pass_decay, self.lr_decay = trainer, lr, pass_decay, lr_decay
+
+    def update(self, prior_passes: int, cur_passes: float):
+        if prior_passes != int(cur_passes) and (int(cur_passes) + 1) % self.pass_decay == 0:
+            self.lr *= self.lr_decay
+            self.trainer.set_lr(self.lr)
+
+
+def _regulariser_weights(args):
+    drop = args.get('drop_type') or ''
+    if drop and 'variational' not in drop:
+        return float(args['lambda_drop_loss']), float(args['lambda_weight_loss'])
+    return 0.0, 0.0
+
+
+def solve_phase(model, volume, n_voxels, args, max_pass, lr, decay: bool, seed=0, rank=0, world=1, group=None,
+                regularise=True, verbose=False):
+    """The reference's pass accounting (training.py:87,112-114,178): stop once int(volume_passes) >= max_pass."""
+    batch = int(args['batch_size']) * int(args['sample_size'])
+    w1, w2 = _regulariser_weights(args) if regularise else (0.0, 0.0)
+    trainer = FastTrainer(model, volume, batch // world if world > 1 else batch, lr=lr, seed=seed, rank=rank,
+                          world_size=world, process_group=group, weight_l1=w1, weight_l2=w2)
+    sched = NeurcompDecay(trainer, lr, int(args['pass_decay']), float(args['lr_decay'])) if decay else None
+    seen = 0.0
+    passes = 0.0
+    per_step = trainer.batch * world
+    while int(passes) + 1 < max_pass:
+        prior = int(seen / n_voxels)
+        trainer.step()
+        seen += per_step
+        passes = seen / n_voxels
+        if sched is not None:
+            sched.update(prior, passes)
+        if verbose and trainer.steps_done % 500 == 0:
+            print('pass %.3f / %.1f  mse %.6f' % (passes, max_pass, trainer.last_loss()))
+        if int(passes) >= max_pass:
+            break
+    torch.cuda.synchronize()
+    return trainer
+
+
+def train_volume(args: dict, volume: Optional[torch.Tensor] = None, seed: int = 0, verbose: bool = False):
+    """Two-phase training + evaluation with the reference's schedule (training/training.py:184-243): 2/3 of the
+    passes with masks and regularisers, bake the masks, 1/3 fine-tuning at lr/10, strip the mask layers, reconstruct
+    the volume and report PSNR / compression ratio."""
+    from ..data.IndexDataset import IndexDataset, get_tensor
+    from ..model.model_utils import setup_model
+    from ..visualization.OutputToVTK import tiled_net_out
+
+    if volume is None:
+        volume = get_tensor(args['data'])
+    dataset = IndexDataset(volume, args['sample_size'])
+    device = torch.device('cuda')
+    volume_dev = volume.to(device)
+    model = setup_model(args['d_in'], args['n_hidden_size'], args['d_out'], args['n_layers'], args['embedding_type'],
+                        args['n_embedding_freq'], args['drop_type'], args['drop_momentum'], args['drop_threshold'],
+                        args['wavelet_filter'], args['grid_features'], args['grid_size'], args.get('checkpoint_path', ''))
+    model.to(device)
+    model.train()
+    t1 = solve_phase(model, volume_dev, dataset.n_voxels, args, args['max_pass'] * (2.0 / 3.0), args['lr'], True,
+                     seed=seed, verbose=verbose)
+    zeros = model.save_dropvalues_on_grid(device)
+    # phase 2: plain MSE, lr / 10, no decay (the reference's strategy object stays bound to the first optimizer)
+    t2 = solve_phase(model, volume_dev, dataset.n_voxels, args, args['max_pass'] * (1.0 / 3.0), args['lr'] / 10.0, False,
+                     seed=seed + 1, regularise=False, verbose=verbose)
+    model.remove_drop_layers(device)
+    psnr, l1, mse, rmse = tiled_net_out(dataset, model, True, gt_vol=volume_dev, evaluate=True, write_vols=False)
+    n_params = sum(p.numel() for n, p in model.named_parameters() if 'drop' not in n)
+    ratio = dataset.n_voxels / (n_params - float(zeros))
+    return dict(psnr=psnr, l1_diff=l1, mse=mse, rmse=rmse, num_parameters=n_params, num_zeros=float(zeros),
+                compression_ratio=ratio, steps=t1.steps_done + t2.steps_done, model=model)

@@ -632,8 +632,10 @@ def reconstruction_coords(vol_shape, tiled_res=32):
 
 
 def _torch_linspace_f32(start, end, steps):
-    """torch.linspace float32 semantics (ATen RangeFactories: step = (end-start)/(steps-1); first half computed
-    from start, second half from end)."""
+    """torch.linspace in float32, scalar form (ATen RangeFactories: step = (end-start)/(steps-1); first half
+    start + step*i, second half end - step*(n-1-i)).  ATen's vectorised kernel re-associates the additions, so the
+    reference's values can differ from this by one ulp; the golden fixture (reconstruct.npz axis0/1/2) holds the
+    reference's exact coordinates and the tests bound the difference."""
     start, end = np.float32(start), np.float32(end)
     if steps == 1:
         return np.asarray([start], dtype=np.float32)

@@ -307,15 +307,30 @@ def reconstruct_case():
     # reference eval forward is broken under torch>=2: route the one call through the patched forward
     model.eval()
     orig_forward = FGM.Feature_Grid_Model.forward
-    FGM.Feature_Grid_Model.forward = lambda self, t: ref_harness.patched_eval_forward(self, t)
+    seen_tiles = []
+
+    def recording_forward(self, t):
+        seen_tiles.append(t.detach().clone())
+        return ref_harness.patched_eval_forward(self, t)
+    FGM.Feature_Grid_Model.forward = recording_forward
     try:
         with torch.no_grad():
             full = field_from_net(ds, model, False, tiled_res=32)
     finally:
         FGM.Feature_Grid_Model.forward = orig_forward
+    # the coordinates the reference fed to the network, re-assembled in its tile order (x, then y, then z)
+    coords = torch.zeros(*shape, 3)
+    it = iter(seen_tiles)
+    for xb in range(0, shape[0], 32):
+        for yb in range(0, shape[1], 32):
+            for zb in range(0, shape[2], 32):
+                t = next(it)[0]
+                coords[xb:xb + t.shape[0], yb:yb + t.shape[1], zb:zb + t.shape[2]] = t
     psnr, l1, mse, rmse = calculate_deviation_statistics(full, vol)
     out = {'vol': npy(vol), 'full': npy(full), 'stats': np.asarray([psnr, l1, mse, rmse], dtype=np.float64),
-           'scales': npy(ds.scales)}
+           'scales': npy(ds.scales), 'axis0': npy(coords[:, 0, 0, 0]), 'axis1': npy(coords[0, :, 0, 1]),
+           'axis2': npy(coords[0, 0, :, 2])}
+    assert torch.equal(coords[..., 0], coords[:, :1, :1, 0].expand(*shape))
     for name, prm in model.state_dict().items():
         out['sd.' + name] = npy(prm)
     np.savez_compressed(os.path.join(HERE, 'reconstruct.npz'), **out)
@@ -385,6 +400,10 @@ def trajectory_case(tag, drop_type, steps=12):
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1:  # regenerate selected fixtures only: python make_golden.py reconstruct_case ...
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+        sys.exit(0)
     model_case('basic_db2_c16_g15', '', 'db2', 16, 15)
     model_case('basic_haar_c4_g16', '', 'haar', 4, 16, N=64)
     model_case('basic_db2_c8_g17_h64_l3_f3', '', 'db2', 8, 17, H=64, L=3, F=3, N=64)

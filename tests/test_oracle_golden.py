@@ -234,6 +234,9 @@ def test_reconstruction_coords_and_volume():
     g = load('reconstruct')
     vol = g['vol']
     coords = O.reconstruction_coords(vol.shape, 32)
+    for a, sl in enumerate(((slice(None), 0, 0), (0, slice(None), 0), (0, 0, slice(None)))):
+        mine = coords[sl + (a,)]
+        assert np.abs(mine - g['axis%d' % a]).max() <= 1.2e-7  # <= 1 ulp of the reference's linspace (see oracle doc)
     spec = O.Spec(4, 15, 32, 4, 2, 'db2', '')
     y = O.model_forward(state(g), spec, coords.reshape(-1, 3), training=False, clamp=True)
     full = y.reshape(vol.shape)
