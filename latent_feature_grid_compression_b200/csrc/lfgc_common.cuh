@@ -59,15 +59,40 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// SnakeAlt(x) = 0.5 x + sin^2 x and its derivative 0.5 + sin 2x (model/Feature_Grid_Model.py:12-13).
-// Precise path: sincosf (full-range reduction, <= 2 ulp) so that fp32 parity (1e-5 rel) holds for any argument.
+// Branch-free fp32 sin/cos: Cody-Waite reduction by pi/2 (three-term split, exact products through FMA) followed
+// by the classic minimax polynomials on [-pi/4, pi/4].  Max error ~1 ulp for |x| < 1e4 (beyond that the 3-term
+// reduction slowly loses bits; MLP pre-activations and embedding arguments are orders of magnitude smaller).
+// About 20 instructions for both values and no divergent slow path, unlike sincosf.
+__device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
+    const float n = rintf(x * 0.636619772f);  // x * 2/pi
+    float r = fmaf(n, -1.57079601e+00f, x);
+    r = fmaf(n, -3.13916473e-07f, r);
+    r = fmaf(n, -5.39030253e-15f, r);
+    const int q = __float2int_rn(n);
+    const float r2 = r * r;
+    float ps = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
+    ps = fmaf(ps, r2, -1.66666546e-1f);
+    ps = fmaf(ps * r2, r, r);                 // sin(r)
+    float pc = fmaf(r2, 2.44331571e-5f, -1.38873163e-3f);
+    pc = fmaf(pc, r2, 4.16666457e-2f);
+    pc = fmaf(pc, r2, -0.5f);
+    pc = fmaf(pc, r2, 1.0f);                  // cos(r)
+    const float sv = (q & 1) ? pc : ps;
+    const float cv = (q & 1) ? ps : pc;
+    s = (q & 2) ? -sv : sv;
+    c = ((q + 1) & 2) ? -cv : cv;
+}
+
+// SnakeAlt(x) = 0.5 x + sin^2 x and its derivative 0.5 + sin 2x = 0.5 + 2 sin x cos x
+// (model/Feature_Grid_Model.py:12-13).
 __device__ __forceinline__ float snake_precise(float z) {
-    float s = sinf(z);
+    float s, c;
+    sincos_cw(z, s, c);
     return fmaf(s, s, 0.5f * z);
 }
 __device__ __forceinline__ void snake_and_grad_precise(float z, float& h, float& g) {
     float s, c;
-    sincosf(z, &s, &c);
+    sincos_cw(z, s, c);
     h = fmaf(s, s, 0.5f * z);
     g = fmaf(2.0f * s, c, 0.5f);
 }

@@ -380,13 +380,25 @@ __global__ void __launch_bounds__(kThreads, 1) sample_backward_kernel(const __gr
     for (int e = threadIdx.x; e < A.pcount; e += blockDim.x) dst[e] = accum[e];
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nslices, int pcount,
-                                       float* __restrict__ grad, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pcount) return;
+// grad[i] (+)= sum over CTA slices; block = 32 parameters x 8 slice lanes (fixed summation order: deterministic)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nslices,
+                                                              int pcount, float* __restrict__ grad, int accumulate) {
+    __shared__ float red[8][33];
+    const int px = threadIdx.x & 31, sy = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + px;
     float s = 0.0f;
-    for (int b = 0; b < nslices; ++b) s += partial[(size_t)b * pcount + i];
-    grad[i] = accumulate ? grad[i] + s : s;
+    if (i < pcount) {
+#pragma unroll 4
+        for (int b = sy; b < nslices; b += 8) s += partial[(size_t)b * pcount + i];
+    }
+    red[sy][px] = s;
+    __syncthreads();
+    if (sy == 0 && i < pcount) {
+        float t = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += red[r][px];
+        grad[i] = accumulate ? grad[i] + t : t;
+    }
 }
 
 template <int HP, int FUSED>
@@ -408,7 +420,7 @@ static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* wo
     A.partial = reinterpret_cast<float*>(workspace);
     kern<<<(unsigned)grid, kThreads, smem, st>>>(A);
     LFGC_LAUNCH_OK();
-    reduce_partials_kernel<<<(A.pcount + 127) / 128, 128, 0, st>>>(A.partial, (int)grid, A.pcount, grad_mlp, accumulate);
+    reduce_partials_kernel<<<(A.pcount + 31) / 32, 256, 0, st>>>(A.partial, (int)grid, A.pcount, grad_mlp, accumulate);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }

@@ -66,13 +66,13 @@ __device__ __forceinline__ void stage_inputs(const SampleParams& P, const float*
     for (int f = 0; f < P.F; ++f) {
         const float om = P.omega[f];
         float s, c;
-        sincosf(__fmul_rn(cx, om), &s, &c);  // the argument is rounded to fp32 first (Feature_Embedding.py:33)
+        sincos_cw(__fmul_rn(cx, om), s, c);  // the argument is rounded to fp32 first (Feature_Embedding.py:33)
         X[(3 + 6 * f + 0) * S + col] = s;
         X[(3 + 6 * f + 3) * S + col] = c;
-        sincosf(__fmul_rn(cy, om), &s, &c);
+        sincos_cw(__fmul_rn(cy, om), s, c);
         X[(3 + 6 * f + 1) * S + col] = s;
         X[(3 + 6 * f + 4) * S + col] = c;
-        sincosf(__fmul_rn(cz, om), &s, &c);
+        sincos_cw(__fmul_rn(cz, om), s, c);
         X[(3 + 6 * f + 2) * S + col] = s;
         X[(3 + 6 * f + 5) * S + col] = c;
     }

@@ -80,13 +80,16 @@ __global__ void smallify_ema_kernel(const float* __restrict__ betas, float* __re
 // ---------------------------------------------------------------------------------------------------------------
 // one synthesis level
 // ---------------------------------------------------------------------------------------------------------------
+// Layouts: coefficient tensors (the nn.Parameters) stay in the reference layout, channels-first (C,[7,]d0,d1,d2);
+// everything the kernels produce (intermediate low-pass volumes, the final grid, their gradients) is channels-last
+// with the channel as the fastest thread index, so that neighbouring lanes read/write neighbouring addresses.
 struct LevelArgs {
-    const float* low;    // (C, d0, d1, d2)   running low-pass, channels-first
+    const float* low;    // coarsest level: coeff[0] (C,d0,d1,d2) channels-first; otherwise (d0,d1,d2,C) channels-last
     const float* high;   // (C, 7, d0, d1, d2)
     const float* mlow;   // (d0, d1, d2) or null: multiplier of the low-pass input (coarsest level only)
     const float* mhigh;  // (7, d0, d1, d2) or null
-    float* out;          // channels-first (C, t0, t1, t2) or channels-last (t0, t1, t2, Cp)
-    int C, Cp, out_cl;
+    float* out;          // (t0, t1, t2, Cs) channels-last, Cs = Cp for the final grid, C otherwise
+    int C, Cs, low_cl;
     int d[3], t[3], off[3];
     int ntaps;
     float lo[LFGC_MAX_TAPS], hi[LFGC_MAX_TAPS];
@@ -96,18 +99,10 @@ struct LevelArgs {
 // (Torch_Wavelet_Transform.py:39-57 outer-product filter bank; :100-104 transposed conv + crop).
 __global__ void idwt_level_kernel(LevelArgs A) {
     const int64_t nvox = (int64_t)A.t[0] * A.t[1] * A.t[2];
-    const int cs = A.out_cl ? A.Cp : A.C;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nvox * cs) return;
-    int c;
-    int64_t p;
-    if (A.out_cl) {
-        c = (int)(idx % cs);
-        p = idx / cs;
-    } else {
-        p = idx % nvox;
-        c = (int)(idx / nvox);
-    }
+    if (idx >= nvox * A.Cs) return;
+    const int c = (int)(idx % A.Cs);
+    const int64_t p = idx / A.Cs;
     if (c >= A.C) {
         A.out[idx] = 0.0f;  // zero pad channels
         return;
@@ -118,7 +113,6 @@ __global__ void idwt_level_kernel(LevelArgs A) {
     const int oz = pz + A.off[0], oy = py + A.off[1], ox = px + A.off[2];
     const int nt = A.ntaps;
     const int64_t dvol = (int64_t)A.d[0] * A.d[1] * A.d[2];
-    const float* lowc = A.low + (int64_t)c * dvol;
     const float* highc = A.high + (int64_t)c * 7 * dvol;
 
     auto lo_i = [&](int o) { int v = o - nt + 1; return v <= 0 ? 0 : (v + 1) >> 1; };
@@ -133,7 +127,7 @@ __global__ void idwt_level_kernel(LevelArgs A) {
                 const int tx = ox - 2 * ix;
                 const float wx[2] = {A.lo[tx], A.hi[tx]};
                 const int64_t b = ((int64_t)iz * A.d[1] + iy) * A.d[2] + ix;
-                float v0 = lowc[b];
+                float v0 = A.low_cl ? A.low[b * A.C + c] : A.low[(int64_t)c * dvol + b];
                 if (A.mlow) v0 *= A.mlow[b];
                 acc = fmaf(v0, wz[0] * wy[0] * wx[0], acc);
 #pragma unroll
@@ -164,31 +158,34 @@ __global__ void copy_to_channels_last_kernel(const float* __restrict__ src, cons
 }
 
 struct LevelBwdArgs {
-    const float* gout;     // d out: channels-first (C,t..) or channels-last (t.., Cp)
-    int gout_cl;
+    const float* gout;     // d out, channels-last (t0,t1,t2,Cs)
+    int Cs;
     const float* c_low;    // coefficient tensors of this level (needed for d mult); c_low only when low_is_coeff
     const float* c_high;
     const float* gm_low;   // gradient multipliers (null = 1)
     const float* gm_high;
-    float* g_low;          // low_is_coeff ? grad of coeff[0] (C,d..) : scratch d(running low-pass) (C,d..)
+    float* g_low;          // low_is_coeff ? grad of coeff[0] (C,d..) channels-first : scratch (d..,C) channels-last
     float* g_high;         // grad of coeff[l] (C,7,d..)
-    float* gmult_low;      // d mult (d..) or null
+    float* gmult_low;      // d mult (d..) or null   (accumulated with atomics: zeroed by the host when !accumulate)
     float* gmult_high;     // (7,d..) or null
     int low_is_coeff;
     int accumulate;
-    int C, Cp;
+    int C;
     int d[3], t[3], off[3];
     int ntaps;
     float lo[LFGC_MAX_TAPS], hi[LFGC_MAX_TAPS];
 };
 
-// one thread per (sub-band k, iz, iy, ix); loops over channels so that d mult = sum_c coeff * g is thread-local
+// One thread per (sub-band k, position b, channel c), channel fastest.  d mult[k][b] = sum_c coeff * g is reduced
+// with warp shuffles when C divides the warp, then one atomic per (k, b).
 __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
     const int64_t dvol = (int64_t)A.d[0] * A.d[1] * A.d[2];
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 8 * dvol) return;
-    const int k = (int)(idx / dvol);
-    const int64_t b = idx % dvol;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = idx < 8 * dvol * A.C;
+    const int c = live ? (int)(idx % A.C) : 0;
+    const int64_t kb = live ? idx / A.C : 0;
+    const int k = (int)(kb / dvol);
+    const int64_t b = kb % dvol;
     const int ix = (int)(b % A.d[2]);
     const int iy = (int)((b / A.d[2]) % A.d[1]);
     const int iz = (int)(b / ((int64_t)A.d[2] * A.d[1]));
@@ -196,11 +193,9 @@ __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
     const float* fy = ((k >> 1) & 1) ? A.hi : A.lo;
     const float* fx = (k & 1) ? A.hi : A.lo;
     const int nt = A.ntaps;
-    const int64_t tvol = (int64_t)A.t[0] * A.t[1] * A.t[2];
 
-    float msum = 0.0f;
-    for (int c = 0; c < A.C; ++c) {
-        float g = 0.0f;
+    float g = 0.0f;
+    if (live) {
         for (int tz = 0; tz < nt; ++tz) {
             const int pz = 2 * iz + tz - A.off[0];
             if (pz < 0 || pz >= A.t[0]) continue;
@@ -212,32 +207,38 @@ __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
                     const int px = 2 * ix + tx - A.off[2];
                     if (px < 0 || px >= A.t[2]) continue;
                     const int64_t p = ((int64_t)pz * A.t[1] + py) * A.t[2] + px;
-                    const float gv = A.gout_cl ? A.gout[p * A.Cp + c] : A.gout[(int64_t)c * tvol + p];
-                    g = fmaf(gv, wzy * fx[tx], g);
+                    g = fmaf(A.gout[p * A.Cs + c], wzy * fx[tx], g);
                 }
             }
         }
+    }
+    float contrib = 0.0f;
+    float* gm = nullptr;
+    if (live) {
         if (k == 0) {
             if (A.low_is_coeff) {
                 const int64_t o = (int64_t)c * dvol + b;
-                msum = fmaf(A.c_low[o], g, msum);
+                if (A.gmult_low) { contrib = A.c_low[o] * g; gm = A.gmult_low + b; }
                 const float v = A.gm_low ? g * A.gm_low[b] : g;
                 A.g_low[o] = A.accumulate ? A.g_low[o] + v : v;
             } else {
-                A.g_low[(int64_t)c * dvol + b] = g;
+                A.g_low[b * A.C + c] = g;
             }
         } else {
             const int64_t o = ((int64_t)c * 7 + (k - 1)) * dvol + b;
-            msum = fmaf(A.c_high[o], g, msum);
+            if (A.gmult_high) { contrib = A.c_high[o] * g; gm = A.gmult_high + (int64_t)(k - 1) * dvol + b; }
             const float v = A.gm_high ? g * A.gm_high[(int64_t)(k - 1) * dvol + b] : g;
             A.g_high[o] = A.accumulate ? A.g_high[o] + v : v;
         }
     }
-    if (k == 0) {
-        if (A.low_is_coeff && A.gmult_low) A.gmult_low[b] = A.accumulate ? A.gmult_low[b] + msum : msum;
-    } else if (A.gmult_high) {
-        const int64_t o = (int64_t)(k - 1) * dvol + b;
-        A.gmult_high[o] = A.accumulate ? A.gmult_high[o] + msum : msum;
+    if (A.gmult_low == nullptr && A.gmult_high == nullptr) return;  // uniform across the grid
+    const int C = A.C;
+    if (C <= 32 && (32 % C) == 0 && (blockDim.x % 32) == 0) {
+        // a warp holds 32/C complete channel groups: segmented butterfly reduction
+        for (int m = C >> 1; m >= 1; m >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, m);
+        if (gm && c == 0) atomicAdd(gm, contrib);
+    } else if (gm) {
+        atomicAdd(gm, contrib);
     }
 }
 
@@ -406,9 +407,9 @@ extern "C" int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* c
         A.mhigh = mult ? mult[l] : nullptr;
         const bool last = (l == w->n_coeff - 1);
         A.out = last ? grid_cl : buf[l & 1];
-        A.out_cl = last ? 1 : 0;
+        A.low_cl = (l == 1) ? 0 : 1;
         A.C = w->C;
-        A.Cp = Cp;
+        A.Cs = last ? Cp : w->C;
         A.ntaps = w->n_taps;
         for (int a = 0; a < 3; ++a) {
             A.d[a] = w->dims[l][a];
@@ -419,7 +420,7 @@ extern "C" int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* c
             A.lo[i] = w->rec_lo[i];
             A.hi[i] = w->rec_hi[i];
         }
-        const int64_t total = (int64_t)A.t[0] * A.t[1] * A.t[2] * (last ? Cp : A.C);
+        const int64_t total = (int64_t)A.t[0] * A.t[1] * A.t[2] * A.Cs;
         idwt_level_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(A);
         LFGC_LAUNCH_OK();
         low = A.out;
@@ -450,7 +451,7 @@ extern "C" int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_gri
     for (int l = w->n_coeff - 1; l >= 1; --l) {
         LevelBwdArgs A;
         A.gout = gout;
-        A.gout_cl = (l == w->n_coeff - 1) ? 1 : 0;
+        A.Cs = (l == w->n_coeff - 1) ? Cp : w->C;
         A.low_is_coeff = (l == 1) ? 1 : 0;
         A.c_low = coeff[0];
         A.c_high = coeff[l];
@@ -462,7 +463,6 @@ extern "C" int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_gri
         A.gmult_high = grad_mult ? grad_mult[l] : nullptr;
         A.accumulate = accumulate;
         A.C = w->C;
-        A.Cp = Cp;
         A.ntaps = w->n_taps;
         for (int a = 0; a < 3; ++a) {
             A.d[a] = w->dims[l][a];
@@ -474,8 +474,13 @@ extern "C" int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_gri
             A.hi[i] = w->rec_hi[i];
         }
         if (!A.g_low || !A.g_high) return fail(LFGC_E_INVALID, "decode_bwd: grad_coeff[%d] null", l);
-        const int64_t total = 8 * (int64_t)A.d[0] * A.d[1] * A.d[2];
-        idwt_level_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(A);
+        const int64_t dvol = (int64_t)A.d[0] * A.d[1] * A.d[2];
+        if (!accumulate) {  // d mult is accumulated with atomics
+            if (A.gmult_low) LFGC_CUDA_OK(cudaMemsetAsync(A.gmult_low, 0, dvol * sizeof(float), st));
+            if (A.gmult_high) LFGC_CUDA_OK(cudaMemsetAsync(A.gmult_high, 0, 7 * dvol * sizeof(float), st));
+        }
+        const int64_t total = 8 * dvol * A.C;
+        idwt_level_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
         LFGC_LAUNCH_OK();
         gout = A.g_low;
     }
