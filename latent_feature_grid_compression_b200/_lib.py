@@ -7,7 +7,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from .build import LIB_PATH
+from .build import LIB_PATH as _DEFAULT_LIB_PATH
+
+LIB_PATH = os.environ.get('LFGC_LIB', _DEFAULT_LIB_PATH)  # debug builds only; the shipped path is the in-tree library
 
 MAX_LEVELS = 12
 MAX_TAPS = 16

@@ -15,33 +15,11 @@
 //                         the 128 samples of the tile; accumulated in shared memory across the persistent loop
 // At the end each CTA writes its accumulators to a per-CTA slice of the workspace and a second tiny kernel sums the
 // slices (deterministic, no atomics on the MLP gradient).
-#include "sample_common.cuh"
+#include "sample_backward.cuh"
 
 namespace lfgc {
 
 constexpr int kS = 132;  // row stride (floats) of the activation rows
-
-struct BwdArgs {
-    SampleParams P;
-    // sample source
-    const float* coords;        // compat mode: [n][3]
-    const float* grad_out;      // compat mode: [n]
-    const float* volume;        // fused mode
-    int R[3];
-    float max_idx[3], scales[3];
-    unsigned long long n_voxels;
-    uint64_t seed, sample_offset, step_stride;
-    const int32_t* step_dev;
-    const int64_t* explicit_idx;
-    float loss_scale2;          // 2 * loss_scale
-    float* loss_sum;
-    int64_t n;
-    const float* grid;
-    const float* mlp;
-    float* grad_grid;
-    float* partial;             // [gridDim.x][pcount]
-    int pcount;                 // packed MLP parameter count
-};
 
 struct BwdLayout {
     int Wt, bias, Wf, bf, Wb, W0f, acc, X, Hs, Gs, DF, AUX, total;
@@ -401,9 +379,18 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     }
 }
 
+void launch_reduce_partials(const float* partial, int nslices, int pcount, float* grad, int accumulate,
+                            cudaStream_t st) {
+    reduce_partials_kernel<<<(pcount + 31) / 32, 256, 0, st>>>(partial, nslices, pcount, grad, accumulate);
+}
+
 template <int HP, int FUSED>
 static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
                            cudaStream_t st) {
+    {
+        const int rc = launch_backward_v2(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
+        if (rc != 1) return rc;
+    }
     const BwdLayout Lo = bwd_layout<HP>(A.P, A.pcount);
     const size_t smem = (size_t)Lo.total * sizeof(float);
     if ((int)smem > max_smem_optin())
@@ -420,7 +407,7 @@ static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* wo
     A.partial = reinterpret_cast<float*>(workspace);
     kern<<<(unsigned)grid, kThreads, smem, st>>>(A);
     LFGC_LAUNCH_OK();
-    reduce_partials_kernel<<<(A.pcount + 31) / 32, 256, 0, st>>>(A.partial, (int)grid, A.pcount, grad_mlp, accumulate);
+    launch_reduce_partials(A.partial, (int)grid, A.pcount, grad_mlp, accumulate, st);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }
@@ -434,7 +421,10 @@ extern "C" size_t lfgc_backward_workspace_bytes(const lfgc_model_desc* m) {
     const int64_t p = lfgc_mlp_param_count(m);
     int sms = sm_count();
     if (sms <= 0) sms = 148;  // no device visible (build container): size for a B200
-    return (size_t)sms * (size_t)p * sizeof(float);
+    size_t fl = (size_t)sms * (size_t)p;
+    const size_t v2 = backward_v2_workspace_floats((int)p, sms);
+    if (v2 > fl) fl = v2;
+    return fl * sizeof(float);
 }
 
 static int common_checks(const lfgc_model_desc* m, int64_t n, const float* grid_cl, const float* mlp,

@@ -1,0 +1,38 @@
+// Argument block shared by the generic (v1) and the wide (v2) fused backward kernels.
+#pragma once
+#include "sample_common.cuh"
+
+namespace lfgc {
+
+struct BwdArgs {
+    SampleParams P;
+    // sample source
+    const float* coords;        // compat mode: [n][3]
+    const float* grad_out;      // compat mode: [n]
+    const float* volume;        // fused mode
+    int R[3];
+    float max_idx[3], scales[3];
+    unsigned long long n_voxels;
+    uint64_t seed, sample_offset, step_stride;
+    const int32_t* step_dev;
+    const int64_t* explicit_idx;
+    float loss_scale2;          // 2 * loss_scale
+    float* loss_sum;
+    int64_t n;
+    const float* grid;
+    const float* mlp;
+    float* grad_grid;
+    float* partial;             // [gridDim.x][pcount]
+    int pcount;                 // packed MLP parameter count
+};
+
+// Tries the wide kernel (v2: 8-12 warps per CTA, S'(z) in registers, packed FFMA2).  Returns LFGC_OK after
+// launching, or 1 when the configuration is not covered (the caller then uses the generic kernel), or an error.
+int launch_backward_v2(BwdArgs& A, int fused, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st);
+size_t backward_v2_workspace_floats(int pcount, int sms);
+
+// grad[i] (+)= sum_b partial[b][i]   (fixed order: deterministic)
+void launch_reduce_partials(const float* partial, int nslices, int pcount, float* grad, int accumulate, cudaStream_t st);
+
+}  // namespace lfgc
