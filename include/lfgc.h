@@ -124,9 +124,11 @@ size_t lfgc_decode_scratch_bytes(const lfgc_wavelet_desc* w);
 
 /* grid_cl[z][y][x][Cp] = synthesis of (coeff[l] * mult[l]); mult[l] may be NULL (identity).
  * coeff / mult are HOST arrays of n_coeff DEVICE pointers.  Pad channels [C, Cp) are written as zero.
- * With n_coeff == 1 this is a masked NCDHW -> channels-last transpose. */
+ * With n_coeff == 1 this is a masked NCDHW -> channels-last transpose.
+ * also_zero (nullable): a buffer shaped like grid_cl that is cleared in the same pass -- the gradient accumulator
+ * the coming lfgc_backward / lfgc_train_step scatters into (saves a separate memset launch per step). */
 int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* coeff, const float* const* mult,
-                    float* scratch, float* grid_cl, int Cp, void* stream);
+                    float* scratch, float* grid_cl, int Cp, float* also_zero, void* stream);
 
 /* Adjoint of lfgc_decode_fwd (autograd of conv_transpose3d + mul, training/training.py:137).
  * grad_coeff[l] (+)= d(coeff*mult) * gmul[l]  where gmul[l] is the gradient multiplier (aux of the mask; NULL = 1)
@@ -168,7 +170,7 @@ int lfgc_backward(const lfgc_model_desc* m, const float* coords, int64_t n, cons
  *   + *step_dev * step_stride); step_dev (nullable) is a DEVICE int32 step counter (the one lfgc_adam increments),
  *   which lets a captured CUDA graph draw fresh samples on every replay
  *   loss_scale: d(loss)/d(pred) = loss_scale * 2 * (pred - gt); pass 1/N_global for the mean over the global batch
- *   loss_sum[0] += sum (pred-gt)^2 over this call's samples (fp32 atomic, caller zeroes it)
+ *   loss_sum[0] = sum (pred-gt)^2 over this call's samples (overwritten; summed with the MLP gradient partials)
  *   explicit_idx (nullable, int64[n]): use these flat voxel indices instead of Philox (parity tests) */
 int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
                     uint64_t seed, uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
@@ -209,8 +211,9 @@ int lfgc_deviation_stats(const float* pred, const float* gt, int64_t n, double* 
 
 /* ---- optimiser ----------------------------------------------------------------------------------------------- */
 
-/* torch.optim.Adam (training/training.py:199,232) on flat buffers, one launch.  step_count is a DEVICE int32
- * holding the number of steps taken so far (incremented by the kernel, so the call is graph-replayable);
+/* torch.optim.Adam (training/training.py:199,232) on flat buffers, one launch.  step_count is a DEVICE int32[2]:
+ * [0] = number of steps taken so far (incremented by the kernel, so the call is graph-replayable; this is the
+ * counter lfgc_train_step reads), [1] = scratch ticket counter that must be zero-initialised;
  * lr is a DEVICE float (the host decay strategies write it).  grad_scale multiplies the gradient first
  * (1/world for data parallel means).  l2[n] (nullable) adds 2*l2_weight*p (the Sum coeff^2 regulariser of
  * SmallifyLoss / VariationalDropoutLoss) and l1 similarly adds l1_weight*sign(p) where the flags say so. */

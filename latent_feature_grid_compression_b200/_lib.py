@@ -49,7 +49,7 @@ _SIGNATURES = {
     'lfgc_dwt_level': (C.c_int, [_f, C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_float),
                                  C.POINTER(C.c_float), _f, C.POINTER(C.c_int32), _f]),
     'lfgc_decode_scratch_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
-    'lfgc_decode_fwd': (C.c_int, [C.POINTER(WaveletDesc), C.POINTER(_f), C.POINTER(_f), _f, _f, C.c_int, _f]),
+    'lfgc_decode_fwd': (C.c_int, [C.POINTER(WaveletDesc), C.POINTER(_f), C.POINTER(_f), _f, _f, C.c_int, _f, _f]),
     'lfgc_decode_bwd': (C.c_int, [C.POINTER(WaveletDesc), _f, C.c_int, C.POINTER(_f), C.POINTER(_f), _f,
                                   C.POINTER(_f), C.POINTER(_f), C.c_int, _f]),
     'lfgc_mlp_param_count': (_i64, [C.POINTER(ModelDesc)]),

@@ -4,14 +4,17 @@
 
 namespace lfgc {
 
-__global__ void adam_tick_kernel(int32_t* step) { *step += 1; }
-
+// step_ptr[0] = optimiser steps taken so far, step_ptr[1] = ticket counter (must start at 0).  Every block reads the
+// step before it takes its ticket and the block drawing the last ticket publishes step + 1, so the whole update is
+// one launch and stays correct under CUDA-graph replay.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, const float* __restrict__ lr_ptr,
-                            const int32_t* __restrict__ step_ptr, float b1, float b2, float eps, float gscale) {
+                            int32_t* __restrict__ step_ptr, float b1, float b2, float eps, float gscale) {
     __shared__ float s_step_size, s_bc2_sqrt;
+    __shared__ int s_step;
     if (threadIdx.x == 0) {
-        const int step = *step_ptr;  // already incremented by adam_tick_kernel
+        const int step = *reinterpret_cast<volatile int32_t*>(step_ptr) + 1;
+        s_step = step;
         const double bc1 = 1.0 - pow((double)b1, (double)step);
         const double bc2 = 1.0 - pow((double)b2, (double)step);
         s_step_size = (float)((double)*lr_ptr / bc1);
@@ -19,15 +22,26 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float gi = g[i] * gscale;
-    float mi = m[i], vi = v[i];
-    mi = mi + (gi - mi) * (1.0f - b1);              // exp_avg.lerp_(grad, 1 - beta1)
-    vi = vi * b2 + (1.0f - b2) * gi * gi;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-    const float denom = sqrtf(vi) / s_bc2_sqrt + eps;
-    p[i] = p[i] - s_step_size * (mi / denom);       // param.addcdiv_(exp_avg, denom, value=-step_size)
-    m[i] = mi;
-    v[i] = vi;
+    if (i < n) {
+        const float gi = g[i] * gscale;
+        float mi = m[i], vi = v[i];
+        mi = mi + (gi - mi) * (1.0f - b1);              // exp_avg.lerp_(grad, 1 - beta1)
+        vi = vi * b2 + (1.0f - b2) * gi * gi;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        const float denom = sqrtf(vi) / s_bc2_sqrt + eps;
+        p[i] = p[i] - s_step_size * (mi / denom);       // param.addcdiv_(exp_avg, denom, value=-step_size)
+        m[i] = mi;
+        v[i] = vi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(step_ptr + 1, 1);
+        if (ticket == (int)gridDim.x - 1) {
+            step_ptr[1] = 0;
+            __threadfence();
+            step_ptr[0] = s_step;
+        }
+    }
 }
 
 __global__ void add_l2_grad_kernel(float* __restrict__ g, const float* __restrict__ p, int64_t n, float w2) {
@@ -50,10 +64,8 @@ extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n
                          float beta1, float beta2, float eps, float grad_scale, void* stream) {
     if (!p || !g || !m || !v || !lr || !step_count || n < 0) return fail(LFGC_E_INVALID, "adam: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    adam_tick_kernel<<<1, 1, 0, st>>>(step_count);
-    LFGC_LAUNCH_OK();
-    if (n == 0) return LFGC_OK;
-    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale);
+    const int64_t blocks = n == 0 ? 1 : (n + 255) / 256;
+    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }

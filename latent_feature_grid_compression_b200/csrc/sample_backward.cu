@@ -35,7 +35,7 @@ __host__ __device__ inline BwdLayout bwd_layout(const SampleParams& P, int pcoun
     o.bf = p;   p += 4;
     o.Wb = p;   p += (P.L - 1) * HP * HP;
     o.W0f = p;  p += HP * P.Cp;
-    o.acc = p;  p += (pcount + 3) & ~3;
+    o.acc = p;  p += (pcount + 4) & ~3;    // + 1: loss partial
     o.X = p;    p += P.in0p * kS;
     o.Hs = p;   p += (P.L - 1) * HP * kS;
     o.Gs = p;   p += P.L * HP * kS;
@@ -97,19 +97,8 @@ __global__ void __launch_bounds__(kThreads, 1) sample_backward_kernel(const __gr
     const int H = P.H, in0 = P.in0, L = P.L;
     load_fwd_weights<HP>(P, A.mlp, Wt, bias, Wf, smem + Lo.bf);
     // backward layout: Wb_l[j][k] = W_l[j][k] (l >= 1), W0f[j][c] = W_0[j][3+6F+c]
-    for (int l = 1; l < L; ++l) {
-        const float* W = A.mlp + mlp_w_off(l, in0, H);
-        float* dst = Wb + (l - 1) * HP * HP;
-        for (int e = threadIdx.x; e < HP * HP; e += blockDim.x) {
-            const int j = e / HP, k = e % HP;
-            dst[e] = (j < H && k < H) ? __ldg(W + j * H + k) : 0.0f;
-        }
-    }
-    for (int e = threadIdx.x; e < HP * P.Cp; e += blockDim.x) {
-        const int j = e / P.Cp, c = e % P.Cp;
-        W0f[e] = (j < H && c < P.C) ? __ldg(A.mlp + j * in0 + 3 + 6 * P.F + c) : 0.0f;
-    }
-    for (int e = threadIdx.x; e < ((A.pcount + 3) & ~3); e += blockDim.x) accum[e] = 0.0f;
+    load_bwd_weights<HP>(P, A.mlp, Wb, W0f);
+    for (int e = threadIdx.x; e < ((A.pcount + 4) & ~3); e += blockDim.x) accum[e] = 0.0f;
     __syncthreads();
     const float bf = smem[Lo.bf];
 
@@ -350,38 +339,42 @@ __global__ void __launch_bounds__(kThreads, 1) sample_backward_kernel(const __gr
         }
         if (lane == 0) {
             atomicAdd(accum + mlp_wf_off(L, in0, H) + H, v);
-            if (FUSED && A.loss_sum) atomicAdd(A.loss_sum, e);
+            if (FUSED) atomicAdd(accum + A.pcount, e);
         }
     }
     __syncthreads();
-    float* dst = A.partial + (size_t)blockIdx.x * A.pcount;
-    for (int e = threadIdx.x; e < A.pcount; e += blockDim.x) dst[e] = accum[e];
+    float* dst = A.partial + (size_t)blockIdx.x * A.pstride;
+    for (int e = threadIdx.x; e < A.pstride; e += blockDim.x) dst[e] = accum[e];
 }
 
-// grad[i] (+)= sum over CTA slices; block = 32 parameters x 8 slice lanes (fixed summation order: deterministic)
+// grad[i] (+)= sum over CTA slices; block = 32 entries x 8 slice lanes (fixed summation order: deterministic).
+// Entry pcount of every slice is the loss partial; its sum goes to loss_out (overwritten).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nslices,
-                                                              int pcount, float* __restrict__ grad, int accumulate) {
+                                                              int pstride, int pcount, float* __restrict__ grad,
+                                                              int accumulate, float* __restrict__ loss_out) {
     __shared__ float red[8][33];
     const int px = threadIdx.x & 31, sy = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + px;
     float s = 0.0f;
-    if (i < pcount) {
+    if (i <= pcount) {
 #pragma unroll 4
-        for (int b = sy; b < nslices; b += 8) s += partial[(size_t)b * pcount + i];
+        for (int b = sy; b < nslices; b += 8) s += partial[(size_t)b * pstride + i];
     }
     red[sy][px] = s;
     __syncthreads();
-    if (sy == 0 && i < pcount) {
+    if (sy == 0 && i <= pcount) {
         float t = 0.0f;
 #pragma unroll
         for (int r = 0; r < 8; ++r) t += red[r][px];
-        grad[i] = accumulate ? grad[i] + t : t;
+        if (i < pcount) grad[i] = accumulate ? grad[i] + t : t;
+        else if (loss_out) loss_out[0] = t;
     }
 }
 
-void launch_reduce_partials(const float* partial, int nslices, int pcount, float* grad, int accumulate,
-                            cudaStream_t st) {
-    reduce_partials_kernel<<<(pcount + 31) / 32, 256, 0, st>>>(partial, nslices, pcount, grad, accumulate);
+void launch_reduce_partials(const float* partial, int nslices, int pstride, int pcount, float* grad, int accumulate,
+                            float* loss_out, cudaStream_t st) {
+    reduce_partials_kernel<<<(pcount + 1 + 31) / 32, 256, 0, st>>>(partial, nslices, pstride, pcount, grad, accumulate,
+                                                                  loss_out);
 }
 
 template <int HP, int FUSED>
@@ -401,13 +394,13 @@ static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* wo
     const int64_t ntiles = (A.n + kTile - 1) / kTile;
     int64_t grid = sm_count();
     if (grid > ntiles) grid = ntiles;
-    if (workspace_bytes < (size_t)grid * A.pcount * sizeof(float))
+    if (workspace_bytes < (size_t)grid * A.pstride * sizeof(float))
         return fail(LFGC_E_WORKSPACE, "backward workspace too small: %zu < %zu", workspace_bytes,
-                    (size_t)grid * A.pcount * sizeof(float));
+                    (size_t)grid * A.pstride * sizeof(float));
     A.partial = reinterpret_cast<float*>(workspace);
     kern<<<(unsigned)grid, kThreads, smem, st>>>(A);
     LFGC_LAUNCH_OK();
-    launch_reduce_partials(A.partial, (int)grid, A.pcount, grad_mlp, accumulate, st);
+    launch_reduce_partials(A.partial, (int)grid, A.pstride, A.pcount, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }
@@ -421,7 +414,7 @@ extern "C" size_t lfgc_backward_workspace_bytes(const lfgc_model_desc* m) {
     const int64_t p = lfgc_mlp_param_count(m);
     int sms = sm_count();
     if (sms <= 0) sms = 148;  // no device visible (build container): size for a B200
-    size_t fl = (size_t)sms * (size_t)p;
+    size_t fl = (size_t)sms * (size_t)(p + 1);
     const size_t v2 = backward_v2_workspace_floats((int)p, sms);
     if (v2 > fl) fl = v2;
     return fl * sizeof(float);
@@ -447,6 +440,7 @@ extern "C" int lfgc_backward(const lfgc_model_desc* m, const float* coords, int6
     if (grad_coords) return fail(LFGC_E_UNSUPPORTED, "coordinate gradients are not produced (the reference never reads them)");
     if (n > 0 && (!coords || !grad_out)) return fail(LFGC_E_INVALID, "backward: coords/grad_out null");
     A.pcount = (int)lfgc_mlp_param_count(m);
+    A.pstride = A.pcount + 1;
     if (n == 0) {
         if (!accumulate_mlp) LFGC_CUDA_OK(cudaMemsetAsync(grad_mlp, 0, A.pcount * sizeof(float), (cudaStream_t)stream));
         return LFGC_OK;
@@ -481,6 +475,7 @@ extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, co
     if (rc) return rc;
     if (!volume || !R || R[0] < 1 || R[1] < 1 || R[2] < 1) return fail(LFGC_E_INVALID, "train_step: bad volume");
     A.pcount = (int)lfgc_mlp_param_count(m);
+    A.pstride = A.pcount + 1;
     if (n == 0) {
         if (!accumulate_mlp) LFGC_CUDA_OK(cudaMemsetAsync(grad_mlp, 0, A.pcount * sizeof(float), (cudaStream_t)stream));
         return LFGC_OK;

@@ -24,6 +24,7 @@ struct BwdArgs {
     float* grad_grid;
     float* partial;             // [gridDim.x][pcount]
     int pcount;                 // packed MLP parameter count
+    int pstride;                // floats per workspace slice: pcount + 1 (the last entry carries the loss partial)
 };
 
 // Tries the wide kernel (v2: 8-12 warps per CTA, S'(z) in registers, packed FFMA2).  Returns LFGC_OK after
@@ -32,7 +33,8 @@ int launch_backward_v2(BwdArgs& A, int fused, float* grad_mlp, int accumulate, v
                        cudaStream_t st);
 size_t backward_v2_workspace_floats(int pcount, int sms);
 
-// grad[i] (+)= sum_b partial[b][i]   (fixed order: deterministic)
-void launch_reduce_partials(const float* partial, int nslices, int pcount, float* grad, int accumulate, cudaStream_t st);
+// grad[i] (+)= sum_b partial[b][i] for i < pcount; loss_out[0] = sum_b partial[b][pcount] (fixed order: deterministic)
+void launch_reduce_partials(const float* partial, int nslices, int pstride, int pcount, float* grad, int accumulate,
+                            float* loss_out, cudaStream_t st);
 
 }  // namespace lfgc

@@ -233,18 +233,7 @@ __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_co
 
     const int H = P.H, in0 = P.in0, L = P.L;
     load_fwd_weights<HP>(P, A.mlp, Wt, bias, Wf, smem + Lo.bf);
-    for (int l = 1; l < L; ++l) {
-        const float* W = A.mlp + mlp_w_off(l, in0, H);
-        float* dst = Wb + (l - 1) * HP * HP;
-        for (int e = threadIdx.x; e < HP * HP; e += blockDim.x) {
-            const int j = e / HP, k = e % HP;
-            dst[e] = (j < H && k < H) ? __ldg(W + j * H + k) : 0.0f;
-        }
-    }
-    for (int e = threadIdx.x; e < HP * P.Cp; e += blockDim.x) {
-        const int j = e / P.Cp, c = e % P.Cp;
-        W0f[e] = (j < H && c < P.C) ? __ldg(A.mlp + j * in0 + 3 + 6 * P.F + c) : 0.0f;
-    }
+    load_bwd_weights<HP>(P, A.mlp, Wb, W0f);
     for (int e = threadIdx.x; e < NW * kBaccStride; e += blockDim.x) bacc[e] = 0.0f;
     for (int e = P.in0p * S + threadIdx.x; e < x_rows(P) * S; e += blockDim.x) X[e] = 0.0f;  // pad rows of the input block
     __syncthreads();
@@ -475,7 +464,7 @@ __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_co
         }
         if (lane == 0) {
             wacc[LMAX * HP + HP] = v;
-            if (FUSED && A.loss_sum) atomicAdd(A.loss_sum, e);
+            wacc[LMAX * HP + HP + 1] = FUSED ? e : 0.0f;
         }
     }
     __syncthreads();
@@ -486,9 +475,9 @@ __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_co
         bacc[e] = t;
     }
     __syncthreads();
-    float* dst = A.partial + ((size_t)blockIdx.x * KGmax + kg) * A.pcount;
+    float* dst = A.partial + ((size_t)blockIdx.x * KGmax + kg) * A.pstride;
     // a row group with fewer warps than KGmax leaves its rows of the last slice to its first warp (zeros)
-    float* dstz = (KG < KGmax && kg == 0) ? A.partial + ((size_t)blockIdx.x * KGmax + KGmax - 1) * A.pcount : nullptr;
+    float* dstz = (KG < KGmax && kg == 0) ? A.partial + ((size_t)blockIdx.x * KGmax + KGmax - 1) * A.pstride : nullptr;
 #pragma unroll
     for (int l = 0; l < LMAX; ++l) {
         if (l < L) {
@@ -514,7 +503,8 @@ __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_co
     }
     // biases, final layer: slice 0 carries the CTA's sums, the other slices hold zeros there
     for (int k = 0; k < KGmax; ++k) {
-        float* d = A.partial + ((size_t)blockIdx.x * KGmax + k) * A.pcount;
+        float* d = A.partial + ((size_t)blockIdx.x * KGmax + k) * A.pstride;
+        if (threadIdx.x == 0) d[A.pcount] = k == 0 ? bacc[LMAX * HP + HP + 1] : 0.0f;  // loss partial
         for (int l = 0; l < L; ++l)
             for (int j = threadIdx.x; j < H; j += blockDim.x) d[mlp_b_off(l, in0, H) + j] = k == 0 ? bacc[l * HP + j] : 0.0f;
         for (int j = threadIdx.x; j < H + 1; j += blockDim.x)
@@ -550,12 +540,13 @@ static int launch_nw(BwdArgs& A, float* grad_mlp, int accumulate, void* workspac
     int64_t grid = sm_count();
     if (grid > ntiles) grid = ntiles;
     constexpr int KGmax = (NW + 3) / 4;
-    const size_t need = (size_t)grid * KGmax * A.pcount * sizeof(float);
+    const size_t need = (size_t)grid * KGmax * A.pstride * sizeof(float);
     if (workspace_bytes < need) return fail(LFGC_E_WORKSPACE, "backward workspace too small: %zu < %zu", workspace_bytes, need);
     A.partial = reinterpret_cast<float*>(workspace);
     kern<<<(unsigned)grid, 32 * NW, smem, st>>>(A);
     LFGC_LAUNCH_OK();
-    launch_reduce_partials(A.partial, (int)grid * KGmax, A.pcount, grad_mlp, accumulate, st);
+    launch_reduce_partials(A.partial, (int)grid * KGmax, A.pstride, A.pcount, grad_mlp, accumulate,
+                           FUSED ? A.loss_sum : nullptr, st);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }
@@ -585,7 +576,7 @@ static int launch(BwdArgs& A, float* grad_mlp, int accumulate, void* workspace, 
 
 }  // namespace v2
 
-size_t backward_v2_workspace_floats(int pcount, int sms) { return (size_t)sms * 4 * (size_t)pcount; }  // <= 16 warps
+size_t backward_v2_workspace_floats(int pcount, int sms) { return (size_t)sms * 4 * (size_t)(pcount + 1); }  // <= 16 warps
 
 int launch_backward_v2(BwdArgs& A, int fused, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
                        cudaStream_t st) {

@@ -111,18 +111,38 @@ __device__ __forceinline__ int mlp_w_off(int l, int in0, int H) {
 __device__ __forceinline__ int mlp_b_off(int l, int in0, int H) { return mlp_w_off(l, in0, H) + (l == 0 ? in0 : H) * H; }
 __device__ __forceinline__ int mlp_wf_off(int L, int in0, int H) { return mlp_w_off(L, in0, H); }
 
+// Stage the MLP parameters into shared memory.  Global reads run along the packed buffer (coalesced; 16-byte
+// vectors where the layer's block is aligned), the transposition happens on the shared-memory side.
 template <int HP>
 __device__ __forceinline__ void load_fwd_weights(const SampleParams& P, const float* __restrict__ mlp, float* Wt,
                                                  float* bias, float* Wf, float* bf) {
     const int H = P.H, in0 = P.in0;
+    const int total = FwdWeights<HP>::total(P.L, in0);
+    if (H < HP) {  // pad columns must read as zero
+        for (int e = threadIdx.x; e < total; e += blockDim.x) Wt[e] = 0.0f;
+        __syncthreads();
+    }
     for (int l = 0; l < P.L; ++l) {
         const int K = l == 0 ? in0 : H;
-        const int Kp = l == 0 ? in0 : HP;
-        const float* W = mlp + mlp_w_off(l, in0, H);
+        const int woff = mlp_w_off(l, in0, H);
+        const float* W = mlp + woff;
         float* dst = Wt + FwdWeights<HP>::layer_off(l, in0);
-        for (int e = threadIdx.x; e < Kp * HP; e += blockDim.x) {
-            const int k = e / HP, j = e % HP;
-            dst[e] = (j < H && k < K) ? __ldg(W + j * K + k) : 0.0f;
+        if ((K & 3) == 0 && (woff & 3) == 0) {
+            const int n4 = (H * K) >> 2;
+            for (int e4 = threadIdx.x; e4 < n4; e4 += blockDim.x) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(W) + e4);
+                const int e = e4 << 2;
+                const int j = e / K, k = e - j * K;
+                dst[(k + 0) * HP + j] = v.x;
+                dst[(k + 1) * HP + j] = v.y;
+                dst[(k + 2) * HP + j] = v.z;
+                dst[(k + 3) * HP + j] = v.w;
+            }
+        } else {
+            for (int e = threadIdx.x; e < H * K; e += blockDim.x) {
+                const int j = e / K, k = e - j * K;
+                dst[k * HP + j] = __ldg(W + e);
+            }
         }
         const float* b = mlp + mlp_b_off(l, in0, H);
         for (int j = threadIdx.x; j < HP; j += blockDim.x) bias[l * HP + j] = j < H ? __ldg(b + j) : 0.0f;
@@ -130,6 +150,32 @@ __device__ __forceinline__ void load_fwd_weights(const SampleParams& P, const fl
     const float* wf = mlp + mlp_wf_off(P.L, in0, H);
     for (int j = threadIdx.x; j < HP; j += blockDim.x) Wf[j] = j < H ? __ldg(wf + j) : 0.0f;
     if (threadIdx.x == 0) *bf = __ldg(wf + H);
+}
+
+// Backward-layout weights: Wb_l[j][k] = W_l[j][k] (l >= 1, row stride HP) and the layer-0 feature columns
+// W0f[j][c] = W_0[j][3+6F+c] (row stride Cp); pads are zero.
+template <int HP>
+__device__ __forceinline__ void load_bwd_weights(const SampleParams& P, const float* __restrict__ mlp, float* Wb,
+                                                 float* W0f) {
+    const int H = P.H, in0 = P.in0;
+    for (int l = 1; l < P.L; ++l) {
+        const int woff = mlp_w_off(l, in0, H);
+        const float* W = mlp + woff;
+        float* dst = Wb + (l - 1) * HP * HP;
+        if (H == HP && (woff & 3) == 0) {
+            for (int e4 = threadIdx.x; e4 < (HP * HP) >> 2; e4 += blockDim.x)
+                reinterpret_cast<float4*>(dst)[e4] = __ldg(reinterpret_cast<const float4*>(W) + e4);
+        } else {
+            for (int e = threadIdx.x; e < HP * HP; e += blockDim.x) {
+                const int j = e / HP, k = e % HP;
+                dst[e] = (j < H && k < H) ? __ldg(W + j * H + k) : 0.0f;
+            }
+        }
+    }
+    for (int e = threadIdx.x; e < HP * P.Cp; e += blockDim.x) {
+        const int j = e / P.Cp, c = e % P.Cp;
+        W0f[e] = (j < H && c < P.C) ? __ldg(mlp + j * in0 + 3 + 6 * P.F + c) : 0.0f;
+    }
 }
 
 // One dense layer for a warp's 32 samples, register-tiled 4 samples x NO outputs per lane:

@@ -89,6 +89,7 @@ struct LevelArgs {
     const float* mlow;   // (d0, d1, d2) or null: multiplier of the low-pass input (coarsest level only)
     const float* mhigh;  // (7, d0, d1, d2) or null
     float* out;          // (t0, t1, t2, Cs) channels-last, Cs = Cp for the final grid, C otherwise
+    float* also_zero;    // optional buffer of the same shape as `out`, cleared in the same pass (gradient accumulator)
     int C, Cs, low_cl;
     int d[3], t[3], off[3];
     int ntaps;
@@ -97,14 +98,79 @@ struct LevelArgs {
 
 // u[o] = sum_k sum_i c_k[i] r_a[oz-2iz] r_b[oy-2iy] r_c[ox-2ix], out[p] = u[p + off], sub-band k = 4a+2b+c
 // (Torch_Wavelet_Transform.py:39-57 outer-product filter bank; :100-104 transposed conv + crop).
+// With NT taps an output position sees NT/2 input positions per axis: i = (o >> 1) - a, tap (o & 1) + 2a.  The
+// template unrolls all (NT/2)^3 x 8 coefficient loads so that they are issued back to back (one L2 round trip)
+// instead of one dependent load per loop iteration; out-of-range positions are clamped and get weight zero.
+template <int NT>
 __global__ void idwt_level_kernel(LevelArgs A) {
+    constexpr int NP = NT / 2;
     const int64_t nvox = (int64_t)A.t[0] * A.t[1] * A.t[2];
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nvox * A.Cs) return;
     const int c = (int)(idx % A.Cs);
     const int64_t p = idx / A.Cs;
+    if (A.also_zero) A.also_zero[idx] = 0.0f;
     if (c >= A.C) {
         A.out[idx] = 0.0f;  // zero pad channels
+        return;
+    }
+    const int px = (int)(p % A.t[2]);
+    const int py = (int)((p / A.t[2]) % A.t[1]);
+    const int pz = (int)(p / ((int64_t)A.t[2] * A.t[1]));
+    const int o[3] = {pz + A.off[0], py + A.off[1], px + A.off[2]};
+    const int64_t dvol = (int64_t)A.d[0] * A.d[1] * A.d[2];
+    const float* highc = A.high + (int64_t)c * 7 * dvol;
+
+    int ii[3][NP];
+    float wl[3][NP], wh[3][NP];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax)
+#pragma unroll
+        for (int a = 0; a < NP; ++a) {
+            const int i = (o[ax] >> 1) - a;
+            const int t = (o[ax] & 1) + 2 * a;
+            const bool ok = i >= 0 && i < A.d[ax];
+            ii[ax][a] = ok ? i : 0;
+            wl[ax][a] = ok ? A.lo[t] : 0.0f;
+            wh[ax][a] = ok ? A.hi[t] : 0.0f;
+        }
+    float acc = 0.0f;
+#pragma unroll
+    for (int az = 0; az < NP; ++az)
+#pragma unroll
+        for (int ay = 0; ay < NP; ++ay)
+#pragma unroll
+            for (int axx = 0; axx < NP; ++axx) {
+                const int64_t b = ((int64_t)ii[0][az] * A.d[1] + ii[1][ay]) * A.d[2] + ii[2][axx];
+                float v[8];
+                v[0] = A.low_cl ? A.low[b * A.C + c] : A.low[(int64_t)c * dvol + b];
+                if (A.mlow) v[0] *= A.mlow[b];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) {
+                    v[k] = highc[(int64_t)(k - 1) * dvol + b];
+                    if (A.mhigh) v[k] *= A.mhigh[(int64_t)(k - 1) * dvol + b];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float wz = (k & 4) ? wh[0][az] : wl[0][az];
+                    const float wy = (k & 2) ? wh[1][ay] : wl[1][ay];
+                    const float wx = (k & 1) ? wh[2][axx] : wl[2][axx];
+                    acc = fmaf(v[k], wz * wy * wx, acc);
+                }
+            }
+    A.out[idx] = acc;
+}
+
+// any (even) filter length: plain loops
+__global__ void idwt_level_generic_kernel(LevelArgs A) {
+    const int64_t nvox = (int64_t)A.t[0] * A.t[1] * A.t[2];
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nvox * A.Cs) return;
+    const int c = (int)(idx % A.Cs);
+    const int64_t p = idx / A.Cs;
+    if (A.also_zero) A.also_zero[idx] = 0.0f;
+    if (c >= A.C) {
+        A.out[idx] = 0.0f;
         return;
     }
     int px = (int)(p % A.t[2]);
@@ -114,7 +180,6 @@ __global__ void idwt_level_kernel(LevelArgs A) {
     const int nt = A.ntaps;
     const int64_t dvol = (int64_t)A.d[0] * A.d[1] * A.d[2];
     const float* highc = A.high + (int64_t)c * 7 * dvol;
-
     auto lo_i = [&](int o) { int v = o - nt + 1; return v <= 0 ? 0 : (v + 1) >> 1; };
     float acc = 0.0f;
     for (int iz = lo_i(oz); iz <= min(A.d[0] - 1, oz >> 1); ++iz) {
@@ -142,11 +207,21 @@ __global__ void idwt_level_kernel(LevelArgs A) {
     A.out[idx] = acc;
 }
 
+static void launch_idwt_level(const LevelArgs& A, int64_t total, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((total + 127) / 128);
+    if (A.ntaps == 2) idwt_level_kernel<2><<<blocks, 128, 0, st>>>(A);
+    else if (A.ntaps == 4) idwt_level_kernel<4><<<blocks, 128, 0, st>>>(A);
+    else if (A.ntaps == 6) idwt_level_kernel<6><<<blocks, 128, 0, st>>>(A);
+    else idwt_level_generic_kernel<<<blocks, 128, 0, st>>>(A);
+}
+
 // n_coeff == 1 (grid too small for a wavelet level): masked NCDHW -> channels-last copy
 __global__ void copy_to_channels_last_kernel(const float* __restrict__ src, const float* __restrict__ mult,
-                                             float* __restrict__ dst, int C, int Cp, int64_t nvox) {
+                                             float* __restrict__ dst, float* __restrict__ also_zero, int C, int Cp,
+                                             int64_t nvox) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nvox * Cp) return;
+    if (also_zero) also_zero[idx] = 0.0f;
     int c = (int)(idx % Cp);
     int64_t p = idx / Cp;
     float v = 0.0f;
@@ -178,6 +253,7 @@ struct LevelBwdArgs {
 
 // One thread per (sub-band k, position b, channel c), channel fastest.  d mult[k][b] = sum_c coeff * g is reduced
 // with warp shuffles when C divides the warp, then one atomic per (k, b).
+template <int NT>
 __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
     const int64_t dvol = (int64_t)A.d[0] * A.d[1] * A.d[2];
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,22 +268,48 @@ __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
     const float* fz = ((k >> 2) & 1) ? A.hi : A.lo;
     const float* fy = ((k >> 1) & 1) ? A.hi : A.lo;
     const float* fx = (k & 1) ? A.hi : A.lo;
-    const int nt = A.ntaps;
-
     float g = 0.0f;
     if (live) {
-        for (int tz = 0; tz < nt; ++tz) {
-            const int pz = 2 * iz + tz - A.off[0];
-            if (pz < 0 || pz >= A.t[0]) continue;
-            for (int ty = 0; ty < nt; ++ty) {
-                const int py = 2 * iy + ty - A.off[1];
-                if (py < 0 || py >= A.t[1]) continue;
-                const float wzy = fz[tz] * fy[ty];
-                for (int tx = 0; tx < nt; ++tx) {
-                    const int px = 2 * ix + tx - A.off[2];
-                    if (px < 0 || px >= A.t[2]) continue;
-                    const int64_t p = ((int64_t)pz * A.t[1] + py) * A.t[2] + px;
-                    g = fmaf(A.gout[p * A.Cs + c], wzy * fx[tx], g);
+        if (NT > 0) {
+            // all NT^3 loads are independent: clamp the position, zero the weight when it falls outside the target
+            int pp[3][NT > 0 ? NT : 1];
+            float ww[3][NT > 0 ? NT : 1];
+            const int i3[3] = {iz, iy, ix};
+            const float* f3[3] = {fz, fy, fx};
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax)
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const int q = 2 * i3[ax] + t - A.off[ax];
+                    const bool ok = q >= 0 && q < A.t[ax];
+                    pp[ax][t] = ok ? q : 0;
+                    ww[ax][t] = ok ? f3[ax][t] : 0.0f;
+                }
+#pragma unroll
+            for (int tz = 0; tz < NT; ++tz)
+#pragma unroll
+                for (int ty = 0; ty < NT; ++ty) {
+                    const float wzy = ww[0][tz] * ww[1][ty];
+                    const int64_t rowp = ((int64_t)pp[0][tz] * A.t[1] + pp[1][ty]) * A.t[2];
+#pragma unroll
+                    for (int tx = 0; tx < NT; ++tx)
+                        g = fmaf(A.gout[(rowp + pp[2][tx]) * A.Cs + c], wzy * ww[2][tx], g);
+                }
+        } else {
+            const int nt = A.ntaps;
+            for (int tz = 0; tz < nt; ++tz) {
+                const int pz = 2 * iz + tz - A.off[0];
+                if (pz < 0 || pz >= A.t[0]) continue;
+                for (int ty = 0; ty < nt; ++ty) {
+                    const int py = 2 * iy + ty - A.off[1];
+                    if (py < 0 || py >= A.t[1]) continue;
+                    const float wzy = fz[tz] * fy[ty];
+                    for (int tx = 0; tx < nt; ++tx) {
+                        const int px = 2 * ix + tx - A.off[2];
+                        if (px < 0 || px >= A.t[2]) continue;
+                        const int64_t p = ((int64_t)pz * A.t[1] + py) * A.t[2] + px;
+                        g = fmaf(A.gout[p * A.Cs + c], wzy * fx[tx], g);
+                    }
                 }
             }
         }
@@ -240,6 +342,13 @@ __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
     } else if (gm) {
         atomicAdd(gm, contrib);
     }
+}
+
+static void launch_idwt_level_bwd(const LevelBwdArgs& A, int64_t total, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (A.ntaps == 2) idwt_level_bwd_kernel<2><<<blocks, 256, 0, st>>>(A);
+    else if (A.ntaps == 4) idwt_level_bwd_kernel<4><<<blocks, 256, 0, st>>>(A);
+    else idwt_level_bwd_kernel<0><<<blocks, 256, 0, st>>>(A);
 }
 
 // n_coeff == 1: adjoint of the masked transpose
@@ -382,7 +491,7 @@ extern "C" size_t lfgc_decode_scratch_bytes(const lfgc_wavelet_desc* w) {
 }
 
 extern "C" int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* coeff, const float* const* mult,
-                               float* scratch, float* grid_cl, int Cp, void* stream) {
+                               float* scratch, float* grid_cl, int Cp, float* also_zero, void* stream) {
     int rc = check_desc(w);
     if (rc) return rc;
     if (!coeff || !grid_cl) return fail(LFGC_E_INVALID, "decode_fwd: null pointer");
@@ -391,7 +500,7 @@ extern "C" int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* c
     if (w->n_coeff == 1) {
         const int64_t nvox = (int64_t)w->dims[0][0] * w->dims[0][1] * w->dims[0][2];
         copy_to_channels_last_kernel<<<(unsigned)((nvox * Cp + 255) / 256), 256, 0, st>>>(coeff[0], mult ? mult[0] : nullptr,
-                                                                                        grid_cl, w->C, Cp, nvox);
+                                                                                        grid_cl, also_zero, w->C, Cp, nvox);
         LFGC_LAUNCH_OK();
         return LFGC_OK;
     }
@@ -407,6 +516,7 @@ extern "C" int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* c
         A.mhigh = mult ? mult[l] : nullptr;
         const bool last = (l == w->n_coeff - 1);
         A.out = last ? grid_cl : buf[l & 1];
+        A.also_zero = last ? also_zero : nullptr;
         A.low_cl = (l == 1) ? 0 : 1;
         A.C = w->C;
         A.Cs = last ? Cp : w->C;
@@ -421,7 +531,7 @@ extern "C" int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* c
             A.hi[i] = w->rec_hi[i];
         }
         const int64_t total = (int64_t)A.t[0] * A.t[1] * A.t[2] * A.Cs;
-        idwt_level_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(A);
+        launch_idwt_level(A, total, st);
         LFGC_LAUNCH_OK();
         low = A.out;
     }
@@ -480,7 +590,7 @@ extern "C" int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_gri
             if (A.gmult_high) LFGC_CUDA_OK(cudaMemsetAsync(A.gmult_high, 0, 7 * dvol * sizeof(float), st));
         }
         const int64_t total = 8 * dvol * A.C;
-        idwt_level_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A);
+        launch_idwt_level_bwd(A, total, st);
         LFGC_LAUNCH_OK();
         gout = A.g_low;
     }

@@ -144,7 +144,8 @@ def dwt_level(x: torch.Tensor, wavelet: str):
 
 
 def decode_fwd(geom: Geometry, coeffs: Sequence[torch.Tensor], mults: Sequence[Optional[torch.Tensor]],
-               scratch: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+               scratch: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+               also_zero: Optional[torch.Tensor] = None):
     lib = L.load()
     dev = coeffs[0].device
     for i, c in enumerate(coeffs):
@@ -159,8 +160,8 @@ def decode_fwd(geom: Geometry, coeffs: Sequence[torch.Tensor], mults: Sequence[O
     if out is None:
         out = torch.empty((*geom.G, geom.Cp), device=dev, dtype=torch.float32)
     L.check(lib.lfgc_decode_fwd(ct.byref(geom.wavelet_desc), L.ptr_array([_p(c) for c in coeffs]),
-                                L.ptr_array([_p(m) for m in mults]), _p(scratch), _p(out), geom.Cp, _stream()),
-            'lfgc_decode_fwd')
+                                L.ptr_array([_p(m) for m in mults]), _p(scratch), _p(out), geom.Cp, _p(also_zero),
+                                _stream()), 'lfgc_decode_fwd')
     return out
 
 

@@ -30,6 +30,7 @@ import torch.nn as nn
 
 from .. import _lib as L
 from .. import ops
+from . import parallel
 from ..model.Dropout_Layer import DropoutLayer
 from ..model.Feature_Grid_Model import Feature_Grid_Model, _multipliers
 from ..model.Smallify_Dropout import SmallifyDropout
@@ -96,7 +97,7 @@ class FastTrainer:
             self._grad_view[id(p)] = self.flat_g[o:o + n].view(p.shape)
 
         self.lr_dev = torch.tensor([lr], device=self.device, dtype=torch.float32)
-        self.step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.step_dev = torch.zeros(2, device=self.device, dtype=torch.int32)  # [steps taken, Adam ticket scratch]
         self.loss_sum = torch.zeros(1, device=self.device, dtype=torch.float32)
         self.grid_cl = torch.empty((*self.geom.G, self.geom.Cp), device=self.device, dtype=torch.float32)
         self.grad_grid = torch.zeros_like(self.grid_cl)
@@ -116,11 +117,12 @@ class FastTrainer:
         specs = model.mask_specs()
         mults, auxs = _multipliers(specs)
         coeffs = [p.data for p in self.coeff_params]
-        ops.decode_fwd(geom, coeffs, mults, scratch=self.scratch, out=self.grid_cl)
-        self.grad_grid.zero_()
-        self.loss_sum.zero_()
+        # the synthesis also clears the grid-gradient accumulator; the fused kernel overwrites loss_sum
+        ops.decode_fwd(geom, coeffs, mults, scratch=self.scratch, out=self.grid_cl, also_zero=self.grad_grid)
         n_global = self.batch * self.world
-        ops.train_step(geom, self.volume, self.batch, self.seed, self.rank * self.batch, 1.0 / n_global, self.grid_cl,
+        ops.train_step(geom, self.volume, self.batch, self.seed,
+                       parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
+                       parallel.loss_scale(self.batch, self.world), self.grid_cl,
                        self.mlp_flat, self.grad_grid, self.flat_g[self.mlp_off:], self.loss_sum, self.workspace,
                        step_dev=self.step_dev, step_stride=n_global)
         want = [s is not None and len(s.grad_params) > 0 for s in specs]

@@ -1,0 +1,117 @@
+"""Size-independent properties at the full BASELINE.json sizes (where the oracle would take too long): adjointness,
+linearity, determinism, permutation invariance, perfect reconstruction; plus wavelets the golden fixtures do not
+cover (db3 runs the 6-tap template forward and the generic adjoint, db4 the generic kernels)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(C, G, wavelet='db2', H=32, L=4, F=2, seed=0):
+    from latent_feature_grid_compression_b200.model.model_utils import setup_model
+    torch.manual_seed(seed)
+    return setup_model(3, H, 1, L, 'fourier', F, '', 0.1, 0.9, wavelet, C, G, '').cuda().train()
+
+
+@pytest.mark.parametrize('C,G,wavelet', [(16, 15, 'db2'), (32, 64, 'db2'), (6, 21, 'db3'), (4, 24, 'db4'), (8, 32, 'haar')])
+def test_synthesis_adjoint_and_perfect_reconstruction(C, G, wavelet):
+    from latent_feature_grid_compression_b200 import ops
+    m = _model(C, G, wavelet)
+    geom = m.geometry()
+    coeffs = [f.detach().contiguous() for f in m.feature_grid]
+    # perfect reconstruction: encode(decode(c)) == c is implied by decode(encode(x)) == x
+    x = torch.rand(C, G, G, G, device='cuda')
+    feats, _ = m.encode_volume(x)
+    cl = ops.decode_fwd(geom, [f.contiguous() for f in feats], [None] * len(feats))
+    back = cl[..., :C].permute(3, 0, 1, 2)
+    assert float((back - x).abs().max()) < 5e-6
+    # <decode(c), g> == <c, decode^T(g)>   (fp64 accumulation of the inner products)
+    g = torch.randn(*geom.G, geom.Cp, device='cuda')
+    g[..., C:] = 0
+    out = ops.decode_fwd(geom, coeffs, [None] * len(coeffs))
+    gc, _ = ops.decode_bwd(geom, g, coeffs, [None] * len(coeffs), [False] * len(coeffs))
+    lhs = float((out.double() * g.double()).sum())
+    rhs = float(sum((c.double() * d.double()).sum() for c, d in zip(coeffs, gc)))
+    assert abs(lhs - rhs) <= 2e-5 * max(abs(lhs), 1.0)
+    assert float(out[..., C:].abs().max()) == 0.0 if geom.Cp > C else True
+
+
+@pytest.mark.parametrize('C,G,n', [(16, 15, 32768), (32, 64, 262144), (22, 17, 5000)])
+def test_backward_linearity_determinism_and_permutation(C, G, n):
+    from latent_feature_grid_compression_b200 import ops
+    m = _model(C, G)
+    geom = m.geometry()
+    coeffs = [f.detach().contiguous() for f in m.feature_grid]
+    grid_cl = ops.decode_fwd(geom, coeffs, [None] * len(coeffs))
+    mlp = m.mlp_flat()
+    gen = torch.Generator(device='cuda').manual_seed(1)
+    coords = torch.rand(n, 3, device='cuda', generator=gen) * 2 - 1
+    g1 = torch.randn(n, device='cuda', generator=gen)
+    g2 = torch.randn(n, device='cuda', generator=gen)
+    y = ops.sample_forward(geom, coords, grid_cl, mlp)
+    assert torch.equal(y, ops.sample_forward(geom, coords, grid_cl, mlp))          # forward is deterministic
+    a_grid, a_mlp = ops.sample_backward(geom, coords, g1, grid_cl, mlp)
+    b_grid, b_mlp = ops.sample_backward(geom, coords, g2, grid_cl, mlp)
+    c_grid, c_mlp = ops.sample_backward(geom, coords, (g1 + 2 * g2).contiguous(), grid_cl, mlp)
+    tol_m = 2e-5 * float(c_mlp.abs().max())
+    tol_g = 2e-5 * float(c_grid.abs().max())
+    assert float((a_mlp + 2 * b_mlp - c_mlp).abs().max()) <= tol_m                   # linear in d(out)
+    assert float((a_grid + 2 * b_grid - c_grid).abs().max()) <= tol_g
+    a2_grid, a2_mlp = ops.sample_backward(geom, coords, g1, grid_cl, mlp)
+    assert torch.equal(a_mlp, a2_mlp)                                                # MLP gradient: fixed reduction order
+    assert float((a_grid - a2_grid).abs().max()) <= tol_g                            # grid gradient: atomics re-order only
+    perm = torch.randperm(n, device='cuda', generator=gen)
+    p_grid, p_mlp = ops.sample_backward(geom, coords[perm].contiguous(), g1[perm].contiguous(), grid_cl, mlp)
+    assert float((p_mlp - a_mlp).abs().max()) <= tol_m                               # a sum over samples
+    assert float((p_grid - a_grid).abs().max()) <= tol_g
+    assert float(c_grid[..., C:].abs().max()) == 0.0 if geom.Cp > C else True
+    # zero upstream gradient -> zero gradients; only the first k samples contribute when the rest is zero
+    z_grid, z_mlp = ops.sample_backward(geom, coords, torch.zeros(n, device='cuda'), grid_cl, mlp)
+    assert float(z_mlp.abs().max()) == 0.0 and float(z_grid.abs().max()) == 0.0
+
+
+def test_gradient_against_finite_differences_full_model():
+    """d loss / d theta through decode + sample kernels vs central differences in fp64-free form (directional)."""
+    m = _model(16, 15, seed=3)
+    coords = (torch.rand(4096, 3, device='cuda') * 2 - 1)
+    w = torch.randn(4096, 1, device='cuda')
+    y = m(coords)
+    (y * w).sum().backward()
+    params = [p for p in m.parameters()]
+    torch.manual_seed(9)
+    dirs = [torch.randn_like(p) for p in params]
+    analytic = float(sum((p.grad.double() * d.double()).sum() for p, d in zip(params, dirs)))
+    eps = 1e-3
+    with torch.no_grad():
+        for p, d in zip(params, dirs):
+            p.add_(eps * d)
+        up = float((m(coords).double() * w.double()).sum())
+        for p, d in zip(params, dirs):
+            p.sub_(2 * eps * d)
+        dn = float((m(coords).double() * w.double()).sum())
+    numeric = (up - dn) / (2 * eps)
+    assert abs(numeric - analytic) <= 2e-3 * max(abs(analytic), 1.0)
+
+
+def test_reconstruction_full_size_slabs_and_idempotence():
+    from latent_feature_grid_compression_b200.data.IndexDataset import IndexDataset
+    from latent_feature_grid_compression_b200.training.parallel import slab_bounds
+    from latent_feature_grid_compression_b200.visualization.OutputToVTK import field_from_net
+    m = _model(16, 15).eval()
+    vol = torch.zeros(255, 255, 255)
+    ds = IndexDataset(vol, 16)
+    full = field_from_net(ds, m, True, to_cpu=False)
+    assert tuple(full.shape) == (255, 255, 255)
+    assert torch.equal(full, field_from_net(ds, m, True, to_cpu=False))              # idempotent / deterministic
+    parts = [field_from_net(ds, m, True, slab=slab_bounds(255, r, 8), to_cpu=False) for r in range(8)]
+    assert torch.equal(torch.cat(parts, 0), full)                                    # 8 z-slabs == whole volume
+    assert float(full.max()) <= 1.0 and float(full.min()) >= -1.0
+    # same values as the per-point API on an arbitrary subset of voxels
+    from latent_feature_grid_compression_b200.visualization.OutputToVTK import axis_tables
+    ax = axis_tables(ds, 32)
+    i = torch.randint(0, 255, (1000, 3), device='cuda')
+    pts = torch.stack([ax[0][i[:, 0]], ax[1][i[:, 1]], ax[2][i[:, 2]]], dim=-1).view(1, 1, 10, 10, 10, 3)
+    with torch.no_grad():
+        vals = m(pts).view(-1)
+    assert torch.equal(vals, full[i[:, 0], i[:, 1], i[:, 2]])
