@@ -127,7 +127,7 @@ __device__ __forceinline__ void load_fwd_weights(const SampleParams& P, const fl
         const int woff = mlp_w_off(l, in0, H);
         const float* W = mlp + woff;
         float* dst = Wt + FwdWeights<HP>::layer_off(l, in0);
-        if ((K & 3) == 0 && (woff & 3) == 0) {
+        if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
             const int n4 = (H * K) >> 2;
             for (int e4 = threadIdx.x; e4 < n4; e4 += blockDim.x) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(W) + e4);
@@ -162,7 +162,7 @@ __device__ __forceinline__ void load_bwd_weights(const SampleParams& P, const fl
         const int woff = mlp_w_off(l, in0, H);
         const float* W = mlp + woff;
         float* dst = Wb + (l - 1) * HP * HP;
-        if (H == HP && (woff & 3) == 0) {
+        if (H == HP && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
             for (int e4 = threadIdx.x; e4 < (HP * HP) >> 2; e4 += blockDim.x)
                 reinterpret_cast<float4*>(dst)[e4] = __ldg(reinterpret_cast<const float4*>(W) + e4);
         } else {

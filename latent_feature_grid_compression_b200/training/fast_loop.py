@@ -68,18 +68,24 @@ class FastTrainer:
                 self.mask_params += [p for p in d.parameters()]
         self.mlp_params = model._mlp_params()
         every = self.coeff_params + self.mask_params + self.mlp_params
-        with torch.no_grad():
-            self.flat_p = torch.cat([p.detach().reshape(-1).to(self.device, torch.float32) for p in every])
-            self._slices = []
-            off = 0
-            for p in every:
-                n = p.numel()
-                p.data = self.flat_p[off:off + n].view(p.shape)
-                self._slices.append((off, n))
-                off += n
+        # sections start on 16-byte boundaries (the kernels use 128-bit loads where the alignment allows)
+        def pad4(n):
+            return (n + 3) // 4 * 4
         self.n_coeff_elems = sum(p.numel() for p in self.coeff_params)
         self.n_mask_elems = sum(p.numel() for p in self.mask_params)
-        self.mlp_off = self.n_coeff_elems + self.n_mask_elems
+        self.mask_off = pad4(self.n_coeff_elems)
+        self.mlp_off = self.mask_off + pad4(self.n_mask_elems)
+        total = self.mlp_off + sum(p.numel() for p in self.mlp_params)
+        with torch.no_grad():
+            self.flat_p = torch.zeros(total, device=self.device, dtype=torch.float32)
+            self._slices = []
+            for group, off in ((self.coeff_params, 0), (self.mask_params, self.mask_off), (self.mlp_params, self.mlp_off)):
+                for p in group:
+                    n = p.numel()
+                    self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+                    p.data = self.flat_p[off:off + n].view(p.shape)
+                    self._slices.append((off, n))
+                    off += n
         self.flat_g = torch.zeros_like(self.flat_p)
         self.flat_m = torch.zeros_like(self.flat_p)
         self.flat_v = torch.zeros_like(self.flat_p)
@@ -142,8 +148,8 @@ class FastTrainer:
         if self.weight_l2 > 0.0 and self.n_coeff_elems:
             ops.add_l2_grad(self.flat_g[:self.n_coeff_elems], self.flat_p[:self.n_coeff_elems], self.weight_l2)
         if self.weight_l1 > 0.0 and self.n_mask_elems:
-            ops.add_l1_grad(self.flat_g[self.n_coeff_elems:self.mlp_off], self.flat_p[self.n_coeff_elems:self.mlp_off],
-                            self.weight_l1)
+            a, b = self.mask_off, self.mask_off + self.n_mask_elems
+            ops.add_l1_grad(self.flat_g[a:b], self.flat_p[a:b], self.weight_l1)
         ops.adam(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_dev, self.step_dev, self.betas[0],
                  self.betas[1], self.eps)
 
