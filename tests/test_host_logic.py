@@ -131,3 +131,23 @@ def test_model_refuses_cpu_tensors():
     with pytest.raises(LfgcError):
         trilinear_f_interpolation(torch.zeros(4, 3), torch.zeros(3, 3, 3), torch.zeros(3), torch.ones(3) * 2,
                                   torch.tensor([3.0, 3.0, 3.0]))
+
+
+def test_dropin_aliases_expose_the_reference_module_names():
+    """with dropin/ first on sys.path the reference's import statements resolve to this package."""
+    import subprocess
+    import sys
+    code = ("import model.model_utils as mu, data.IndexDataset as d, visualization.OutputToVTK as v\n"
+            "from model.Smallify_Dropout import SmallifyLoss\n"
+            "from model.Variational_Dropout_Layer import VariationalDropoutLoss, Variance_Model, VariationalDropout\n"
+            "from data.Interpolation import trilinear_f_interpolation, finite_difference_trilinear_grad\n"
+            "from data.IndexDataset import get_tensor, IndexDataset\n"
+            "from visualization.OutputToVTK import tiled_net_out\n"
+            "from visualization.pltUtils import dict_from_file\n"
+            "from model.model_utils import write_dict, setup_model, store_model_parameters, restore_model\n"
+            "from wavelet_transform.Torch_Wavelet_Transform import WaveletFilter3d, _WaveletFilterNd\n"
+            "assert mu.setup_model.__module__.startswith('latent_feature_grid_compression_b200')\n"
+            "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, 'dropin') + os.pathsep + ROOT)
+    out = subprocess.run([sys.executable, '-c', code], cwd='/tmp', env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == 'ok', out.stderr
