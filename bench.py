@@ -117,6 +117,30 @@ class ClockSampler:
         return out
 
 
+def host_threads() -> int:
+    """CPU threads this process may really use: affinity mask and cgroup quota, not the machine's core count
+    (a container on a 200-core host with a 16-CPU quota must not start 200 compute threads)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            quota, period = f.read().split()
+        if quota != 'max':
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def dist_env():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -132,7 +156,7 @@ def cpu_port_rate(steps_budget_s: float, opt_steps: int = None, warmup: int = 1)
     """samples/s of the CPU port on the bench workload; runs about `steps_budget_s` seconds unless opt_steps given."""
     from oracle import fvsrn_numpy as O
     from oracle import torch_port as TP
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     spec = O.Spec(CFG['C'], CFG['G'], CFG['H'], CFG['L'], CFG['F'], CFG['wavelet'], '')
     vol = synthetic_volume(CFG['R'], 'cpu')
     port = TP.CpuPort(spec, TP.make_state(spec, 0), lr=CFG['lr'])
@@ -158,10 +182,9 @@ def run_reference(args):
     if rank != 0:
         return
     steps_per_pass = math.ceil(CFG['R'] ** 3 / CFG['batch'])
-    # bounded sample: as many optimiser steps per bench step as fit ~150 s for the whole K+W run
     from oracle import fvsrn_numpy as O
     from oracle import torch_port as TP
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     spec = O.Spec(CFG['C'], CFG['G'], CFG['H'], CFG['L'], CFG['F'], CFG['wavelet'], '')
     vol = synthetic_volume(CFG['R'], 'cpu')
     port = TP.CpuPort(spec, TP.make_state(spec, 0), lr=CFG['lr'])
@@ -171,17 +194,26 @@ def run_reference(args):
     t0 = time.perf_counter()
     port.train_step(vol, n, gen)
     t1 = max(time.perf_counter() - t0, 1e-4)
-    budget_s = float(os.environ.get('LFGC_BENCH_CPU_BUDGET_S', '120'))
+    # bounded sample: as many optimiser steps per bench step as fit the budget for the whole K+W run
+    budget_s = float(os.environ.get('LFGC_BENCH_CPU_BUDGET_S', '90'))
     per_step = int(max(1, min(steps_per_pass, budget_s / ((args.steps + args.warmup) * t1))))
+    deadline = time.perf_counter() + 2.0 * budget_s          # hard guard: never run away on a slow / shared host
     for _ in range(args.warmup * per_step):
         port.train_step(vol, n, gen)
+        if time.perf_counter() > deadline:
+            break
+    done = 0
     t0 = time.perf_counter()
     for _ in range(args.steps * per_step):
         port.train_step(vol, n, gen)
+        done += 1
+        if time.perf_counter() > deadline and done >= args.steps:
+            break
     dt = time.perf_counter() - t0
-    rate = args.steps * per_step * n / dt
-    sample = '%d of the %d optimiser steps of a volume pass per bench step (32768 samples each: sampler + GT + ' \
-             'synthesis + fwd + MSE + bwd + Adam), ATen-op port of the reference on all host threads' % (per_step, steps_per_pass)
+    rate = done * n / dt
+    sample = '%.1f of the %d optimiser steps of a volume pass per bench step (32768 samples each: sampler + GT + ' \
+             'synthesis + fwd + MSE + bwd + Adam), ATen-op port of the reference on %d host threads' % (
+                 done / args.steps, steps_per_pass, torch.get_num_threads())
     line = dict(impl='reference', metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic',
