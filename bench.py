@@ -332,6 +332,9 @@ def run_native(args):
     roofline_hbm = dict(bound='hbm', achieved=hbm_ach, peak=pk['hbm_gbs'], unit='GB/s', frac=hbm_ach / pk['hbm_gbs'],
                         traffic=traffic, peak_source=pk['source'])
 
+    # ---- full-volume reconstruction (the path's second metric: decode voxels/s), this rank's slab ---------------------
+    recon = reconstruct_rate(model, volume, rank, world, dev, fp32_peak)
+
     # ---- end to end through the reference-facing nn.Module API with HOST buffers ------------------------------------
     e2e = e2e_module_path(model, volume, n, rank, world, dev)
 
@@ -355,7 +358,7 @@ def run_native(args):
                     e2e=e2e, gpu_launches=int(trainer.launches_per_step * steps_per_pass * args.steps),
                     clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'], reasons=clk['reasons'],
                                 samples=clk['samples']),
-                    roofline=roofline, roofline_hbm=roofline_hbm, cpu_baseline=cpu,
+                    roofline=roofline, roofline_hbm=roofline_hbm, reconstruct=recon, cpu_baseline=cpu,
                     extra=dict(us_per_optimiser_step=1e3 * total_ms / (args.steps * steps_per_pass),
                                hot_l2_samples_per_s=steps_per_pass * n * world / (hot_ms * 1e-3),
                                wall_s_timed_region=wall, final_mse=final_loss,
@@ -364,6 +367,42 @@ def run_native(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def reconstruct_rate(model, volume, rank, world, dev, fp32_peak, reps=10):
+    """decode voxels/s: field_from_net over this rank's slab of the 255^3 volume (grid decoded once, one launch),
+    output left on the device; whole-job rate = sum of the slabs / max time over ranks."""
+    import torch.distributed as dist
+    from latent_feature_grid_compression_b200.data.IndexDataset import IndexDataset
+    from latent_feature_grid_compression_b200.training.parallel import slab_bounds
+    from latent_feature_grid_compression_b200.visualization.OutputToVTK import field_from_net
+    R = volume.shape[0]
+    ds = IndexDataset(torch.zeros(1, 1, 1).expand(R, R, R), 16)
+    slab = slab_bounds(R, rank, world)
+    model.eval()
+    for _ in range(3):
+        out = field_from_net(ds, model, True, slab=slab, to_cpu=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = field_from_net(ds, model, True, slab=slab, to_cpu=False)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    model.train()
+    ms = float(t.item())
+    vox = R ** 3
+    tf = 8192.0 * (slab[1] - slab[0]) * R * R / (ms * 1e-3) / 1e12
+    return dict(metric='decode_voxels_per_s', value=vox / (ms * 1e-3), unit='voxels/s', ms_per_volume=ms,
+                volume='%d^3, z-slab sharded over %d GPU(s), no communication' % (R, world),
+                includes='axis tables + mask multipliers + wavelet synthesis + fused sample kernel, output stays in HBM',
+                roofline=dict(bound='fp32', achieved=tf, peak=fp32_peak, unit='TFLOP/s', frac=tf / fp32_peak,
+                              note='per GPU; 8192 FLOP/voxel; HBM-algorithmic 4 B/voxel written'))
 
 
 def e2e_module_path(model, volume, n, rank, world, dev, steps=100, warmup=10):

@@ -67,23 +67,6 @@ __host__ __device__ inline Layout make_layout(const SampleParams& P, int nw) {
     return o;
 }
 
-__device__ __forceinline__ void ffma2(float2& d, float a, float2 b) {
-    unsigned long long ra, rb, rd;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(ra) : "f"(a));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rd) : "f"(d.x), "f"(d.y));
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rd) : "l"(ra), "l"(rb));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-}
-__device__ __forceinline__ void ffma2v(float2& d, float2 a, float2 b) {
-    unsigned long long ra, rb, rd;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rd) : "f"(d.x), "f"(d.y));
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rd) : "l"(ra), "l"(rb));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-}
-
 // acc[s][p] = (out 2p, out 2p+1) of sample s:  acc = bias + sum_k in[k][s] * W[k][0..3]
 // `in` points at the lane's 4 samples of row 0, `W` at the lane's 4 outputs of row 0; S and LDW are compile-time so
 // that every load of the unrolled body is base + immediate.
@@ -186,13 +169,20 @@ __device__ __forceinline__ void dw_block(const float* __restrict__ dzp, const fl
         for (int c = 0; c < 4; ++c) t[r][c] = make_float2(0.f, 0.f);
     dzp += n0;
     hp += n0;
-#pragma unroll 2
-    for (; n0 < TILE; n0 += step, dzp += step, hp += step) {
-        float4 dz[2], hv[4];
+    // software pipeline: the loads of sample block i+1 are in flight while block i is multiplied
+    float4 dz[2], hv[4], dzn[2], hvn[4];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) dz[r] = *reinterpret_cast<const float4*>(dzp + r * 4 * S);
+    for (int r = 0; r < 2; ++r) dz[r] = *reinterpret_cast<const float4*>(dzp + r * 4 * S);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) hv[c] = *reinterpret_cast<const float4*>(hp + c * 8 * S);
+    for (int c = 0; c < 4; ++c) hv[c] = *reinterpret_cast<const float4*>(hp + c * 8 * S);
+    while (true) {
+        const bool more = n0 + step < TILE;
+        if (more) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) dzn[r] = *reinterpret_cast<const float4*>(dzp + step + r * 4 * S);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) hvn[c] = *reinterpret_cast<const float4*>(hp + step + c * 8 * S);
+        }
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -200,6 +190,14 @@ __device__ __forceinline__ void dw_block(const float* __restrict__ dzp, const fl
                 ffma2v(t[r][c], make_float2(dz[r].x, dz[r].y), make_float2(hv[c].x, hv[c].y));
                 ffma2v(t[r][c], make_float2(dz[r].z, dz[r].w), make_float2(hv[c].z, hv[c].w));
             }
+        if (!more) break;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) dz[r] = dzn[r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) hv[c] = hvn[c];
+        n0 += step;
+        dzp += step;
+        hp += step;
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r)
