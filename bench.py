@@ -336,7 +336,8 @@ def run_native(args):
     recon = reconstruct_rate(model, volume, rank, world, dev, fp32_peak)
 
     # ---- end to end through the reference-facing nn.Module API with HOST buffers ------------------------------------
-    e2e = e2e_module_path(model, volume, n, rank, world, dev)
+    e2e = e2e_host_fed(volume, n, rank, world, dev)
+    e2e_module = e2e_module_path(model, volume, n, rank, world, dev)
 
     line = None
     if rank == 0:
@@ -359,6 +360,7 @@ def run_native(args):
                     clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'], reasons=clk['reasons'],
                                 samples=clk['samples']),
                     roofline=roofline, roofline_hbm=roofline_hbm, reconstruct=recon, cpu_baseline=cpu,
+                    e2e_module_api=e2e_module,
                     extra=dict(us_per_optimiser_step=1e3 * total_ms / (args.steps * steps_per_pass),
                                hot_l2_samples_per_s=steps_per_pass * n * world / (hot_ms * 1e-3),
                                wall_s_timed_region=wall, final_mse=final_loss,
@@ -403,6 +405,48 @@ def reconstruct_rate(model, volume, rank, world, dev, fp32_peak, reps=10):
                 includes='axis tables + mask multipliers + wavelet synthesis + fused sample kernel, output stays in HBM',
                 roofline=dict(bound='fp32', achieved=tf, peak=fp32_peak, unit='TFLOP/s', frac=tf / fp32_peak,
                               note='per GPU; 8192 FLOP/voxel; HBM-algorithmic 4 B/voxel written'))
+
+
+def e2e_host_fed(volume, n, rank, world, dev, steps=300, warmup=20):
+    """samples/s of whole optimiser steps fed from HOST memory through the public trainer API
+    (FastTrainer.step_host): every step copies that step's positions (n x 3 fp32) and target values (n fp32) from
+    pinned host buffers, replays the captured step (synthesis + forward + MSE + backward + adjoint [+ all-reduce] +
+    Adam) and reads the loss back to the host."""
+    import torch.distributed as dist
+    from latent_feature_grid_compression_b200 import ops
+    from latent_feature_grid_compression_b200.model.model_utils import setup_model
+    from latent_feature_grid_compression_b200.training.fast_loop import FastTrainer
+    torch.manual_seed(0)
+    m = setup_model(3, CFG['H'], 1, CFG['L'], 'fourier', CFG['F'], '', 0.1, 0.9, CFG['wavelet'], CFG['C'], CFG['G'], '')
+    m.to(dev).train()
+    tr = FastTrainer(m, volume, n, lr=CFG['lr'], seed=7, rank=rank, world_size=world)
+    n_buf = 8
+    host = []
+    for b in range(n_buf):
+        raw, norm, gt = ops.sample(volume.shape, n, seed=99 + rank, sample_offset=b * n, volume=volume, want_gt=True)
+        host.append((norm.cpu().pin_memory(), gt.cpu().pin_memory()))
+    last = 0.0
+    for i in range(warmup):
+        tr.step_host(*host[i % n_buf])
+        last = tr.last_loss()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        tr.step_host(*host[i % n_buf])
+        last = tr.last_loss()          # device -> host read of the step's result, every step
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return dict(value=steps * n * world / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=n * 16, d2h_bytes_per_step=4,
+                api='FastTrainer.step_host(coords, targets) + last_loss(): one optimiser step of 32768 host-resident '
+                    'samples per GPU per call (lfgc_train_step with caller-supplied samples, CUDA-graph replay)',
+                us_per_optimiser_step=1e3 * ms / steps, final_mse=last)
 
 
 def e2e_module_path(model, volume, n, rank, world, dev, steps=100, warmup=10):

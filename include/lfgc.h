@@ -171,11 +171,14 @@ int lfgc_backward(const lfgc_model_desc* m, const float* coords, int64_t n, cons
  *   which lets a captured CUDA graph draw fresh samples on every replay
  *   loss_scale: d(loss)/d(pred) = loss_scale * 2 * (pred - gt); pass 1/N_global for the mean over the global batch
  *   loss_sum[0] = sum (pred-gt)^2 over this call's samples (overwritten; summed with the MLP gradient partials)
- *   explicit_idx (nullable, int64[n]): use these flat voxel indices instead of Philox (parity tests) */
+ *   explicit_idx (nullable, int64[n]): use these flat voxel indices instead of Philox (parity tests)
+ *   explicit_coords / explicit_gt (nullable, both or neither; fp32 [n][3] normalised positions and [n] target
+ *   values): caller-supplied samples instead of the in-kernel sampler -- the host-fed training step (the
+ *   reference's DataLoader contract, training/training.py:89-109); volume may then be NULL */
 int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
                     uint64_t seed, uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
-                    const int64_t* explicit_idx, float loss_scale,
-                    const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
+                    const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
+                    float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
                     float* loss_sum, int accumulate_mlp, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- sampler / ground truth ---------------------------------------------------------------------------------- */

@@ -57,7 +57,7 @@ _SIGNATURES = {
     'lfgc_backward_workspace_bytes': (C.c_size_t, [C.POINTER(ModelDesc)]),
     'lfgc_backward': (C.c_int, [C.POINTER(ModelDesc), _f, _i64, _f, _f, _f, _f, _f, _f, C.c_int, _f, C.c_size_t, _f]),
     'lfgc_train_step': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f,
-                                  C.c_uint64, _f, C.c_float, _f, _f, _f, _f, _f, C.c_int, _f, C.c_size_t, _f]),
+                                  C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, _f, C.c_int, _f, C.c_size_t, _f]),
     'lfgc_sample': (C.c_int, [_f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f, _f, _f, _f, _f]),
     'lfgc_trilinear': (C.c_int, [_f, _i64, _f, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float), _f, _f]),
     'lfgc_reconstruct': (C.c_int, [C.POINTER(ModelDesc), _f, _f, C.POINTER(C.c_int32), _f, _f, _f, C.c_int32,

@@ -129,7 +129,12 @@ __global__ void __launch_bounds__(kThreads, 1) sample_backward_kernel(const __gr
             valid = s < A.n;
             float cx = 0.f, cy = 0.f, cz = 0.f, aux = 0.f;
             if (valid) {
-                if (FUSED) {
+                if (FUSED && A.coords) {  // host-fed step: caller-supplied positions and target values
+                    cx = __ldg(A.coords + 3 * s);
+                    cy = __ldg(A.coords + 3 * s + 1);
+                    cz = __ldg(A.coords + 3 * s + 2);
+                    aux = __ldg(A.grad_out + s);
+                } else if (FUSED) {
                     unsigned long long v = A.explicit_idx ? (unsigned long long)A.explicit_idx[s]
                                                           : philox_voxel(A.seed, sample_base + (uint64_t)s, A.n_voxels);
                     const unsigned long long r12 = (unsigned long long)A.R[1] * A.R[2];
@@ -464,8 +469,8 @@ extern "C" int lfgc_backward(const lfgc_model_desc* m, const float* coords, int6
 
 extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
                                uint64_t seed, uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
-                               const int64_t* explicit_idx, float loss_scale,
-                               const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
+                               const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
+                               float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
                                float* loss_sum, int accumulate_mlp, void* workspace, size_t workspace_bytes,
                                void* stream) {
     BwdArgs A;
@@ -473,15 +478,18 @@ extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, co
     if (rc) return rc;
     rc = common_checks(m, n, grid_cl, mlp, grad_grid_cl, grad_mlp, workspace);
     if (rc) return rc;
-    if (!volume || !R || R[0] < 1 || R[1] < 1 || R[2] < 1) return fail(LFGC_E_INVALID, "train_step: bad volume");
+    if ((explicit_coords == nullptr) != (explicit_gt == nullptr))
+        return fail(LFGC_E_INVALID, "train_step: explicit_coords and explicit_gt go together");
+    if (!explicit_coords && (!volume || !R || R[0] < 1 || R[1] < 1 || R[2] < 1))
+        return fail(LFGC_E_INVALID, "train_step: bad volume");
     A.pcount = (int)lfgc_mlp_param_count(m);
     A.pstride = A.pcount + 1;
     if (n == 0) {
         if (!accumulate_mlp) LFGC_CUDA_OK(cudaMemsetAsync(grad_mlp, 0, A.pcount * sizeof(float), (cudaStream_t)stream));
         return LFGC_OK;
     }
-    A.coords = nullptr;
-    A.grad_out = nullptr;
+    A.coords = explicit_coords;   // non-null: host-fed samples (positions) ...
+    A.grad_out = explicit_gt;     // ... and their target values
     A.volume = volume;
     A.explicit_idx = explicit_idx;
     A.loss_sum = loss_sum;
@@ -490,6 +498,8 @@ extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, co
     A.sample_offset = sample_offset;
     A.step_dev = step_dev;
     A.step_stride = step_stride;
+    const int32_t unit[3] = {1, 1, 1};
+    if (!R) R = unit;
     A.n_voxels = (unsigned long long)R[0] * R[1] * R[2];
     float mx = 0.0f;
     for (int a = 0; a < 3; ++a) {
@@ -497,7 +507,7 @@ extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, co
         A.max_idx[a] = (float)R[a] - 1.0f;  // vol_res - 1 in fp32 (data/IndexDataset.py:57)
         if (A.max_idx[a] > mx) mx = A.max_idx[a];
     }
-    for (int a = 0; a < 3; ++a) A.scales[a] = A.max_idx[a] / mx;  // fp32 division (:65)
+    for (int a = 0; a < 3; ++a) A.scales[a] = mx > 0.0f ? A.max_idx[a] / mx : 1.0f;  // fp32 division (:65)
     A.n = n;
     A.grid = grid_cl;
     A.mlp = mlp;

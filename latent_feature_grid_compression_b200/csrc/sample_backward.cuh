@@ -7,8 +7,8 @@ namespace lfgc {
 struct BwdArgs {
     SampleParams P;
     // sample source
-    const float* coords;        // compat mode: [n][3]
-    const float* grad_out;      // compat mode: [n]
+    const float* coords;        // [n][3] positions: backward-only mode, or host-fed samples in fused mode
+    const float* grad_out;      // [n] d(loss)/d(out) in backward-only mode, target values in fused host-fed mode
     const float* volume;        // fused mode
     int R[3];
     float max_idx[3], scales[3];

@@ -277,7 +277,12 @@ __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_co
             const bool valid = s < A.n;
             float cx = 0.f, cy = 0.f, cz = 0.f, aux = 0.f;
             if (valid) {
-                if (FUSED) {
+                if (FUSED && A.coords) {  // host-fed step: caller-supplied positions and target values
+                    cx = __ldg(A.coords + 3 * s);
+                    cy = __ldg(A.coords + 3 * s + 1);
+                    cz = __ldg(A.coords + 3 * s + 2);
+                    if (half == 0) aux = __ldg(A.grad_out + s);
+                } else if (FUSED) {
                     unsigned long long v = A.explicit_idx ? (unsigned long long)A.explicit_idx[s]
                                                           : philox_voxel(A.seed, sample_base + (uint64_t)s, A.n_voxels);
                     const unsigned long long r12 = (unsigned long long)A.R[1] * A.R[2];

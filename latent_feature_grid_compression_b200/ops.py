@@ -219,14 +219,21 @@ def sample_backward(geom: Geometry, coords, grad_out, grid_cl, mlp_flat, grad_gr
 
 def train_step(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl, mlp_flat,
                grad_grid_cl, grad_mlp, loss_sum, workspace, explicit_idx=None, accumulate_mlp=False, step_dev=None,
-               step_stride: int = 0):
+               step_stride: int = 0, coords=None, targets=None):
+    """Fused sampler + forward + MSE + backward.  With ``coords`` (n,3) and ``targets`` (n,) the caller supplies the
+    samples (host-fed step) and ``volume`` may be None."""
     lib = L.load()
-    _req(volume, 'volume')
+    if volume is not None:
+        _req(volume, 'volume')
     if explicit_idx is not None:
         _req(explicit_idx, 'explicit_idx', torch.int64)
-    L.check(lib.lfgc_train_step(ct.byref(geom.model_desc), _p(volume), L.int3(volume.shape), int(n), int(seed),
-                                int(sample_offset), _p(step_dev), int(step_stride), _p(explicit_idx), float(loss_scale),
-                                _p(_req(grid_cl, 'grid_cl')),
+    if coords is not None:
+        _req(coords, 'coords')
+        _req(targets, 'targets')
+    shape3 = L.int3(volume.shape) if volume is not None else None
+    L.check(lib.lfgc_train_step(ct.byref(geom.model_desc), _p(volume), shape3, int(n), int(seed),
+                                int(sample_offset), _p(step_dev), int(step_stride), _p(explicit_idx), _p(coords),
+                                _p(targets), float(loss_scale), _p(_req(grid_cl, 'grid_cl')),
                                 _p(_req(mlp_flat, 'mlp')), _p(grad_grid_cl), _p(grad_mlp), _p(loss_sum),
                                 1 if accumulate_mlp else 0, _p(workspace), workspace.numel() * 4, _stream()),
             'lfgc_train_step')

@@ -111,14 +111,17 @@ class FastTrainer:
         self.workspace = torch.empty(self.geom.backward_workspace_bytes // 4, device=self.device)
         self.steps_done = 0
         self.launches_per_step = None
-        self._graph = None
+        self._graphs = {}
         self._use_graph = use_graph
+        # staging buffers of the host-fed step (step_host)
+        self._in_coords = torch.zeros((self.batch, 3), device=self.device, dtype=torch.float32)
+        self._in_targets = torch.zeros(self.batch, device=self.device, dtype=torch.float32)
 
     # ------------------------------------------------------------------------------------------------------------
     def grad_of(self, p):
         return self._grad_view[id(p)]
 
-    def _step_body(self):
+    def _step_body(self, host_fed=False):
         model, geom = self.model, self.geom
         specs = model.mask_specs()
         mults, auxs = _multipliers(specs)
@@ -130,7 +133,8 @@ class FastTrainer:
                        parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
                        parallel.loss_scale(self.batch, self.world), self.grid_cl,
                        self.mlp_flat, self.grad_grid, self.flat_g[self.mlp_off:], self.loss_sum, self.workspace,
-                       step_dev=self.step_dev, step_stride=n_global)
+                       step_dev=self.step_dev, step_stride=n_global,
+                       coords=self._in_coords if host_fed else None, targets=self._in_targets if host_fed else None)
         want = [s is not None and len(s.grad_params) > 0 for s in specs]
         _, gmults = ops.decode_bwd(geom, self.grad_grid, coeffs, auxs, want, scratch=self.scratch,
                                    grad_coeffs=[self.grad_of(p) for p in self.coeff_params])
@@ -153,8 +157,9 @@ class FastTrainer:
         ops.adam(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_dev, self.step_dev, self.betas[0],
                  self.betas[1], self.eps)
 
-    def capture(self):
-        """Warm up eagerly (counts launches), then record the step into a CUDA graph."""
+    def capture(self, host_fed=False):
+        """Warm up eagerly (counts launches), then record the step into a CUDA graph; the optimiser state the
+        warm-up touched is restored so that training starts from the initial state."""
         state = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.step_dev.clone())
         trackers = [(d.tracker.EMA.clone(), d.tracker.EMAVar.clone()) for d in self.model.drop
                     if isinstance(d, SmallifyDropout)]
@@ -163,15 +168,16 @@ class FastTrainer:
         with torch.cuda.stream(s):
             for _ in range(2):
                 before = ops.launch_count()
-                self._step_body()
+                self._step_body(host_fed)
                 self.launches_per_step = ops.launch_count() - before
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        graph = None
         if self._use_graph:
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._step_body()
-        # undo the warm-up / capture side effects so that training starts from the initial state
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._step_body(host_fed)
+        self._graphs[host_fed] = graph
         with torch.no_grad():
             self.flat_p.copy_(state[0])
             self.flat_m.copy_(state[1])
@@ -185,15 +191,28 @@ class FastTrainer:
                     d.tracker.EMAVar.copy_(var)
         torch.cuda.synchronize()
 
-    def step(self):
-        """One optimiser step over ``batch`` fresh samples per rank (asynchronous)."""
-        if self.launches_per_step is None:
-            self.capture()
-        if self._graph is not None:
-            self._graph.replay()
+    def _run(self, host_fed):
+        if host_fed not in self._graphs:
+            self.capture(host_fed)
+        g = self._graphs[host_fed]
+        if g is not None:
+            g.replay()
         else:
-            self._step_body()
+            self._step_body(host_fed)
         self.steps_done += 1
+
+    def step(self):
+        """One optimiser step over ``batch`` fresh samples per rank drawn on the device (asynchronous)."""
+        self._run(False)
+
+    def step_host(self, coords, targets):
+        """One optimiser step on caller-supplied samples -- the reference's DataLoader contract
+        (training/training.py:89-109): ``coords`` (batch, 3) normalised positions and ``targets`` (batch,) volume
+        values in HOST memory (pinned for asynchronous copies).  Two H2D copies + one graph replay; read the loss with
+        ``last_loss()`` (device -> host)."""
+        self._in_coords.copy_(coords.view(self.batch, 3), non_blocking=True)
+        self._in_targets.copy_(targets.view(self.batch), non_blocking=True)
+        self._run(True)
 
     def set_lr(self, lr: float):
         self.lr_dev.fill_(float(lr))

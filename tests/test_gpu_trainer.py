@@ -106,3 +106,22 @@ def test_store_and_restore_model_round_trip(tmp_path):
     tile = (torch.rand(1, 1, 6, 6, 6, 3, device='cuda') * 2 - 1)
     with torch.no_grad():
         assert float((r(tile) - m(tile)).abs().max()) < 0.2
+
+
+def test_host_fed_step_equals_device_sampled_step():
+    """FastTrainer.step_host on the samples the in-kernel sampler would draw == FastTrainer.step."""
+    from latent_feature_grid_compression_b200 import ops
+    from latent_feature_grid_compression_b200.training.fast_loop import FastTrainer
+    vol = _volume()
+    n, steps, seed = 3000, 6, 21
+    a = _make('', 4)
+    b = _make('', 4)
+    b.load_state_dict(copy.deepcopy(a.state_dict()))
+    ta = FastTrainer(a, vol, n, lr=0.008, seed=seed)
+    tb = FastTrainer(b, vol, n, lr=0.008, seed=seed)
+    for s in range(steps):
+        ta.step()
+        raw, norm, gt = ops.sample(vol.shape, n, seed=seed, sample_offset=s * n, volume=vol, want_gt=True)
+        tb.step_host(norm.cpu().pin_memory(), gt.cpu().pin_memory())
+        assert abs(ta.last_loss() - tb.last_loss()) <= 1e-5 * abs(ta.last_loss())
+    assert float((ta.flat_p - tb.flat_p).abs().max()) <= 1e-5 * float(ta.flat_p.abs().max())
