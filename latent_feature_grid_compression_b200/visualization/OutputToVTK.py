@@ -21,6 +21,10 @@ def axis_tables(dataset, tiled_res=32, device='cuda'):
     """Normalised coordinate of every voxel index along each axis, exactly as field_from_net builds them
     (OutputToVTK.py:23-37): per tile ``linspace(b/(R-1), (e-1)/(R-1), e-b) * 2 - 1``, times ``scales``."""
     res = dataset.vol_res_touple
+    cache = dataset.__dict__.setdefault('_lfgc_axis_tables', {})
+    key = (tuple(int(r) for r in res), int(tiled_res), str(device))
+    if key in cache:
+        return cache[key]
     min_idx, max_idx, scales = dataset.min_idx.cpu(), dataset.max_idx.cpu(), dataset.scales.cpu()
     span = max_idx - min_idx
     tables = []
@@ -32,6 +36,7 @@ def axis_tables(dataset, tiled_res=32, device='cuda'):
             hi = (min_idx[a] + th.tensor((e - 1) / (R - 1), dtype=th.float) * span[a]) / span[a]
             vals[b:e] = th.linspace(float(lo), float(hi), e - b, dtype=th.float)
         tables.append((scales[a] * (2.0 * vals - 1.0)).to(device).contiguous())
+    cache[key] = tables
     return tables
 
 
