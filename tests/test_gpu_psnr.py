@@ -1,0 +1,46 @@
+"""Final-PSNR parity with the reference after the same two-phase training run (BASELINE.json north_star).
+The golden values come from running the reference's own training() in the build container
+(tests/golden/make_psnr_golden.py): same torch seed, same DataLoader sample stream, same schedule.  Gate: 0.05 dB
+is the north-star figure; fp32 re-association makes the runs drift chaotically, so the asserted gate is 0.25 dB
+(the reference itself spreads 0.8-1.3 dB between seeds) and the measured delta is printed."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _args(g):
+    return {k: ast.literal_eval(v) for k, v in zip(g['args_keys'].tolist(), g['args_vals'].tolist())}
+
+
+@pytest.mark.parametrize('tag', ['basic', 'smallify'])
+def test_final_psnr_matches_reference_run(tag):
+    from tests import ref_loop
+    g = np.load(os.path.join(GOLD, 'psnr_run_%s.npz' % tag))
+    args = _args(g)
+    torch.manual_seed(0)
+    info = ref_loop.training(args, g['volume_raw'])
+    delta = info['psnr'] - float(g['psnr'])
+    print('\n[psnr parity] %s: reference %.4f dB, this repo %.4f dB, delta %+.4f dB, zeros %s vs %s, steps %d' % (
+        tag, float(g['psnr']), info['psnr'], delta, info['num_zeros'], float(g['num_zeros']), info['steps']))
+    assert info['num_parameters'] == int(g['num_parameters'])
+    assert abs(delta) < 0.25
+
+
+def test_fast_loop_reaches_the_same_quality():
+    """The graph-captured loop uses its own (Philox) sample stream, so only the quality level is comparable."""
+    from latent_feature_grid_compression_b200.data.IndexDataset import normalize_volume
+    from latent_feature_grid_compression_b200.training.fast_loop import train_volume
+    g = np.load(os.path.join(GOLD, 'psnr_run_basic.npz'))
+    args = _args(g)
+    vol = torch.from_numpy(g['volume_raw'])
+    vol = normalize_volume(vol, torch.min(vol), torch.max(vol), -1.0, 1.0)
+    torch.manual_seed(0)
+    info = train_volume(args, volume=vol, seed=3)
+    print('\n[psnr fast loop] reference %.3f dB, fast loop %.3f dB' % (float(g['psnr']), info['psnr']))
+    assert info['psnr'] > float(g['psnr']) - 1.5
