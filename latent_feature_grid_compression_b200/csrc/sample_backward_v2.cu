@@ -169,20 +169,16 @@ __device__ __forceinline__ void dw_block(const float* __restrict__ dzp, const fl
         for (int c = 0; c < 4; ++c) t[r][c] = make_float2(0.f, 0.f);
     dzp += n0;
     hp += n0;
-    // software pipeline: the loads of sample block i+1 are in flight while block i is multiplied
-    float4 dz[2], hv[4], dzn[2], hvn[4];
+    // software pipeline over two register buffers (A/B): the loads of sample block i+1 are in flight while block i
+    // is multiplied, without register copies
+    float4 dzA[2], hvA[4], dzB[2], hvB[4];
+    auto load = [&](float4 (&dz)[2], float4 (&hv)[4], int off) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) dz[r] = *reinterpret_cast<const float4*>(dzp + r * 4 * S);
+        for (int r = 0; r < 2; ++r) dz[r] = *reinterpret_cast<const float4*>(dzp + off + r * 4 * S);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) hv[c] = *reinterpret_cast<const float4*>(hp + c * 8 * S);
-    while (true) {
-        const bool more = n0 + step < TILE;
-        if (more) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) dzn[r] = *reinterpret_cast<const float4*>(dzp + step + r * 4 * S);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) hvn[c] = *reinterpret_cast<const float4*>(hp + step + c * 8 * S);
-        }
+        for (int c = 0; c < 4; ++c) hv[c] = *reinterpret_cast<const float4*>(hp + off + c * 8 * S);
+    };
+    auto mac = [&](const float4 (&dz)[2], const float4 (&hv)[4]) {
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -190,14 +186,18 @@ __device__ __forceinline__ void dw_block(const float* __restrict__ dzp, const fl
                 ffma2v(t[r][c], make_float2(dz[r].x, dz[r].y), make_float2(hv[c].x, hv[c].y));
                 ffma2v(t[r][c], make_float2(dz[r].z, dz[r].w), make_float2(hv[c].z, hv[c].w));
             }
-        if (!more) break;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) dz[r] = dzn[r];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) hv[c] = hvn[c];
-        n0 += step;
-        dzp += step;
-        hp += step;
+    };
+    load(dzA, hvA, 0);
+    while (true) {
+        if (n0 + step < TILE) load(dzB, hvB, step);
+        mac(dzA, hvA);
+        if (n0 + step >= TILE) break;
+        if (n0 + 2 * step < TILE) load(dzA, hvA, 2 * step);
+        mac(dzB, hvB);
+        if (n0 + 2 * step >= TILE) break;
+        n0 += 2 * step;
+        dzp += 2 * step;
+        hp += 2 * step;
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r)

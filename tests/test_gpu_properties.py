@@ -14,7 +14,8 @@ def _model(C, G, wavelet='db2', H=32, L=4, F=2, seed=0):
     return setup_model(3, H, 1, L, 'fourier', F, '', 0.1, 0.9, wavelet, C, G, '').cuda().train()
 
 
-@pytest.mark.parametrize('C,G,wavelet', [(16, 15, 'db2'), (32, 64, 'db2'), (6, 21, 'db3'), (4, 24, 'db4'), (8, 32, 'haar')])
+@pytest.mark.parametrize('C,G,wavelet', [(16, 15, 'db2'), (32, 64, 'db2'), (6, 21, 'db3'), (4, 24, 'db4'), (8, 32, 'haar'),
+                                            (5, 12, 'db3'), (3, 14, 'db4'), (7, 16, 'haar')])
 def test_synthesis_adjoint_and_perfect_reconstruction(C, G, wavelet):
     from latent_feature_grid_compression_b200 import ops
     m = _model(C, G, wavelet)
