@@ -417,219 +417,6 @@ __global__ void dwt_level_kernel(DwtArgs A) {
     A.out[idx] = acc;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Small grids (the shipped configs: G = 15): all synthesis levels of one channel in ONE CTA, intermediates in shared
-// memory -- one launch per direction instead of one per level.  grid = Cp CTAs (pad channels only write zeros).
-// ---------------------------------------------------------------------------------------------------------------
-struct FusedArgs {
-    int n_coeff, C, Cp, ntaps, accumulate;
-    int d[LFGC_MAX_LEVELS][3], t[LFGC_MAX_LEVELS][3], off[LFGC_MAX_LEVELS][3];
-    float lo[LFGC_MAX_TAPS], hi[LFGC_MAX_TAPS];
-    const float* coeff[LFGC_MAX_LEVELS];
-    const float* mult[LFGC_MAX_LEVELS];     // forward: value multipliers; backward: gradient multipliers
-    float* grid_cl;                          // forward output / backward input (d grid)
-    float* also_zero;
-    float* gcoeff[LFGC_MAX_LEVELS];
-    float* gmult[LFGC_MAX_LEVELS];
-    int buf_elems;                           // floats per shared-memory buffer
-};
-
-template <int NT>
-__global__ void __launch_bounds__(256) decode_fused_fwd_kernel(const __grid_constant__ FusedArgs A) {
-    extern __shared__ float sm[];
-    float* cur = sm;
-    float* nxt = sm + A.buf_elems;
-    const int c = blockIdx.x;
-    const int last = A.n_coeff - 1;
-    const int64_t gvol = (int64_t)A.t[last][0] * A.t[last][1] * A.t[last][2];
-    if (c >= A.C) {  // pad channel
-        for (int64_t p = threadIdx.x; p < gvol; p += blockDim.x) {
-            A.grid_cl[p * A.Cp + c] = 0.0f;
-            if (A.also_zero) A.also_zero[p * A.Cp + c] = 0.0f;
-        }
-        return;
-    }
-    {
-        const int dv = A.d[0][0] * A.d[0][1] * A.d[0][2];
-        const float* src = A.coeff[0] + (int64_t)c * dv;
-        for (int b = threadIdx.x; b < dv; b += blockDim.x) cur[b] = A.mult[0] ? src[b] * A.mult[0][b] : src[b];
-    }
-    __syncthreads();
-    for (int l = 1; l <= last; ++l) {
-        const int d0 = A.d[l][0], d1 = A.d[l][1], d2 = A.d[l][2];
-        const int t0 = A.t[l][0], t1 = A.t[l][1], t2 = A.t[l][2];
-        const int dv = d0 * d1 * d2;
-        const float* high = A.coeff[l] + (int64_t)c * 7 * dv;
-        const float* mh = A.mult[l];
-        for (int p = threadIdx.x; p < t0 * t1 * t2; p += blockDim.x) {
-            const int o[3] = {p / (t1 * t2) + A.off[l][0], (p / t2) % t1 + A.off[l][1], p % t2 + A.off[l][2]};
-            const int dd[3] = {d0, d1, d2};
-            float acc = 0.0f;
-            if (NT > 0) {
-                constexpr int NP = NT > 0 ? NT / 2 : 1;
-                int ii[3][NP];
-                float wl[3][NP], wh[3][NP];
-#pragma unroll
-                for (int ax = 0; ax < 3; ++ax)
-#pragma unroll
-                    for (int a = 0; a < NP; ++a) {
-                        const int i = (o[ax] >> 1) - a, tp = (o[ax] & 1) + 2 * a;
-                        const bool ok = i >= 0 && i < dd[ax];
-                        ii[ax][a] = ok ? i : 0;
-                        wl[ax][a] = ok ? A.lo[tp] : 0.0f;
-                        wh[ax][a] = ok ? A.hi[tp] : 0.0f;
-                    }
-#pragma unroll
-                for (int az = 0; az < NP; ++az)
-#pragma unroll
-                    for (int ay = 0; ay < NP; ++ay)
-#pragma unroll
-                        for (int axx = 0; axx < NP; ++axx) {
-                            const int b = (ii[0][az] * d1 + ii[1][ay]) * d2 + ii[2][axx];
-                            acc = fmaf(cur[b], wl[0][az] * wl[1][ay] * wl[2][axx], acc);
-#pragma unroll
-                            for (int k = 1; k < 8; ++k) {
-                                float v = __ldg(high + (k - 1) * dv + b);
-                                if (mh) v *= __ldg(mh + (k - 1) * dv + b);
-                                acc = fmaf(v, ((k & 4) ? wh[0][az] : wl[0][az]) * ((k & 2) ? wh[1][ay] : wl[1][ay]) *
-                                                  ((k & 1) ? wh[2][axx] : wl[2][axx]), acc);
-                            }
-                        }
-            } else {
-                const int nt = A.ntaps;
-                auto lo_i = [&](int q) { int v = q - nt + 1; return v <= 0 ? 0 : (v + 1) >> 1; };
-                for (int iz = lo_i(o[0]); iz <= min(d0 - 1, o[0] >> 1); ++iz)
-                    for (int iy = lo_i(o[1]); iy <= min(d1 - 1, o[1] >> 1); ++iy)
-                        for (int ix = lo_i(o[2]); ix <= min(d2 - 1, o[2] >> 1); ++ix) {
-                            const int tz = o[0] - 2 * iz, ty = o[1] - 2 * iy, tx = o[2] - 2 * ix;
-                            const int b = (iz * d1 + iy) * d2 + ix;
-                            acc = fmaf(cur[b], A.lo[tz] * A.lo[ty] * A.lo[tx], acc);
-                            for (int k = 1; k < 8; ++k) {
-                                float v = __ldg(high + (k - 1) * dv + b);
-                                if (mh) v *= __ldg(mh + (k - 1) * dv + b);
-                                acc = fmaf(v, ((k & 4) ? A.hi[tz] : A.lo[tz]) * ((k & 2) ? A.hi[ty] : A.lo[ty]) *
-                                                  ((k & 1) ? A.hi[tx] : A.lo[tx]), acc);
-                            }
-                        }
-            }
-            nxt[p] = acc;
-        }
-        __syncthreads();
-        float* tmp = cur; cur = nxt; nxt = tmp;
-    }
-    for (int64_t p = threadIdx.x; p < gvol; p += blockDim.x) {
-        A.grid_cl[p * A.Cp + c] = cur[p];
-        if (A.also_zero) A.also_zero[p * A.Cp + c] = 0.0f;
-    }
-}
-
-template <int NT>
-__global__ void __launch_bounds__(256) decode_fused_bwd_kernel(const __grid_constant__ FusedArgs A) {
-    extern __shared__ float sm[];
-    float* cur = sm;
-    float* nxt = sm + A.buf_elems;
-    const int c = blockIdx.x;  // grid = C CTAs
-    const int last = A.n_coeff - 1;
-    const int64_t gvol = (int64_t)A.t[last][0] * A.t[last][1] * A.t[last][2];
-    for (int64_t p = threadIdx.x; p < gvol; p += blockDim.x) cur[p] = A.grid_cl[p * A.Cp + c];
-    __syncthreads();
-    for (int l = last; l >= 1; --l) {
-        const int d0 = A.d[l][0], d1 = A.d[l][1], d2 = A.d[l][2];
-        const int t0 = A.t[l][0], t1 = A.t[l][1], t2 = A.t[l][2];
-        const int dv = d0 * d1 * d2;
-        for (int idx = threadIdx.x; idx < 8 * dv; idx += blockDim.x) {
-            const int k = idx / dv, b = idx % dv;
-            const int i3[3] = {b / (d1 * d2), (b / d2) % d1, b % d2};
-            const float* f3[3] = {(k & 4) ? A.hi : A.lo, (k & 2) ? A.hi : A.lo, (k & 1) ? A.hi : A.lo};
-            const int tt[3] = {t0, t1, t2};
-            float g = 0.0f;
-            if (NT > 0) {
-                int pp[3][NT > 0 ? NT : 1];
-                float ww[3][NT > 0 ? NT : 1];
-#pragma unroll
-                for (int ax = 0; ax < 3; ++ax)
-#pragma unroll
-                    for (int tp = 0; tp < NT; ++tp) {
-                        const int q = 2 * i3[ax] + tp - A.off[l][ax];
-                        const bool ok = q >= 0 && q < tt[ax];
-                        pp[ax][tp] = ok ? q : 0;
-                        ww[ax][tp] = ok ? f3[ax][tp] : 0.0f;
-                    }
-#pragma unroll
-                for (int tz = 0; tz < NT; ++tz)
-#pragma unroll
-                    for (int ty = 0; ty < NT; ++ty) {
-                        const float wzy = ww[0][tz] * ww[1][ty];
-                        const int rowp = (pp[0][tz] * t1 + pp[1][ty]) * t2;
-#pragma unroll
-                        for (int tx = 0; tx < NT; ++tx) g = fmaf(cur[rowp + pp[2][tx]], wzy * ww[2][tx], g);
-                    }
-            } else {
-                for (int tz = 0; tz < A.ntaps; ++tz) {
-                    const int pz = 2 * i3[0] + tz - A.off[l][0];
-                    if (pz < 0 || pz >= t0) continue;
-                    for (int ty = 0; ty < A.ntaps; ++ty) {
-                        const int py = 2 * i3[1] + ty - A.off[l][1];
-                        if (py < 0 || py >= t1) continue;
-                        for (int tx = 0; tx < A.ntaps; ++tx) {
-                            const int px = 2 * i3[2] + tx - A.off[l][2];
-                            if (px < 0 || px >= t2) continue;
-                            g = fmaf(cur[(pz * t1 + py) * t2 + px], f3[0][tz] * f3[1][ty] * f3[2][tx], g);
-                        }
-                    }
-                }
-            }
-            if (k == 0) {
-                if (l == 1) {
-                    const int64_t o = (int64_t)c * dv + b;
-                    if (A.gmult[0]) atomicAdd(A.gmult[0] + b, A.coeff[0][o] * g);
-                    const float v = A.mult[0] ? g * A.mult[0][b] : g;
-                    A.gcoeff[0][o] = A.accumulate ? A.gcoeff[0][o] + v : v;
-                } else {
-                    nxt[b] = g;
-                }
-            } else {
-                const int64_t o = ((int64_t)c * 7 + (k - 1)) * dv + b;
-                if (A.gmult[l]) atomicAdd(A.gmult[l] + (k - 1) * dv + b, A.coeff[l][o] * g);
-                const float v = A.mult[l] ? g * A.mult[l][(k - 1) * dv + b] : g;
-                A.gcoeff[l][o] = A.accumulate ? A.gcoeff[l][o] + v : v;
-            }
-        }
-        __syncthreads();
-        float* tmp = cur; cur = nxt; nxt = tmp;
-    }
-}
-
-// the fused path is taken when two per-channel volumes fit comfortably in shared memory and the serial work per CTA
-// stays small
-static bool fused_applicable(const lfgc_wavelet_desc* w, int* buf_elems) {
-    if (w->n_coeff < 2) return false;
-    int64_t mx = (int64_t)w->dims[0][0] * w->dims[0][1] * w->dims[0][2];
-    for (int l = 1; l < w->n_coeff; ++l) {
-        const int64_t v = (int64_t)w->target[l][0] * w->target[l][1] * w->target[l][2];
-        if (v > mx) mx = v;
-    }
-    if (mx > 8192) return false;
-    *buf_elems = (int)((mx + 3) & ~3);
-    return true;
-}
-
-static void fill_fused(const lfgc_wavelet_desc* w, FusedArgs& A, int Cp) {
-    A.n_coeff = w->n_coeff;
-    A.C = w->C;
-    A.Cp = Cp;
-    A.ntaps = w->n_taps;
-    for (int l = 0; l < LFGC_MAX_LEVELS; ++l) {
-        A.coeff[l] = nullptr; A.mult[l] = nullptr; A.gcoeff[l] = nullptr; A.gmult[l] = nullptr;
-        for (int a = 0; a < 3; ++a) {
-            A.d[l][a] = l < w->n_coeff ? w->dims[l][a] : 0;
-            A.t[l][a] = (l >= 1 && l < w->n_coeff) ? w->target[l][a] : 0;
-            A.off[l][a] = (l >= 1 && l < w->n_coeff) ? (2 * A.d[l][a] + A.ntaps - 2 - A.t[l][a]) / 2 : 0;
-        }
-    }
-    for (int i = 0; i < LFGC_MAX_TAPS; ++i) { A.lo[i] = w->rec_lo[i]; A.hi[i] = w->rec_hi[i]; }
-}
-
 static int check_desc(const lfgc_wavelet_desc* w) {
     if (!w) return fail(LFGC_E_INVALID, "wavelet desc is null");
     if (w->n_coeff < 1 || w->n_coeff > LFGC_MAX_LEVELS) return fail(LFGC_E_INVALID, "n_coeff=%d out of range", w->n_coeff);
@@ -717,24 +504,6 @@ extern "C" int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* c
         LFGC_LAUNCH_OK();
         return LFGC_OK;
     }
-    {
-        int be = 0;
-        if (fused_applicable(w, &be)) {
-            FusedArgs F;
-            fill_fused(w, F, Cp);
-            for (int l = 0; l < w->n_coeff; ++l) { F.coeff[l] = coeff[l]; F.mult[l] = mult ? mult[l] : nullptr; }
-            F.grid_cl = grid_cl;
-            F.also_zero = also_zero;
-            F.accumulate = 0;
-            F.buf_elems = be;
-            const size_t smem = 2 * (size_t)be * sizeof(float);
-            auto kern = w->n_taps == 2 ? decode_fused_fwd_kernel<2> : (w->n_taps == 4 ? decode_fused_fwd_kernel<4> : decode_fused_fwd_kernel<0>);
-            LFGC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<Cp, 256, smem, st>>>(F);
-            LFGC_LAUNCH_OK();
-            return LFGC_OK;
-        }
-    }
     const size_t inter = intermediate_elems(w);
     if (inter && !scratch) return fail(LFGC_E_WORKSPACE, "decode_fwd: scratch required");
     float* buf[2] = {scratch, scratch ? scratch + inter : nullptr};
@@ -784,34 +553,6 @@ extern "C" int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_gri
             Cp, nvox, accumulate);
         LFGC_LAUNCH_OK();
         return LFGC_OK;
-    }
-    {
-        int be = 0;
-        if (fused_applicable(w, &be)) {
-            FusedArgs F;
-            fill_fused(w, F, Cp);
-            for (int l = 0; l < w->n_coeff; ++l) {
-                if (!grad_coeff[l]) return fail(LFGC_E_INVALID, "decode_bwd: grad_coeff[%d] null", l);
-                F.coeff[l] = coeff[l];
-                F.mult[l] = gmul ? gmul[l] : nullptr;
-                F.gcoeff[l] = grad_coeff[l];
-                F.gmult[l] = grad_mult ? grad_mult[l] : nullptr;
-                if (F.gmult[l] && !accumulate) {
-                    const size_t dv = (size_t)w->dims[l][0] * w->dims[l][1] * w->dims[l][2];
-                    LFGC_CUDA_OK(cudaMemsetAsync(F.gmult[l], 0, (l == 0 ? dv : 7 * dv) * sizeof(float), st));
-                }
-            }
-            F.grid_cl = const_cast<float*>(grad_grid_cl);
-            F.also_zero = nullptr;
-            F.accumulate = accumulate;
-            F.buf_elems = be;
-            const size_t smem = 2 * (size_t)be * sizeof(float);
-            auto kern = w->n_taps == 2 ? decode_fused_bwd_kernel<2> : (w->n_taps == 4 ? decode_fused_bwd_kernel<4> : decode_fused_bwd_kernel<0>);
-            LFGC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<w->C, 256, smem, st>>>(F);
-            LFGC_LAUNCH_OK();
-            return LFGC_OK;
-        }
     }
     const size_t inter = intermediate_elems(w);
     if (inter && !scratch) return fail(LFGC_E_WORKSPACE, "decode_bwd: scratch required");
