@@ -64,11 +64,15 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterp
 // reduction slowly loses bits; MLP pre-activations and embedding arguments are orders of magnitude smaller).
 // About 20 instructions for both values and no divergent slow path, unlike sincosf.
 __device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
-    const float n = rintf(x * 0.636619772f);  // x * 2/pi
+    // n = rint(x * 2/pi) by the magic-number trick (two FADDs on the FMA pipe instead of FRND + F2I on the
+    // quarter-rate conversion unit); the low mantissa bits of the biased sum are the quadrant.  Valid for
+    // |x * 2/pi| < 2^22, far beyond the 1e4 the reduction below is accurate for.
+    const float biased = __fadd_rn(__fmul_rn(x, 0.636619772f), 12582912.0f);  // 1.5 * 2^23
+    const int q = __float_as_int(biased);
+    const float n = __fsub_rn(biased, 12582912.0f);
     float r = fmaf(n, -1.57079601e+00f, x);
     r = fmaf(n, -3.13916473e-07f, r);
     r = fmaf(n, -5.39030253e-15f, r);
-    const int q = __float2int_rn(n);
     const float r2 = r * r;
     float ps = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
     ps = fmaf(ps, r2, -1.66666546e-1f);

@@ -12,7 +12,18 @@
 // persistent loop.
 #include "sample_common.cuh"
 
+#include <stdlib.h>
+
 namespace lfgc {
+
+// tensor-core variant (sample_forward_tc.cu); returns 1 when the shape is not covered
+int launch_forward_tc(const SampleParams& P, const float* coords, const float* const axis[3], int R1, int R2,
+                      int64_t first, int64_t n, const float* grid, const float* mlp, float* out, cudaStream_t st);
+
+static bool forward_tc_enabled() {
+    const char* e = getenv("LFGC_FORWARD_TC");  // "0" forces the FFMA2 kernel, "1" the tcgen05 kernel
+    return e ? (e[0] != '0') : false;
+}
 
 struct FwdArgs {
     SampleParams P;
@@ -178,6 +189,10 @@ extern "C" int lfgc_forward(const lfgc_model_desc* m, const float* coords, int64
     A.grid = grid_cl;
     A.mlp = mlp;
     A.out = out;
+    if (forward_tc_enabled()) {
+        rc = launch_forward_tc(A.P, coords, nullptr, 1, 1, 0, n, grid_cl, mlp, out, (cudaStream_t)stream);
+        if (rc != 1) return rc;
+    }
     if (m->H <= 32) return launch_forward<32, 0>(A, (cudaStream_t)stream);
     return launch_forward<64, 0>(A, (cudaStream_t)stream);
 }
@@ -202,6 +217,10 @@ extern "C" int lfgc_reconstruct(const lfgc_model_desc* m, const float* grid_cl, 
     A.grid = grid_cl;
     A.mlp = mlp;
     A.out = out_slab;
+    if (forward_tc_enabled()) {
+        rc = launch_forward_tc(A.P, nullptr, A.axis, A.R1, A.R2, A.first, A.n, grid_cl, mlp, out_slab, (cudaStream_t)stream);
+        if (rc != 1) return rc;
+    }
     if (m->H <= 32) return launch_forward<32, 1>(A, (cudaStream_t)stream);
     return launch_forward<64, 1>(A, (cudaStream_t)stream);
 }
