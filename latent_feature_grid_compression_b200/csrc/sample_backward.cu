@@ -17,6 +17,8 @@
 // slices (deterministic, no atomics on the MLP gradient).
 #include "sample_backward.cuh"
 
+#include <stdlib.h>
+
 namespace lfgc {
 
 constexpr int kS = 132;  // row stride (floats) of the activation rows
@@ -385,6 +387,13 @@ void launch_reduce_partials(const float* partial, int nslices, int pstride, int 
 template <int HP, int FUSED>
 static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
                            cudaStream_t st) {
+    {
+        const char* e = getenv("LFGC_BACKWARD_TC");
+        if (e && e[0] == '1') {
+            const int rc = launch_backward_tc(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
+            if (rc != 1) return rc;
+        }
+    }
     {
         const int rc = launch_backward_v2(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
         if (rc != 1) return rc;

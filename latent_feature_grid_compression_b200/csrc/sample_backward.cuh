@@ -33,6 +33,10 @@ int launch_backward_v2(BwdArgs& A, int fused, float* grad_mlp, int accumulate, v
                        cudaStream_t st);
 size_t backward_v2_workspace_floats(int pcount, int sms);
 
+// Tensor-core kernel (sample_backward_tc.cu: tcgen05 3xTF32 for every contraction).  Same return convention.
+int launch_backward_tc(BwdArgs& A, int fused, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st);
+
 // grad[i] (+)= sum_b partial[b][i] for i < pcount; loss_out[0] = sum_b partial[b][pcount] (fixed order: deterministic)
 void launch_reduce_partials(const float* partial, int nslices, int pstride, int pcount, float* grad, int accumulate,
                             float* loss_out, cudaStream_t st);

@@ -1,0 +1,700 @@
+// Fused training kernel, tensor-core variant: every contraction of the forward AND the backward pass runs on tcgen05
+// (5th-generation tensor cores, accumulators in TMEM) in 3xTF32 split precision, which keeps fp32-level accuracy (the
+// 1e-5 gradient gate) while taking all multiply-accumulates off the CUDA cores.  What is left for the SM's issue slots
+// is the per-sample work: gather, Fourier features, SnakeAlt and its derivative, the hi/lo splits and the scatter --
+// about a quarter of the instructions of the FFMA2 kernel (sample_backward_v2.cu).
+//
+//   tile = 128 samples = the 128 TMEM lanes; TPS threads share one sample (thread (s, q) owns 32/TPS of the 32 hidden
+//   columns), so a CTA is 128*TPS threads.  The kernel owns all 512 TMEM columns of its SM (one CTA per SM):
+//       [  0, 32)  working accumulator: z_l in the forward, dh_l / d(features) in the backward
+//       [ 32, 96)  h_0, the layer-0 input row (fp32)      [ 96,192)  h_1 .. h_3 (fp32)
+//       [192,320)  S'(z_l) of every layer                   [320,448)  dW_l^T accumulators, one 32-column block per layer
+//   Forward, layer l:      z_l = h_l W_l^T          A = h_l  K-major panels (hi/lo), B = W_l  K-major panels
+//   Backward, layer l:     dh_l = dz_l W_l          A = dz_l K-major panels,         B = W_l^T K-major panels
+//                          dW_l^T += [h_l | 1]^T dz_l   A = h_l  MN-major,             B = dz_l MN-major, K = the 128 samples
+//   The weight-gradient accumulators stay in TMEM across the whole persistent loop and leave the SM once.  The ones
+//   column appended to h_l (row 63 of the accumulator) makes the bias gradient part of the same MMA.
+//
+//   tf32 operands read MN-major (contraction over the samples) only work in the SWIZZLE_128B_BASE32B layout on sm_100a
+//   (measured, dbg/umma_addr.cu: every other layout type returns zeros for kind::tf32 with a transposed operand):
+//       element (mn, k) at (mn/32)*LBO + (k/4)*SBO + (k%4)*128 + (((mn%32)/8) ^ (k%4))*32 + (mn%8)*4
+//   i.e. a row-major [sample][32 columns] block whose 32-byte chunks are XOR-swizzled by (sample & 3).  The K-major
+//   operands use the unswizzled 16-byte "chunk panel" layout of sample_forward_tc.cu, so h_l and dz_l are written in
+//   both formats (the forward only in the K-major one; h_l is re-split from its fp32 copy in TMEM in the backward).
+//
+// Layer-0 columns are permuted as in the forward kernel: k = [features (Cp) | xyz | Fourier | zero pad to K0p].
+#include "sample_backward.cuh"
+
+#include <stdlib.h>
+
+#ifdef LFGC_PHASE_TIMING
+__device__ unsigned long long g_btc_cycles[16];
+#define BT_DECL long long _tl = clock64(); unsigned long long _tp[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0};
+#define BT_MARK(i) { long long _n = clock64(); _tp[i] += (unsigned long long)(_n - _tl); _tl = _n; }
+#define BT_FLUSH() { if (threadIdx.x == 0) for (int _i = 0; _i < 16; ++_i) atomicAdd(&g_btc_cycles[_i], _tp[_i]); }
+#else
+#define BT_DECL
+#define BT_MARK(i)
+#define BT_FLUSH()
+#endif
+
+namespace lfgc {
+namespace btc {
+
+constexpr int HP = 32;
+constexpr int TILE = 128;
+constexpr int LMAX = 4;
+constexpr int kPanelA = TILE * 16;   // bytes per K chunk (4 columns) of a K-major activation operand
+constexpr int kPanelW = HP * 16;     // bytes per K chunk of a forward weight operand (32 rows)
+constexpr int kBlkMN = TILE * 128;   // bytes of one MN-major [128 samples][32 columns] block
+constexpr int kOnesRow = 63;         // accumulator row that receives the bias gradient (column 31 of MN group 1)
+
+// TMEM column map
+constexpr int cAcc = 0, cH0 = 32, cH1 = 96, cS = 192, cW = 320, kTmemCols = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE descriptor (cute::UMMA::SmemDescriptor bit layout, version 1)
+__device__ __forceinline__ uint64_t desc_k(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// MN-major, SWIZZLE_128B_BASE32B: LBO = bytes between 32-column groups, SBO = bytes between 4-sample atoms
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((kBlkMN >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((512 >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// kind::tf32, fp32 accumulate, M = 128
+__host__ __device__ constexpr uint32_t idesc(int N, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(id), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);  // round to nearest tf32
+    lo = x - hi;                                                         // exact in fp32
+}
+__device__ __forceinline__ void split4(const float4& a, float4& hi, float4& lo) {
+    split_tf32(a.x, hi.x, lo.x);
+    split_tf32(a.y, hi.y, lo.y);
+    split_tf32(a.z, hi.z, lo.z);
+    split_tf32(a.w, hi.w, lo.w);
+}
+
+// Bounded wait: a lost completion traps (reported as a launch failure) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 2000000000ll) __trap();   // ~1 s
+    }
+}
+
+// ---- TMEM <-> registers (32 lanes x 32 bit, N consecutive columns) ----------------------------------------------------
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_st<4>(uint32_t taddr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st<8>(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st<16>(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::
+            "r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- shared-memory layout (bytes) ---------------------------------------------------------------------------------------
+struct Layout {
+    int ctrl, bias, wf, yx, Hm, Hk, Dk, Wf, Wb, total;
+    int chunksA;   // K chunks of the K-major activation operand = max(K0p, HP) / 4
+    int Np0;       // rows of the layer-0 backward weight operand (feature columns, multiple of 16)
+    int wb0;       // bytes of the layer-0 backward weight operand (one of hi / lo)
+    int wfBytes, wbBytes;  // bytes of one of hi / lo
+};
+
+__host__ __device__ inline Layout make_layout(const SampleParams& P, int K0p, int tps) {
+    Layout o;
+    o.chunksA = (K0p > HP ? K0p : HP) / 4;
+    o.Np0 = (P.Cp + 15) & ~15;
+    o.wb0 = (HP / 4) * o.Np0 * 16;
+    o.wfBytes = (K0p + (P.L - 1) * HP) / 4 * kPanelW;
+    o.wbBytes = o.wb0 + (P.L - 1) * (HP / 4) * kPanelW;
+    int p = 0;
+    o.ctrl = p; p += 64;                      // [0,8) mbarrier, [8,12) TMEM base
+    o.bias = p; p += LMAX * HP * 4;
+    o.wf = p;   p += (HP + 4) * 4;
+    o.yx = p;   p += tps * TILE * 4;          // partial outputs of the threads sharing a sample
+    p = (p + 1023) & ~1023;
+    o.Hm = p;   p += 4 * kBlkMN;              // MN-major [h hi g0 | h hi g1 (+ones) | h lo g0 | h lo g1]
+    o.Hk = p;                                 // K-major h_l (hi | lo), forward only; the backward's MN-major dz (hi | lo)
+    {                                         // lives in the same bytes
+        const int hk = 2 * o.chunksA * kPanelA, dm = 2 * kBlkMN;
+        p += hk > dm ? hk : dm;
+    }
+    o.Dk = p;   p += 2 * (HP / 4) * kPanelA;  // K-major dz_l (hi | lo); also the end-of-kernel reduction scratch
+    o.Wf = p;   p += 2 * o.wfBytes;
+    o.Wb = p;   p += 2 * o.wbBytes;
+    o.total = p;
+    return o;
+}
+
+// byte offset of column j (0..31) of sample s inside an MN-major block
+__device__ __forceinline__ int mn_off(int s, int j) { return s * 128 + ((((j >> 3) ^ s) & 3) << 5) + ((j & 7) << 2); }
+
+template <int FUSED, int TPS>
+__global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid_constant__ BwdArgs A, const int K0p) {
+    constexpr int CW = HP / TPS;   // hidden columns per thread
+    constexpr int NT = TILE * TPS;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    BT_DECL
+    const SampleParams& P = A.P;
+    const Layout Lo = make_layout(P, K0p, TPS);
+    float* bias = reinterpret_cast<float*>(smem + Lo.bias);
+    float* wfs = reinterpret_cast<float*>(smem + Lo.wf);
+    float* yx = reinterpret_cast<float*>(smem + Lo.yx);
+    unsigned char* Hm = smem + Lo.Hm;
+    unsigned char* HkHi = smem + Lo.Hk;
+    unsigned char* HkLo = HkHi + Lo.chunksA * kPanelA;
+    unsigned char* DmHi = smem + Lo.Hk;       // aliases the forward operand (dead once the last forward MMA completed)
+    unsigned char* DmLo = DmHi + kBlkMN;
+    unsigned char* DkHi = smem + Lo.Dk;
+    unsigned char* DkLo = DkHi + (HP / 4) * kPanelA;
+    unsigned char* WfHi = smem + Lo.Wf;
+    unsigned char* WfLo = WfHi + Lo.wfBytes;
+    unsigned char* WbHi = smem + Lo.Wb;
+    unsigned char* WbLo = WbHi + Lo.wbBytes;
+    const uint32_t bar = smem_u32(smem + Lo.ctrl);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Lo.ctrl + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp >> 2;                  // which share of the columns
+    const int s = ((warp & 3) << 5) | lane;   // sample within the tile = TMEM lane
+    const int col0 = q * CW;                  // first hidden column of this thread
+    const int H = P.H, in0 = P.in0, L = P.L;
+    const int nfix = 3 + 6 * P.F;
+    const int Cp = P.Cp;
+
+    // ---- one-time setup ------------------------------------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    for (int e = Lo.Hm / 4 + threadIdx.x; e < Lo.total / 4; e += NT) reinterpret_cast<float*>(smem)[e] = 0.0f;
+    __syncthreads();
+    // ones column (column 31 of group 1 of the hi block): bias gradient row of every dW accumulator
+    for (int r = threadIdx.x; r < TILE; r += NT) *reinterpret_cast<float*>(Hm + kBlkMN + mn_off(r, 31)) = 1.0f;
+    for (int l = 0; l < L; ++l) {
+        const int K = l == 0 ? in0 : H;
+        const float* W = A.mlp + mlp_w_off(l, in0, H);
+        const int fbase = (l == 0 ? 0 : (K0p + (l - 1) * HP) / 4) * kPanelW;
+        const int bbase = l == 0 ? 0 : Lo.wb0 + (l - 1) * (HP / 4) * kPanelW;
+        const int brows = l == 0 ? Lo.Np0 : HP;
+        for (int e = threadIdx.x; e < H * K; e += NT) {
+            const int j = e / K, r = e - j * K;
+            int k = r;
+            if (l == 0) k = r < nfix ? Cp + r : r - nfix;  // permuted layer-0 columns
+            float hi, lo;
+            split_tf32(__ldg(W + e), hi, lo);
+            const int fo = fbase + (k >> 2) * kPanelW + j * 16 + (k & 3) * 4;          // forward: B[n = j][K = k]
+            *reinterpret_cast<float*>(WfHi + fo) = hi;
+            *reinterpret_cast<float*>(WfLo + fo) = lo;
+            if (l > 0 || k < Cp) {                                                     // backward: B[n = k][K = j]
+                const int bo = bbase + (j >> 2) * brows * 16 + k * 16 + (j & 3) * 4;
+                *reinterpret_cast<float*>(WbHi + bo) = hi;
+                *reinterpret_cast<float*>(WbLo + bo) = lo;
+            }
+        }
+        const float* b = A.mlp + mlp_b_off(l, in0, H);
+        for (int j = threadIdx.x; j < HP; j += NT) bias[l * HP + j] = j < H ? __ldg(b + j) : 0.0f;
+    }
+    {
+        const float* wf = A.mlp + mlp_wf_off(L, in0, H);
+        for (int j = threadIdx.x; j < HP; j += NT) wfs[j] = j < H ? __ldg(wf + j) : 0.0f;
+        if (threadIdx.x == 0) wfs[HP] = __ldg(wf + H);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's lane quarter
+    const float bf = wfs[HP];
+    const uint32_t aHkHi = smem_u32(HkHi), aHkLo = smem_u32(HkLo), aDkHi = smem_u32(DkHi), aDkLo = smem_u32(DkLo);
+    const uint32_t aHmHi = smem_u32(Hm), aHmLo = smem_u32(Hm + 2 * kBlkMN), aDmHi = smem_u32(DmHi), aDmLo = smem_u32(DmLo);
+    const uint32_t aWfHi = smem_u32(WfHi), aWfLo = smem_u32(WfLo), aWbHi = smem_u32(WbHi), aWbLo = smem_u32(WbLo);
+    uint32_t parity = 0;
+    bool first_tile = true;
+
+    float accWf[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) accWf[i] = 0.0f;
+    float accbf = 0.0f, loss_part = 0.0f;
+
+    uint64_t sample_base = A.sample_offset;
+    if (FUSED && A.step_dev) sample_base += (uint64_t)(*A.step_dev) * A.step_stride;
+
+    // K-major store of 4 consecutive columns (chunk c) of this thread's sample, hi and lo
+    auto put_k = [&](unsigned char* hi_base, unsigned char* lo_base, int chunk, const float4& v) {
+        float4 hi, lo;
+        split4(v, hi, lo);
+        *reinterpret_cast<float4*>(hi_base + chunk * kPanelA + s * 16) = hi;
+        *reinterpret_cast<float4*>(lo_base + chunk * kPanelA + s * 16) = lo;
+    };
+    // the same into an MN-major block pair (column j0 = first of the 4 columns, within one 32-column group)
+    auto put_mn = [&](unsigned char* hi_base, unsigned char* lo_base, int j0, const float4& v) {
+        float4 hi, lo;
+        split4(v, hi, lo);
+        const int off = mn_off(s, j0);
+        *reinterpret_cast<float4*>(hi_base + off) = hi;
+        *reinterpret_cast<float4*>(lo_base + off) = lo;
+    };
+    BT_MARK(0)  // setup
+
+    const int64_t ntiles = (A.n + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- input stage: the TPS threads of a sample take the K chunks c = q, q + TPS, ... ----------------------------
+        const int64_t sg = tile * TILE + s;
+        const bool valid = sg < A.n;
+        float cx = 0.f, cy = 0.f, cz = 0.f, aux = 0.f;
+        if (valid) {
+            if (FUSED && !A.coords) {
+                unsigned long long v = A.explicit_idx ? (unsigned long long)A.explicit_idx[sg]
+                                                      : philox_voxel(A.seed, sample_base + (uint64_t)sg, A.n_voxels);
+                const unsigned long long r12 = (unsigned long long)A.R[1] * A.R[2];
+                const int i = (int)(v / r12);
+                const int j = (int)((v / A.R[2]) % A.R[1]);
+                const int k = (int)(v % A.R[2]);
+                cx = normalized_coord((float)i, A.max_idx[0], A.scales[0]);
+                cy = normalized_coord((float)j, A.max_idx[1], A.scales[1]);
+                cz = normalized_coord((float)k, A.max_idx[2], A.scales[2]);
+                aux = __ldg(A.volume + v);
+            } else {  // caller-supplied positions; aux = target value (fused) or d(loss)/d(out)
+                cx = __ldg(A.coords + 3 * sg);
+                cy = __ldg(A.coords + 3 * sg + 1);
+                cz = __ldg(A.coords + 3 * sg + 2);
+                aux = __ldg(A.grad_out + sg);
+            }
+        }
+        Corners Kc;
+        make_corners(P, cx, cy, cz, Kc);
+        for (int c = q; c < K0p / 4; c += TPS) {
+            float v4[4];
+            if (4 * c < Cp) {
+                float4 v[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) v[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c);
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    a.x = fmaf(v[cc].x, Kc.w[cc], a.x);
+                    a.y = fmaf(v[cc].y, Kc.w[cc], a.y);
+                    a.z = fmaf(v[cc].z, Kc.w[cc], a.z);
+                    a.w = fmaf(v[cc].w, Kc.w[cc], a.w);
+                }
+                v4[0] = a.x; v4[1] = a.y; v4[2] = a.z; v4[3] = a.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = 4 * c + i - Cp;   // 0..2 xyz, then per frequency [sin x y z | cos x y z]
+                    float val = 0.0f;
+                    if (r < 3) {
+                        val = r == 0 ? cx : (r == 1 ? cy : cz);
+                    } else if (r < nfix) {
+                        const int f = (r - 3) / 6, m = (r - 3) - 6 * f;
+                        const int ax = m >= 3 ? m - 3 : m;
+                        const float coord = ax == 0 ? cx : (ax == 1 ? cy : cz);
+                        float sn, cs;
+                        sincos_cw(__fmul_rn(coord, P.omega[f]), sn, cs);  // argument rounded to fp32 first
+                        val = m >= 3 ? cs : sn;
+                    }
+                    v4[i] = val;
+                }
+            }
+            put_k(HkHi, HkLo, c, make_float4(v4[0], v4[1], v4[2], v4[3]));
+            tmem_st<4>(trow + cH0 + 4 * c, v4);
+        }
+        tmem_st_wait();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        BT_MARK(1)  // input stage
+        __syncthreads();
+        BT_MARK(2)  // barriers
+
+        // ---- forward ------------------------------------------------------------------------------------------------------------
+        float hs[CW], gs[CW];
+        for (int l = 0; l < L; ++l) {
+            if (threadIdx.x == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int nk = (l == 0 ? K0p : HP) / 8;
+                const uint32_t boff = (uint32_t)((l == 0 ? 0 : (K0p + (l - 1) * HP) / 4) * kPanelW);
+                constexpr uint32_t id = idesc(HP, 0, 0);
+                for (int ks = 0; ks < nk; ++ks) {
+                    const uint64_t ah = desc_k(aHkHi + ks * 2 * kPanelA, kPanelA, 128);
+                    const uint64_t al = desc_k(aHkLo + ks * 2 * kPanelA, kPanelA, 128);
+                    const uint64_t bh = desc_k(aWfHi + boff + ks * 2 * kPanelW, kPanelW, 128);
+                    const uint64_t bl = desc_k(aWfLo + boff + ks * 2 * kPanelW, kPanelW, 128);
+                    mma_tf32(tmem + cAcc, ah, bh, id, ks > 0 ? 1u : 0u);
+                    mma_tf32(tmem + cAcc, al, bh, id, 1u);
+                    mma_tf32(tmem + cAcc, ah, bl, id, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            }
+            BT_MARK(3)  // MMA issue
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            BT_MARK(4)  // MMA wait
+
+            float z[CW];
+            tmem_ld<CW>(trow + cAcc + col0, z);
+            const float* bl_ = bias + l * HP + col0;
+#pragma unroll
+            for (int i = 0; i < CW; ++i) snake_and_grad_precise(z[i] + bl_[i], hs[i], gs[i]);
+            if (l + 1 < L) {
+                tmem_st<CW>(trow + cS + l * HP + col0, gs);
+                tmem_st<CW>(trow + cH1 + l * HP + col0, hs);   // h_{l+1}
+#pragma unroll
+                for (int c = 0; c < CW / 4; ++c)
+                    put_k(HkHi, HkLo, col0 / 4 + c, make_float4(hs[4 * c], hs[4 * c + 1], hs[4 * c + 2], hs[4 * c + 3]));
+                tmem_st_wait();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                BT_MARK(5)  // forward epilogue
+                __syncthreads();
+                BT_MARK(2)
+            }
+        }
+
+        // ---- output, loss, dz_{L-1} --------------------------------------------------------------------------------------------
+        {
+            float yp = 0.0f;
+#pragma unroll
+            for (int i = 0; i < CW; ++i) yp = fmaf(hs[i], wfs[col0 + i], yp);
+            yx[q * TILE + s] = yp;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();   // also: every thread has read its z_{L-1} and the forward operand is dead
+        float dy;
+        {
+            float y = bf;
+#pragma unroll
+            for (int t = 0; t < TPS; ++t) y += yx[t * TILE + s];
+            if (FUSED) {
+                const float e = y - aux;
+                dy = valid ? A.loss_scale2 * e : 0.0f;
+                if (q == 0 && valid) loss_part = fmaf(e, e, loss_part);
+            } else {
+                dy = valid ? aux : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CW; ++i) accWf[i] = fmaf(dy, hs[i], accWf[i]);
+        if (q == 0) accbf += dy;
+        float dz[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i) dz[i] = dy * wfs[col0 + i] * gs[i];
+        BT_MARK(6)  // output + loss
+
+        // ---- backward ----------------------------------------------------------------------------------------------------------
+        for (int l = L - 1; l >= 0; --l) {
+            // dz_l -> both operand formats
+#pragma unroll
+            for (int c = 0; c < CW / 4; ++c) {
+                const float4 v = make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
+                put_k(DkHi, DkLo, col0 / 4 + c, v);
+                put_mn(DmHi, DmLo, col0 + 4 * c, v);
+            }
+            // h_l (fp32 copy in TMEM) -> MN-major operand
+            if (l > 0) {
+                float hv[CW];
+                tmem_ld<CW>(trow + cH1 + (l - 1) * HP + col0, hv);
+#pragma unroll
+                for (int c = 0; c < CW / 4; ++c)
+                    put_mn(Hm, Hm + 2 * kBlkMN, col0 + 4 * c, make_float4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]));
+            } else {
+                for (int c = q; c < K0p / 4; c += TPS) {
+                    float hv[4];
+                    tmem_ld<4>(trow + cH0 + 4 * c, hv);
+                    const int g = (4 * c) >> 5;   // 32-column group
+                    put_mn(Hm + g * kBlkMN, Hm + (2 + g) * kBlkMN, (4 * c) & 31, make_float4(hv[0], hv[1], hv[2], hv[3]));
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            BT_MARK(7)  // backward operand staging
+            __syncthreads();
+            BT_MARK(2)
+            if (threadIdx.x == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // dh_l = dz_l W_l  (layer 0: only the feature columns)
+                {
+                    const uint32_t id = l > 0 ? idesc(HP, 0, 0) : idesc(Lo.Np0, 0, 0);
+                    const uint32_t rows16 = (uint32_t)(l > 0 ? HP : Lo.Np0) * 16;
+                    const uint32_t boff = (uint32_t)(l > 0 ? Lo.wb0 + (l - 1) * (HP / 4) * kPanelW : 0);
+                    for (int ks = 0; ks < HP / 8; ++ks) {
+                        const uint64_t ah = desc_k(aDkHi + ks * 2 * kPanelA, kPanelA, 128);
+                        const uint64_t al = desc_k(aDkLo + ks * 2 * kPanelA, kPanelA, 128);
+                        const uint64_t bh = desc_k(aWbHi + boff + ks * 2 * rows16, rows16, 128);
+                        const uint64_t bl = desc_k(aWbLo + boff + ks * 2 * rows16, rows16, 128);
+                        mma_tf32(tmem + cAcc, ah, bh, id, ks > 0 ? 1u : 0u);
+                        mma_tf32(tmem + cAcc, al, bh, id, 1u);
+                        mma_tf32(tmem + cAcc, ah, bl, id, 1u);
+                    }
+                }
+                // dW_l^T += [h_l | 1]^T dz_l, contraction over the 128 samples (8 per MMA)
+                {
+                    constexpr uint32_t id = idesc(HP, 1, 1);
+                    const uint32_t d = tmem + cW + l * HP;
+                    for (int ks = 0; ks < TILE / 8; ++ks) {
+                        const uint64_t ah = desc_mn(aHmHi + ks * 1024);
+                        const uint64_t al = desc_mn(aHmLo + ks * 1024);
+                        const uint64_t bh = desc_mn(aDmHi + ks * 1024);
+                        const uint64_t bl = desc_mn(aDmLo + ks * 1024);
+                        mma_tf32(d, ah, bh, id, (first_tile && ks == 0) ? 0u : 1u);
+                        mma_tf32(d, al, bh, id, 1u);
+                        mma_tf32(d, ah, bl, id, 1u);
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            }
+            BT_MARK(3)
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            BT_MARK(4)
+            if (l > 0) {
+                float dh[CW], g[CW];
+                tmem_ld<CW>(trow + cAcc + col0, dh);
+                tmem_ld<CW>(trow + cS + (l - 1) * HP + col0, g);
+#pragma unroll
+                for (int i = 0; i < CW; ++i) dz[i] = dh[i] * g[i];
+                BT_MARK(8)  // dz
+            } else {
+                // scatter d(features) into the grid gradient
+                for (int c = q; 4 * c < Cp; c += TPS) {
+                    float d[4];
+                    tmem_ld<4>(trow + cAcc + 4 * c, d);   // warp-collective: outside the per-sample predicate
+                    if (valid) {
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc) {
+                            const float w = Kc.w[cc];
+                            if (w != 0.0f)
+                                red_add_v4(A.grad_grid + Kc.off[cc] + 4 * c, make_float4(d[0] * w, d[1] * w, d[2] * w, d[3] * w));
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                BT_MARK(9)  // scatter
+            }
+        }
+        first_tile = false;
+    }
+
+    // ---- flush: weight-gradient accumulators, final-layer gradient, loss ------------------------------------------------------
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* dst = A.partial + (size_t)blockIdx.x * A.pstride;
+    if ((warp & 3) < 2) {   // accumulator rows 0..63 live in lane quarters 0 and 1
+        const int row = ((warp & 3) << 5) | lane;
+        for (int l = q; l < L; l += TPS) {
+            float r[32];
+            tmem_ld<32>(trow + cW + l * HP, r);
+            const int Kin = l == 0 ? in0 : H;
+            const int woff = mlp_w_off(l, in0, H);
+            int orig = -1;   // column of W_l this accumulator row belongs to
+            if (l > 0) {
+                if (row < H) orig = row;
+            } else if (row < Cp) {
+                if (row < P.C) orig = nfix + row;
+            } else if (row < Cp + nfix) {
+                orig = row - Cp;
+            }
+            if (orig >= 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < H) dst[woff + j * Kin + orig] = r[j];
+            }
+            if (row == kOnesRow) {
+                const int boff = mlp_b_off(l, in0, H);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < H) dst[boff + j] = r[j];
+            }
+        }
+    }
+    {
+        float* red = reinterpret_cast<float*>(DkHi);   // [128][36]: 32 Wf partials | bf | loss
+#pragma unroll
+        for (int i = 0; i < CW; ++i) red[s * 36 + col0 + i] = accWf[i];
+        if (q == 0) {
+            red[s * 36 + 32] = accbf;
+            red[s * 36 + 33] = FUSED ? loss_part : 0.0f;
+        }
+        __syncthreads();
+        if (threadIdx.x < 34) {
+            float t = 0.0f;
+            for (int r = 0; r < TILE; ++r) t += red[r * 36 + threadIdx.x];
+            const int wfo = mlp_wf_off(L, in0, H);
+            if (threadIdx.x < 32) {
+                if ((int)threadIdx.x < H) dst[wfo + threadIdx.x] = t;
+            } else if (threadIdx.x == 32) {
+                dst[wfo + H] = t;
+            } else {
+                dst[A.pcount] = t;
+            }
+        }
+    }
+    BT_MARK(10)  // flush
+    BT_FLUSH()
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
+}
+
+template <int FUSED, int TPS>
+static int launch_tps(BwdArgs& A, int K0p, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
+                      cudaStream_t st) {
+    const Layout Lo = make_layout(A.P, K0p, TPS);
+    if (Lo.total > max_smem_optin()) return 1;
+    auto kern = backward_tc_kernel<FUSED, TPS>;
+    LFGC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lo.total));
+    const int64_t ntiles = (A.n + TILE - 1) / TILE;
+    int64_t grid = sm_count();   // the kernel owns the SM's TMEM: one CTA per SM
+    if (grid > ntiles) grid = ntiles;
+    const size_t need = (size_t)grid * A.pstride * sizeof(float);
+    if (workspace_bytes < need) return fail(LFGC_E_WORKSPACE, "backward workspace too small: %zu < %zu", workspace_bytes, need);
+    A.partial = reinterpret_cast<float*>(workspace);
+    kern<<<(unsigned)grid, TILE * TPS, Lo.total, st>>>(A, K0p);
+    LFGC_LAUNCH_OK();
+    launch_reduce_partials(A.partial, (int)grid, A.pstride, A.pcount, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
+
+}  // namespace btc
+
+// Returns LFGC_OK after launching, 1 when the shape is not covered by the tensor-core kernel, or an error code.
+int launch_backward_tc(BwdArgs& A, int fused, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st) {
+    const SampleParams& P = A.P;
+    if (P.H > btc::HP || P.L < 1 || P.L > btc::LMAX) return 1;
+    const int K0 = P.Cp + 3 + 6 * P.F;
+    const int K0p = (K0 + 7) & ~7;
+    if (K0p > 56) return 1;   // two 32-column MN groups, the last column of the second one is the ones column
+    int tps = 2;
+    if (const char* e = getenv("LFGC_TC_TPS")) { const int v = atoi(e); if (v == 2 || v == 4) tps = v; }  // tuning aid
+    if (fused) {
+        return tps == 4 ? btc::launch_tps<1, 4>(A, K0p, grad_mlp, accumulate, workspace, workspace_bytes, st)
+                        : btc::launch_tps<1, 2>(A, K0p, grad_mlp, accumulate, workspace, workspace_bytes, st);
+    }
+    return tps == 4 ? btc::launch_tps<0, 4>(A, K0p, grad_mlp, accumulate, workspace, workspace_bytes, st)
+                    : btc::launch_tps<0, 2>(A, K0p, grad_mlp, accumulate, workspace, workspace_bytes, st);
+}
+
+}  // namespace lfgc
+
+#ifdef LFGC_PHASE_TIMING
+extern "C" int lfgc_btc_timing(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (out16) cudaMemcpyFromSymbol(out16, g_btc_cycles, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_btc_cycles, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
