@@ -323,7 +323,7 @@ def run_native(args):
             traffic = json.load(open(tpath)).get('train_step_dram_bytes_per_launch')
         except Exception:
             traffic = None
-    roofline = dict(bound='fp32', kernel='sample_backward_kernel<32,1> (lfgc_train_step)', achieved=ach_tflops,
+    roofline = dict(bound='fp32', kernel='backward_v2_kernel<FUSED=1> (lfgc_train_step)', achieved=ach_tflops,
                     peak=fp32_peak, unit='TFLOP/s', frac=ach_tflops / fp32_peak, traffic=traffic,
                     kernel_us=k_ms * 1e3, peak_source='148 SMs x 128 FFMA x 2 x %s sm_max_mhz' % pk['source'],
                     note='fp32 FFMA-bound (SURVEY 8d): neither HBM nor tensor pipe limits this path; '
@@ -442,11 +442,37 @@ def e2e_host_fed(volume, n, rank, world, dev, steps=300, warmup=20):
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_serial = float(t.item())
+    # pipelined variant: the same per-step traffic (H2D of the step's samples, D2H of the step's loss, each read by the
+    # host), with the copies on a second stream and the loss of step i read while step i+1 runs
+    for i in range(warmup):
+        tr.step_host_pipelined(*host[i % n_buf])
+    tr.flush_host_pipeline()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(steps):
+        prev = tr.step_host_pipelined(*host[i % n_buf])   # returns the loss of step i-1 (host float)
+        if prev is not None:
+            last = prev
+    last = tr.flush_host_pipeline()
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    t = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     return dict(value=steps * n * world / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=n * 16, d2h_bytes_per_step=4,
-                api='FastTrainer.step_host(coords, targets) + last_loss(): one optimiser step of 32768 host-resident '
-                    'samples per GPU per call (lfgc_train_step with caller-supplied samples, CUDA-graph replay)',
-                us_per_optimiser_step=1e3 * ms / steps, final_mse=last)
+                api='FastTrainer.step_host_pipelined(coords, targets): one optimiser step of 32768 host-resident samples '
+                    'per GPU per call (H2D on a copy stream into double-buffered staging, lfgc_train_step with '
+                    'caller-supplied samples, CUDA-graph replay, every step\'s loss copied to pinned host memory and read '
+                    'one call later); timed = max(CUDA events, host wall clock)',
+                us_per_optimiser_step=1e3 * ms / steps, final_mse=last,
+                serial=dict(value=steps * n * world / (ms_serial * 1e-3), us_per_optimiser_step=1e3 * ms_serial / steps,
+                            api='FastTrainer.step_host + last_loss(): copies, replay and loss read serialised per step'))
 
 
 def e2e_module_path(model, volume, n, rank, world, dev, steps=100, warmup=10):

@@ -181,6 +181,29 @@ int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t
                     float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
                     float* loss_sum, int accumulate_mlp, void* workspace, size_t workspace_bytes, void* stream);
 
+/* lfgc_train_step with the Gaussian log-likelihood of VariationalDropoutLoss (model/Variational_Dropout_Layer.py:24-30,
+ * 54-69) instead of the plain MSE: log_sigma[n] (nullable) is the per-sample log sigma v_i (the Variance_Model output,
+ * training/training.py:119-121);  d(loss)/d(pred_i) = 2 loss_scale (pred_i - gt_i) exp(-2 v_i)  and
+ * dlog_sigma[n] (nullable) receives  d(loss)/d(v_i) = 2 loss_scale (1 - (pred_i - gt_i)^2 exp(-2 v_i)).
+ * Pass loss_scale = n_voxels / (2 N_global) for the reference's batch_scale.  loss_sum stays sum (pred-gt)^2. */
+int lfgc_train_step_weighted(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
+                             uint64_t seed, uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
+                             const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
+                             float loss_scale, const float* log_sigma, float* dlog_sigma, const float* grid_cl,
+                             const float* mlp, float* grad_grid_cl, float* grad_mlp, float* loss_sum, int accumulate_mlp,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Variance_Model (model/Variational_Dropout_Layer.py:159-175) -------------------------------------------------- */
+
+/* out[n] = final(ReLU(net_{L-1}(... ReLU(net_0(x))))) for x[n][3]: the plain coordinate MLP 3 -> H x L -> 1 that
+ * predicts log sigma per sample.  mlp is packed like lfgc_mlp_param_count with an input width of 3
+ * (net_layers.i.weight/.bias, final_layer.weight/.bias).  H <= 32, L <= 4 (the reference builds 32 x 4). */
+int lfgc_plain_mlp_forward(int H, int L, const float* x, int64_t n, const float* mlp, float* out, void* stream);
+size_t lfgc_plain_mlp_workspace_bytes(int H, int L);
+/* grad_mlp (+)= parameter gradients for d(loss)/d(out) = grad_out[n] (forward recomputed, deterministic reduction) */
+int lfgc_plain_mlp_backward(int H, int L, const float* x, int64_t n, const float* grad_out, const float* mlp,
+                            float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- sampler / ground truth ---------------------------------------------------------------------------------- */
 
 /* Random voxel sampler: replaces IndexDataset.__getitem__ + DataLoader collation (data/IndexDataset.py:90-96) and
@@ -189,6 +212,12 @@ int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t
  * operation order, gt_out[n] = volume[i][j][k].  Any output may be NULL.  explicit_idx as above. */
 int lfgc_sample(const float* volume, const int32_t R[3], int64_t n, uint64_t seed, uint64_t sample_offset,
                 const int64_t* explicit_idx, float* raw_out, float* norm_out, float* gt_out, void* stream);
+
+/* lfgc_sample whose Philox counter also advances with a DEVICE step counter (counter = sample_offset + i +
+ * *step_dev * step_stride, as in lfgc_train_step), so a captured CUDA graph draws fresh samples on every replay. */
+int lfgc_sample_stream(const float* volume, const int32_t R[3], int64_t n, uint64_t seed, uint64_t sample_offset,
+                       const int32_t* step_dev, uint64_t step_stride, const int64_t* explicit_idx, float* raw_out,
+                       float* norm_out, float* gt_out, void* stream);
 
 /* General trilinear_f_interpolation(p, f, min_bb, max_bb, res) (data/Interpolation.py:8-44): fp32 lattice
  * coordinates, fp64 alphas, f[x][y][z] indexing, lerp order x -> y -> z. min_bb/max_bb are HOST float[3]. */
@@ -226,6 +255,16 @@ int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const flo
 /* p-gradient of the sample-independent regularisers added in place: g += w_l2 * 2 * p (n_l2 leading elements) */
 int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* stream);
+
+/* Gradient of the KL regulariser of VariationalDropoutLoss (model/Variational_Dropout_Layer.py:54-69,115-122) added
+ * in place to the mask-parameter gradients, and the per-step ramp of its weight (:57-58).  mask_params / mask_grads
+ * point at a buffer holding, per mask layer i, [log_thetas_i (n_i) | log_var_i (n_i)]; layer_sizes is a HOST array
+ * of the n_i.  w_dkl is a DEVICE double[2] (both entries initialised to the starting weight), indexed by the parity
+ * of *step_count (the lfgc_adam counter): w <- w * ramp while w < w_max, then
+ * grad += w * scale * d DKL / d(param), with scale = batch_scale = n_voxels / N. */
+int lfgc_variational_dkl_grad(const float* mask_params, float* mask_grads, int n_layers, const int64_t* layer_sizes,
+                              double* w_dkl, const int32_t* step_count, double ramp, double w_max, float scale,
+                              void* stream);
 
 #ifdef __cplusplus
 }

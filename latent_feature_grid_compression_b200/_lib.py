@@ -58,7 +58,15 @@ _SIGNATURES = {
     'lfgc_backward': (C.c_int, [C.POINTER(ModelDesc), _f, _i64, _f, _f, _f, _f, _f, _f, C.c_int, _f, C.c_size_t, _f]),
     'lfgc_train_step': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f,
                                   C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, _f, C.c_int, _f, C.c_size_t, _f]),
+    'lfgc_train_step_weighted': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64,
+                                           _f, C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, _f, _f, _f, C.c_int, _f,
+                                           C.c_size_t, _f]),
+    'lfgc_plain_mlp_forward': (C.c_int, [C.c_int, C.c_int, _f, _i64, _f, _f, _f]),
+    'lfgc_plain_mlp_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'lfgc_plain_mlp_backward': (C.c_int, [C.c_int, C.c_int, _f, _i64, _f, _f, _f, C.c_int, _f, C.c_size_t, _f]),
     'lfgc_sample': (C.c_int, [_f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f, _f, _f, _f, _f]),
+    'lfgc_sample_stream': (C.c_int, [_f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f, C.c_uint64, _f, _f, _f,
+                                     _f, _f]),
     'lfgc_trilinear': (C.c_int, [_f, _i64, _f, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float), _f, _f]),
     'lfgc_reconstruct': (C.c_int, [C.POINTER(ModelDesc), _f, _f, C.POINTER(C.c_int32), _f, _f, _f, C.c_int32,
                                    C.c_int32, _f, C.c_int, _f]),
@@ -66,6 +74,8 @@ _SIGNATURES = {
     'lfgc_adam': (C.c_int, [_f, _f, _f, _f, _i64, _f, _f, C.c_float, C.c_float, C.c_float, C.c_float, _f]),
     'lfgc_add_l2_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_add_l1_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
+    'lfgc_variational_dkl_grad': (C.c_int, [_f, _f, C.c_int, C.POINTER(C.c_int64), _f, _f, C.c_double, C.c_double,
+                                            C.c_float, _f]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(REPO_ROOT, 'include')
 LIB_PATH = os.path.join(PKG_DIR, 'liblfgc.so')
 
 NVCC_FLAGS = [
-    '-shared', '-Xcompiler', '-fPIC', '-std=c++17', '-O3', '-lineinfo',
+    '-shared', '-Xcompiler', '-fPIC', '-std=c++17', '-O3', '-lineinfo', '-t', '8',
     '-gencode', 'arch=compute_100a,code=sm_100a',
 ]
 

@@ -89,6 +89,34 @@ __device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
 
 // SnakeAlt(x) = 0.5 x + sin^2 x and its derivative 0.5 + sin 2x = 0.5 + 2 sin x cos x
 // (model/Feature_Grid_Model.py:12-13).
+#ifndef LFGC_SNAKE_MUFU
+#define LFGC_SNAKE_MUFU 0
+#endif
+#if LFGC_SNAKE_MUFU
+// sin^2 z = (1 - cos 2z) / 2 and sin 2z on the special-function unit after an exact reduction of z modulo pi
+// (2r in [-pi, pi] is the interval MUFU.SIN / MUFU.COS are specified on: max abs error 2^-21.4 / 2^-21.2).
+// 11 instructions, 2 of them on the otherwise idle XU pipe, instead of ~24 FMA-pipe instructions.
+__device__ __forceinline__ void snake_cos_sin_2z(float z, float& c2, float& s2) {
+    const float biased = __fadd_rn(__fmul_rn(z, 0.318309886f), 12582912.0f);   // rint(z / pi)
+    const float n = __fsub_rn(biased, 12582912.0f);
+    float r = fmaf(n, -3.14159274e+00f, z);
+    r = fmaf(n, 8.74227766e-08f, r);
+    const float w = r + r;
+    c2 = __cosf(w);
+    s2 = __sinf(w);
+}
+__device__ __forceinline__ float snake_precise(float z) {
+    float c2, s2;
+    snake_cos_sin_2z(z, c2, s2);
+    return fmaf(-0.5f, c2, fmaf(0.5f, z, 0.5f));
+}
+__device__ __forceinline__ void snake_and_grad_precise(float z, float& h, float& g) {
+    float c2, s2;
+    snake_cos_sin_2z(z, c2, s2);
+    h = fmaf(-0.5f, c2, fmaf(0.5f, z, 0.5f));
+    g = s2 + 0.5f;
+}
+#else
 __device__ __forceinline__ float snake_precise(float z) {
     float s, c;
     sincos_cw(z, s, c);
@@ -99,6 +127,24 @@ __device__ __forceinline__ void snake_and_grad_precise(float z, float& h, float&
     sincos_cw(z, s, c);
     h = fmaf(s, s, 0.5f * z);
     g = fmaf(2.0f * s, c, 0.5f);
+}
+#endif
+
+// Hidden-layer activation of the fused kernels: ACT 0 = SnakeAlt (the fV-SRN decoder), ACT 1 = ReLU (Variance_Model,
+// model/Variational_Dropout_Layer.py:159-175; gradient 1 where z > 0, as torch's threshold_backward).
+template <int ACT>
+__device__ __forceinline__ float act_value(float z) {
+    if (ACT == 1) return fmaxf(z, 0.0f);
+    return snake_precise(z);
+}
+template <int ACT>
+__device__ __forceinline__ void act_value_grad(float z, float& h, float& g) {
+    if (ACT == 1) {
+        h = fmaxf(z, 0.0f);
+        g = z > 0.0f ? 1.0f : 0.0f;
+    } else {
+        snake_and_grad_precise(z, h, g);
+    }
 }
 
 // Philox4x32-10 counter-based generator (Salmon et al. 2011), one call per sample.

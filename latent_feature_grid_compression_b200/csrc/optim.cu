@@ -56,9 +56,68 @@ __global__ void add_l1_grad_kernel(float* __restrict__ g, const float* __restric
     }
 }
 
+// Gradient of the KL term of VariationalDropoutLoss (model/Variational_Dropout_Layer.py:54-69,115-122) with respect to
+// the mask parameters, plus the per-step ramp of its weight.  The mask section of the flat parameter buffer holds, per
+// mask layer i, [log_thetas_i (n_i) | log_var_i (n_i)]; seg.end[i] is the end (in mask elements, cumulative n_i) of
+// layer i.  DKL = sum(-k1 sigmoid(k2 + k3 la) + 0.5 softplus(-la) + k1), la = log_var - 2 log_thetas.
+// w_dkl[2] is a ping-pong pair indexed by the parity of the optimiser step counter: every thread reads the current
+// weight, applies the ramp locally and one thread publishes the ramped value for the next step, so the whole thing is
+// one launch and graph-replayable.
+struct DklSegments {
+    int n_layers;
+    long long end[LFGC_MAX_LEVELS];
+};
+
+__global__ void variational_dkl_grad_kernel(const float* __restrict__ mask_p, float* __restrict__ mask_g,
+                                            const __grid_constant__ DklSegments seg, double* __restrict__ w_dkl,
+                                            const int32_t* __restrict__ step_ptr, double ramp, double w_max,
+                                            float scale) {
+    const int step = step_ptr ? *step_ptr : 0;
+    const double w_old = w_dkl[step & 1];
+    const double w_new = w_old < w_max ? w_old * ramp : w_old;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) w_dkl[(step + 1) & 1] = w_new;
+    const long long total = seg.end[seg.n_layers - 1];
+    if (i >= total) return;
+    int layer = 0;
+    while (i >= seg.end[layer]) ++layer;
+    const long long begin = layer ? seg.end[layer - 1] : 0;
+    const long long n = seg.end[layer] - begin;
+    const long long lt = 2 * begin + (i - begin), lv = lt + n;
+    const float la = mask_p[lv] - 2.0f * mask_p[lt];
+    const float k1 = 0.63576f, k2 = 1.87320f, k3 = 1.48695f;
+    const float su = 1.0f / (1.0f + expf(-(k2 + k3 * la)));
+    const float sm = 1.0f / (1.0f + expf(la));                 // sigmoid(-la)
+    const float d = -k1 * k3 * su * (1.0f - su) - 0.5f * sm;   // d DKL / d la
+    const float g = (float)w_new * scale * d;
+    mask_g[lv] += g;
+    mask_g[lt] -= 2.0f * g;
+}
+
 }  // namespace lfgc
 
 using namespace lfgc;
+
+extern "C" int lfgc_variational_dkl_grad(const float* mask_params, float* mask_grads, int n_layers,
+                                         const int64_t* layer_sizes, double* w_dkl, const int32_t* step_count,
+                                         double ramp, double w_max, float scale, void* stream) {
+    if (!mask_params || !mask_grads || !layer_sizes || !w_dkl || n_layers < 1 || n_layers > LFGC_MAX_LEVELS)
+        return fail(LFGC_E_INVALID, "variational_dkl_grad: bad arguments");
+    DklSegments seg;
+    seg.n_layers = n_layers;
+    long long acc = 0;
+    for (int i = 0; i < n_layers; ++i) {
+        if (layer_sizes[i] < 0) return fail(LFGC_E_INVALID, "variational_dkl_grad: negative layer size");
+        acc += layer_sizes[i];
+        seg.end[i] = acc;
+    }
+    const long long blocks = acc == 0 ? 1 : (acc + 255) / 256;
+    variational_dkl_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask_params, mask_grads, seg, w_dkl,
+                                                                                  step_count, ramp, w_max, scale);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
+
 
 extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
                          float beta1, float beta2, float eps, float grad_scale, void* stream) {

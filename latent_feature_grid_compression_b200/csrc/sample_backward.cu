@@ -209,6 +209,12 @@ __global__ void __launch_bounds__(kThreads, 1) sample_backward_kernel(const __gr
                     const float e = (y[s] + bf) - aux[s];
                     dy[s] = vv[s] * A.loss_scale2 * e;
                     if (og == 0) loss_part = fmaf(vv[s] * e, e, loss_part);
+                    if (A.log_sigma && vv[s] != 0.0f) {   // Gaussian likelihood with per-sample log sigma
+                        const int64_t gs = tile * kTile + col0 + s;
+                        const float w = expf(-2.0f * __ldg(A.log_sigma + gs));
+                        dy[s] *= w;
+                        if (A.dlog_sigma && og == 0) A.dlog_sigma[gs] = A.loss_scale2 * (1.0f - e * e * w);
+                    }
                 } else {
                     dy[s] = aux[s];
                 }
@@ -389,7 +395,7 @@ static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* wo
                            cudaStream_t st) {
     {
         const char* e = getenv("LFGC_BACKWARD_TC");
-        if (e && e[0] == '1') {
+        if (e && e[0] == '1' && !A.log_sigma && !(A.P.flags & kFlagPlainRelu)) {
             const int rc = launch_backward_tc(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
             if (rc != 1) return rc;
         }
@@ -398,6 +404,7 @@ static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* wo
         const int rc = launch_backward_v2(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
         if (rc != 1) return rc;
     }
+    if (A.P.flags & kFlagPlainRelu) return fail(LFGC_E_UNSUPPORTED, "plain MLP shape not covered by the wide kernel");
     const BwdLayout Lo = bwd_layout<HP>(A.P, A.pcount);
     const size_t smem = (size_t)Lo.total * sizeof(float);
     if ((int)smem > max_smem_optin())
@@ -464,6 +471,8 @@ extern "C" int lfgc_backward(const lfgc_model_desc* m, const float* coords, int6
     A.volume = nullptr;
     A.explicit_idx = nullptr;
     A.loss_sum = nullptr;
+    A.log_sigma = nullptr;
+    A.dlog_sigma = nullptr;
     A.loss_scale2 = 0.0f;
     A.seed = A.sample_offset = A.step_stride = 0;
     A.step_dev = nullptr;
@@ -476,12 +485,12 @@ extern "C" int lfgc_backward(const lfgc_model_desc* m, const float* coords, int6
     return launch_backward<32, 0>(A, grad_mlp, accumulate_mlp, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
-                               uint64_t seed, uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
-                               const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
-                               float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
-                               float* loss_sum, int accumulate_mlp, void* workspace, size_t workspace_bytes,
-                               void* stream) {
+static int train_step_impl(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
+                           uint64_t seed, uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
+                           const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
+                           float loss_scale, const float* log_sigma, float* dlog_sigma, const float* grid_cl,
+                           const float* mlp, float* grad_grid_cl, float* grad_mlp, float* loss_sum, int accumulate_mlp,
+                           void* workspace, size_t workspace_bytes, void* stream) {
     BwdArgs A;
     int rc = fill_sample_params(m, 0, A.P);
     if (rc) return rc;
@@ -502,6 +511,8 @@ extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, co
     A.volume = volume;
     A.explicit_idx = explicit_idx;
     A.loss_sum = loss_sum;
+    A.log_sigma = log_sigma;
+    A.dlog_sigma = dlog_sigma;
     A.loss_scale2 = 2.0f * loss_scale;
     A.seed = seed;
     A.sample_offset = sample_offset;
@@ -522,4 +533,69 @@ extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, co
     A.mlp = mlp;
     A.grad_grid = grad_grid_cl;
     return launch_backward<32, 1>(A, grad_mlp, accumulate_mlp, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
+                               uint64_t seed, uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
+                               const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
+                               float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,
+                               float* loss_sum, int accumulate_mlp, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    return train_step_impl(m, volume, R, n, seed, sample_offset, step_dev, step_stride, explicit_idx, explicit_coords,
+                           explicit_gt, loss_scale, nullptr, nullptr, grid_cl, mlp, grad_grid_cl, grad_mlp, loss_sum,
+                           accumulate_mlp, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lfgc_train_step_weighted(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
+                                        uint64_t seed, uint64_t sample_offset, const int32_t* step_dev,
+                                        uint64_t step_stride, const int64_t* explicit_idx, const float* explicit_coords,
+                                        const float* explicit_gt, float loss_scale, const float* log_sigma,
+                                        float* dlog_sigma, const float* grid_cl, const float* mlp, float* grad_grid_cl,
+                                        float* grad_mlp, float* loss_sum, int accumulate_mlp, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+    return train_step_impl(m, volume, R, n, seed, sample_offset, step_dev, step_stride, explicit_idx, explicit_coords,
+                           explicit_gt, loss_scale, log_sigma, dlog_sigma, grid_cl, mlp, grad_grid_cl, grad_mlp, loss_sum,
+                           accumulate_mlp, workspace, workspace_bytes, stream);
+}
+
+static int64_t plain_mlp_params(int H, int L) { return 3 * (int64_t)H + H + (int64_t)(L - 1) * ((int64_t)H * H + H) + H + 1; }
+
+extern "C" size_t lfgc_plain_mlp_workspace_bytes(int H, int L) {
+    if (H < 1 || L < 1) return 0;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    return backward_v2_workspace_floats((int)plain_mlp_params(H, L), sms) * sizeof(float);
+}
+
+extern "C" int lfgc_plain_mlp_backward(int H, int L, const float* x, int64_t n, const float* grad_out, const float* mlp,
+                                       float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+    BwdArgs A;
+    int rc = fill_plain_params(H, L, A.P);
+    if (rc) return rc;
+    if (n < 0 || !mlp || !grad_mlp || !workspace) return fail(LFGC_E_INVALID, "plain_mlp_backward: null pointer or n<0");
+    if (n > 0 && (!x || !grad_out)) return fail(LFGC_E_INVALID, "plain_mlp_backward: x/grad_out null");
+    A.pcount = (int)plain_mlp_params(H, L);
+    A.pstride = A.pcount + 1;
+    if (n == 0) {
+        if (!accumulate) LFGC_CUDA_OK(cudaMemsetAsync(grad_mlp, 0, A.pcount * sizeof(float), (cudaStream_t)stream));
+        return LFGC_OK;
+    }
+    A.coords = x;
+    A.grad_out = grad_out;
+    A.volume = nullptr;
+    A.explicit_idx = nullptr;
+    A.loss_sum = nullptr;
+    A.log_sigma = nullptr;
+    A.dlog_sigma = nullptr;
+    A.loss_scale2 = 0.0f;
+    A.seed = A.sample_offset = A.step_stride = 0;
+    A.step_dev = nullptr;
+    A.n_voxels = 1;
+    for (int a = 0; a < 3; ++a) { A.R[a] = 1; A.max_idx[a] = 1.0f; A.scales[a] = 1.0f; }
+    A.n = n;
+    A.grid = nullptr;
+    A.mlp = mlp;
+    A.grad_grid = nullptr;
+    return launch_backward<32, 0>(A, grad_mlp, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -18,6 +18,8 @@ struct BwdArgs {
     const int64_t* explicit_idx;
     float loss_scale2;          // 2 * loss_scale
     float* loss_sum;
+    const float* log_sigma;     // fused mode, nullable: per-sample log sigma v_i; d(loss)/d(pred) *= exp(-2 v_i)
+    float* dlog_sigma;          // fused mode, nullable: d(loss)/d(v_i) = 2 loss_scale (1 - e_i^2 exp(-2 v_i))
     int64_t n;
     const float* grid;
     const float* mlp;

@@ -208,7 +208,7 @@ __device__ __forceinline__ void dw_block(const float* __restrict__ dzp, const fl
 // NW (warps per CTA) is a template parameter so that the tile size and the row stride are compile-time constants; it
 // also bounds the registers per thread (registers are per scheduler: 16384 / warps per scheduler / 32):
 // 8 warps -> 255, 12 -> 168, 16 -> 128.
-template <int FUSED, int NC0, int NW>
+template <int FUSED, int NC0, int NW, int ACT>
 __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_constant__ BwdArgs A) {
     extern __shared__ __align__(16) float smem[];
     PHASE_DECL
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_co
                 for (int o = 0; o < 4; ++o) {
                     float h[4];
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) snake_and_grad_precise(pick(acc, s, o), h[s], greg[l][s * 4 + o]);
+                    for (int s = 0; s < 4; ++s) act_value_grad<ACT>(pick(acc, s, o), h[s], greg[l][s * 4 + o]);
                     if (l + 1 < L) {
                         *reinterpret_cast<float4*>(hrow + (j0 + o) * S + col0) = make_float4(h[0], h[1], h[2], h[3]);
                     } else {
@@ -366,6 +366,12 @@ __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_co
                     const float e = (y[s] + bf) - aux[s];
                     dy[s] = vv[s] * A.loss_scale2 * e;
                     if (og == 0) loss_part = fmaf(vv[s] * e, e, loss_part);
+                    if (A.log_sigma && vv[s] != 0.0f) {   // Gaussian likelihood with per-sample log sigma
+                        const int64_t gs = tile * TILE + col0 + s;
+                        const float w = expf(-2.0f * __ldg(A.log_sigma + gs));
+                        dy[s] *= w;
+                        if (A.dlog_sigma && og == 0) A.dlog_sigma[gs] = A.loss_scale2 * (1.0f - e * e * w);
+                    }
                 } else {
                     dy[s] = aux[s];
                 }
@@ -517,13 +523,15 @@ __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_co
     PHASE_FLUSH()
 }
 
+// Relative cost of a launch: waves x tile / (per-sample efficiency of the width) + a fixed set-up term.  The
+// efficiencies are measured (profiles/bwd_sweep.py, B200, C16 H32 L4, n = 262144, relative to 8 warps): 10+ warps are
+// register-limited to 168 / 128 registers and spill, fewer than 8 expose the shared-memory latency.
 static double tile_cost(int64_t n, int nw, int sms) {
+    static const double eff[15] = {0, 0, 0, 0, 0.72, 0.78, 0.86, 0.90, 1.00, 0.85, 0.83, 0.85, 0.90, 0.89, 0.89};
     const int tile = 16 * nw;
     const int64_t tiles = (n + tile - 1) / tile;
     const int64_t waves = (tiles + sms - 1) / sms;
-    // issue efficiency grows with the resident warps per scheduler (1 -> ~0.35, 2 -> ~0.6, 3+ -> ~0.8)
-    const double eff = 0.35 + 0.45 * (double)(nw - 4) / 10.0 + (nw >= 8 ? 0.05 : 0.0);
-    return (double)waves * tile / eff;
+    return (double)waves * tile / eff[nw] + 40.0;
 }
 
 static int env_nw() {
@@ -531,12 +539,12 @@ static int env_nw() {
     return e ? atoi(e) : 0;
 }
 
-template <int FUSED, int NC0, int NW>
+template <int FUSED, int NC0, int NW, int ACT = 0>
 static int launch_nw(BwdArgs& A, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
                      cudaStream_t st) {
     const Layout Lo = make_layout(A.P, NW);
     const size_t smem = (size_t)Lo.total * sizeof(float);
-    auto kern = backward_v2_kernel<FUSED, NC0, NW>;
+    auto kern = backward_v2_kernel<FUSED, NC0, NW, ACT>;
     LFGC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     constexpr int tile = 16 * NW;
     const int64_t ntiles = (A.n + tile - 1) / tile;
@@ -554,7 +562,7 @@ static int launch_nw(BwdArgs& A, float* grad_mlp, int accumulate, void* workspac
     return LFGC_OK;
 }
 
-static const int kWidths[] = {12, 8, 4};
+static const int kWidths[] = {8, 7, 6, 5, 4, 12, 14, 10};  // ties go to the first
 
 template <int FUSED, int NC0>
 static int launch(BwdArgs& A, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -570,8 +578,13 @@ static int launch(BwdArgs& A, float* grad_mlp, int accumulate, void* workspace, 
         if (!best || c < best_cost) { best = nw; best_cost = c; }
     }
     switch (best) {
+        case 14: return launch_nw<FUSED, NC0, 14>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
         case 12: return launch_nw<FUSED, NC0, 12>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
+        case 10: return launch_nw<FUSED, NC0, 10>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
         case 8: return launch_nw<FUSED, NC0, 8>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
+        case 7: return launch_nw<FUSED, NC0, 7>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
+        case 6: return launch_nw<FUSED, NC0, 6>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
+        case 5: return launch_nw<FUSED, NC0, 5>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
         case 4: return launch_nw<FUSED, NC0, 4>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
         default: return 1;
     }
@@ -585,6 +598,10 @@ int launch_backward_v2(BwdArgs& A, int fused, float* grad_mlp, int accumulate, v
                        cudaStream_t st) {
     const SampleParams& P = A.P;
     if (P.H > v2::HP || P.L > v2::LMAX || P.in0 > 64) return 1;
+    if (P.flags & kFlagPlainRelu) {   // Variance_Model: backward-only, ReLU, no grid
+        if (fused) return fail(LFGC_E_INVALID, "plain MLP has no fused sampler mode");
+        return v2::launch_nw<0, 1, 8, 1>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
+    }
     const bool two = P.in0 > 32;
     if (fused) {
         return two ? v2::launch<1, 2>(A, grad_mlp, accumulate, workspace, workspace_bytes, st)

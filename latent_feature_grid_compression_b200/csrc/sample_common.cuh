@@ -235,6 +235,22 @@ __device__ __forceinline__ void warp_gemm(const float* __restrict__ in, const fl
         }
 }
 
+// internal flag (not part of the ABI): ReLU hidden activations, no grid / embedding inputs (Variance_Model)
+constexpr int kFlagPlainRelu = 1 << 16;
+
+// Parameters of the plain coordinate MLP 3 -> H x L (ReLU) -> 1 (model/Variational_Dropout_Layer.py:159-175): the
+// fused kernels run it as a model without grid features and Fourier rows.
+inline int fill_plain_params(int H, int L, SampleParams& P) {
+    if (H < 1 || H > 32) return fail(LFGC_E_UNSUPPORTED, "plain MLP: size_layers=%d unsupported (1..32)", H);
+    if (L < 1 || L > 4) return fail(LFGC_E_UNSUPPORTED, "plain MLP: n_layers=%d unsupported (1..4)", L);
+    P.C = 0; P.Cp = 0; P.H = H; P.L = L; P.F = 0;
+    P.in0 = 3; P.in0p = 3;
+    for (int a = 0; a < 3; ++a) P.G[a] = 1;
+    for (int f = 0; f < kMaxFreq; ++f) P.omega[f] = 0.0f;
+    P.flags = kFlagPlainRelu;
+    return LFGC_OK;
+}
+
 inline int fill_sample_params(const lfgc_model_desc* m, int flags, SampleParams& P) {
     if (!m) return fail(LFGC_E_INVALID, "model desc is null");
     if (m->C < 1 || m->Cp < m->C || (m->Cp & 3)) return fail(LFGC_E_INVALID, "bad C=%d Cp=%d", m->C, m->Cp);

@@ -40,7 +40,7 @@ struct FwdArgs {
 template <int HP>
 __host__ __device__ constexpr int fwd_act_rows(int in0p) { return in0p > HP ? in0p : HP; }
 
-template <int HP, int MODE>
+template <int HP, int MODE, int ACT>
 __global__ void __launch_bounds__(kThreads, HP == 32 ? 6 : 2) sample_forward_kernel(const __grid_constant__ FwdArgs A) {
     constexpr int S = kTile;
     constexpr int NO = HP / 4;
@@ -104,10 +104,10 @@ __global__ void __launch_bounds__(kThreads, HP == 32 ? 6 : 2) sample_forward_ker
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
                     float4 h;
-                    h.x = snake_precise(acc[0][o]);
-                    h.y = snake_precise(acc[1][o]);
-                    h.z = snake_precise(acc[2][o]);
-                    h.w = snake_precise(acc[3][o]);
+                    h.x = act_value<ACT>(acc[0][o]);
+                    h.y = act_value<ACT>(acc[1][o]);
+                    h.z = act_value<ACT>(acc[2][o]);
+                    h.w = act_value<ACT>(acc[3][o]);
                     *reinterpret_cast<float4*>(act0 + (j0 + o) * S + col0) = h;
                 }
                 __syncwarp();
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, HP == 32 ? 6 : 2) sample_forward_ker
                 for (int o = 0; o < NO; ++o) {
                     const float wf = Wf[j0 + o];
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) y[s] = fmaf(snake_precise(acc[s][o]), wf, y[s]);
+                    for (int s = 0; s < 4; ++s) y[s] = fmaf(act_value<ACT>(acc[s][o]), wf, y[s]);
                 }
             }
         }
@@ -146,12 +146,12 @@ static size_t fwd_smem_bytes(const SampleParams& P) {
     return f * sizeof(float);
 }
 
-template <int HP, int MODE>
+template <int HP, int MODE, int ACT = 0>
 static int launch_forward(const FwdArgs& A, cudaStream_t st) {
     const size_t smem = fwd_smem_bytes<HP>(A.P);
     if ((int)smem > max_smem_optin())
         return fail(LFGC_E_UNSUPPORTED, "forward needs %zu B shared memory (> %d)", smem, max_smem_optin());
-    auto kern = sample_forward_kernel<HP, MODE>;
+    auto kern = sample_forward_kernel<HP, MODE, ACT>;
     LFGC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     LFGC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
@@ -195,6 +195,24 @@ extern "C" int lfgc_forward(const lfgc_model_desc* m, const float* coords, int64
     }
     if (m->H <= 32) return launch_forward<32, 0>(A, (cudaStream_t)stream);
     return launch_forward<64, 0>(A, (cudaStream_t)stream);
+}
+
+extern "C" int lfgc_plain_mlp_forward(int H, int L, const float* x, int64_t n, const float* mlp, float* out,
+                                      void* stream) {
+    FwdArgs A;
+    int rc = fill_plain_params(H, L, A.P);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!x || !out)) || !mlp) return fail(LFGC_E_INVALID, "plain_mlp_forward: null pointer or n<0");
+    if (n == 0) return LFGC_OK;
+    A.coords = x;
+    A.axis[0] = A.axis[1] = A.axis[2] = nullptr;
+    A.R1 = A.R2 = 1;
+    A.first = 0;
+    A.n = n;
+    A.grid = nullptr;
+    A.mlp = mlp;
+    A.out = out;
+    return launch_forward<32, 0, 1>(A, (cudaStream_t)stream);
 }
 
 extern "C" int lfgc_reconstruct(const lfgc_model_desc* m, const float* grid_cl, const float* mlp, const int32_t R[3],

@@ -13,7 +13,8 @@ struct SampleArgs {
     float max_idx[3], scales[3];
     unsigned long long n_voxels;
     int64_t n;
-    uint64_t seed, offset;
+    uint64_t seed, offset, step_stride;
+    const int32_t* step_dev;
     const int64_t* explicit_idx;
     float* raw;
     float* norm;
@@ -23,8 +24,10 @@ struct SampleArgs {
 __global__ void sample_kernel(const __grid_constant__ SampleArgs A) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n) return;
+    uint64_t base = A.offset;
+    if (A.step_dev) base += (uint64_t)(*A.step_dev) * A.step_stride;
     const unsigned long long v = A.explicit_idx ? (unsigned long long)A.explicit_idx[s]
-                                                : philox_voxel(A.seed, A.offset + (uint64_t)s, A.n_voxels);
+                                                : philox_voxel(A.seed, base + (uint64_t)s, A.n_voxels);
     const unsigned long long r12 = (unsigned long long)A.R[1] * A.R[2];
     const int i = (int)(v / r12);
     const int j = (int)((v / A.R[2]) % A.R[1]);
@@ -129,8 +132,10 @@ __global__ void deviation_stats_kernel(const float* __restrict__ pred, const flo
 
 using namespace lfgc;
 
-extern "C" int lfgc_sample(const float* volume, const int32_t R[3], int64_t n, uint64_t seed, uint64_t sample_offset,
-                           const int64_t* explicit_idx, float* raw_out, float* norm_out, float* gt_out, void* stream) {
+extern "C" int lfgc_sample_stream(const float* volume, const int32_t R[3], int64_t n, uint64_t seed,
+                                  uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
+                                  const int64_t* explicit_idx, float* raw_out, float* norm_out, float* gt_out,
+                                  void* stream) {
     if (!R || R[0] < 1 || R[1] < 1 || R[2] < 1 || n < 0) return fail(LFGC_E_INVALID, "sample: bad arguments");
     if (gt_out && !volume) return fail(LFGC_E_INVALID, "sample: gt requested without a volume");
     if (n == 0) return LFGC_OK;
@@ -147,6 +152,8 @@ extern "C" int lfgc_sample(const float* volume, const int32_t R[3], int64_t n, u
     A.n = n;
     A.seed = seed;
     A.offset = sample_offset;
+    A.step_dev = step_dev;
+    A.step_stride = step_stride;
     A.explicit_idx = explicit_idx;
     A.raw = raw_out;
     A.norm = norm_out;
@@ -154,6 +161,12 @@ extern "C" int lfgc_sample(const float* volume, const int32_t R[3], int64_t n, u
     sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
+}
+
+extern "C" int lfgc_sample(const float* volume, const int32_t R[3], int64_t n, uint64_t seed, uint64_t sample_offset,
+                           const int64_t* explicit_idx, float* raw_out, float* norm_out, float* gt_out, void* stream) {
+    return lfgc_sample_stream(volume, R, n, seed, sample_offset, nullptr, 0, explicit_idx, raw_out, norm_out, gt_out,
+                              stream);
 }
 
 extern "C" int lfgc_trilinear(const float* p, int64_t n, const float* volume, const int32_t R[3], const float min_bb[3],

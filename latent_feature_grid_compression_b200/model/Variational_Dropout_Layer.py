@@ -131,17 +131,59 @@ class VariationalDropout(DropoutLayer):
         return self.log_thetas.numel()
 
 
+class _PlainMLPFunction(torch.autograd.Function):
+    """lfgc_plain_mlp_forward / lfgc_plain_mlp_backward (forward recomputed in the backward; the coordinate gradient
+    the reference's autograd would also produce is never read, training/training.py:99,119-121)."""
+
+    @staticmethod
+    def forward(ctx, x, width, n_layers, flat, *params):
+        from .. import ops
+        out = ops.plain_mlp_forward(width, n_layers, x, flat)
+        ctx.saved = (x, flat, width, n_layers, [tuple(p.shape) for p in params])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from .. import ops
+        x, flat, width, n_layers, shapes = ctx.saved
+        g = ops.plain_mlp_backward(width, n_layers, x, grad_out.contiguous().float(), flat)
+        grads, off = [], 0
+        for shp in shapes:
+            n = int(np.prod(shp))
+            grads.append(g[off:off + n].view(shp))
+            off += n
+        return (None, None, None, None, *grads)
+
+
 class Variance_Model(nn.Module):
-    """3 -> 32 x 4 -> 1 ReLU MLP predicting log sigma per sample (Variational_Dropout_Layer.py:159-175)."""
+    """3 -> 32 x 4 -> 1 ReLU MLP predicting log sigma per sample (Variational_Dropout_Layer.py:159-175).  Same
+    constructor, ``net_layers`` / ``final_layer`` parameters and ``forward(input) -> (N, 1)``; the arithmetic is the
+    fused coordinate-MLP kernel pair behind lfgc_plain_mlp_forward / _backward."""
 
     def __init__(self, input_ch=3, output_ch=1, n_layers=4, size_layers=32):
         super().__init__()
+        if input_ch != 3 or output_ch != 1 or size_layers > 32 or not 1 <= n_layers <= 4:
+            raise L.LfgcError('Variance_Model kernels are built for 3 -> (<=32) x (<=4) -> 1 (got %d -> %d x %d -> %d)'
+                              % (input_ch, size_layers, n_layers, output_ch))
         self.net_layers = nn.ModuleList(
             [nn.Linear(input_ch, size_layers)] + [nn.Linear(size_layers, size_layers) for _ in range(n_layers - 1)])
         self.final_layer = nn.Linear(size_layers, output_ch)
+        self.width, self.n_layers = size_layers, n_layers
+        from .. import ops
+        self._pack = ops.FlatPack()
+
+    def _params(self):
+        ps = []
+        for layer in self.net_layers:
+            ps += [layer.weight, layer.bias]
+        return ps + [self.final_layer.weight, self.final_layer.bias]
+
+    def mlp_flat(self):
+        return self._pack.ensure(self._params())
 
     def forward(self, input):
-        out = input
-        for net_layer in self.net_layers:
-            out = F.relu(net_layer(out))
-        return self.final_layer(out)
+        if not input.is_cuda:
+            raise L.LfgcError('Variance_Model runs on CUDA only (no CPU fallback); got a %s tensor' % input.device)
+        x = input.detach().reshape(-1, 3).contiguous().float()
+        out = _PlainMLPFunction.apply(x, self.width, self.n_layers, self.mlp_flat(), *self._params())
+        return out.view(*input.shape[:-1], 1)

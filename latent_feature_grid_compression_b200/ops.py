@@ -219,9 +219,10 @@ def sample_backward(geom: Geometry, coords, grad_out, grid_cl, mlp_flat, grad_gr
 
 def train_step(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl, mlp_flat,
                grad_grid_cl, grad_mlp, loss_sum, workspace, explicit_idx=None, accumulate_mlp=False, step_dev=None,
-               step_stride: int = 0, coords=None, targets=None):
+               step_stride: int = 0, coords=None, targets=None, log_sigma=None, dlog_sigma=None):
     """Fused sampler + forward + MSE + backward.  With ``coords`` (n,3) and ``targets`` (n,) the caller supplies the
-    samples (host-fed step) and ``volume`` may be None."""
+    samples (host-fed step) and ``volume`` may be None.  ``log_sigma`` (n,) switches the loss to the Gaussian log
+    likelihood of VariationalDropoutLoss and ``dlog_sigma`` (n,) receives its gradient (lfgc_train_step_weighted)."""
     lib = L.load()
     if volume is not None:
         _req(volume, 'volume')
@@ -231,6 +232,17 @@ def train_step(geom: Geometry, volume, n: int, seed: int, sample_offset: int, lo
         _req(coords, 'coords')
         _req(targets, 'targets')
     shape3 = L.int3(volume.shape) if volume is not None else None
+    if log_sigma is not None:
+        _req(log_sigma, 'log_sigma')
+        if dlog_sigma is not None:
+            _req(dlog_sigma, 'dlog_sigma')
+        L.check(lib.lfgc_train_step_weighted(ct.byref(geom.model_desc), _p(volume), shape3, int(n), int(seed),
+                                             int(sample_offset), _p(step_dev), int(step_stride), _p(explicit_idx),
+                                             _p(coords), _p(targets), float(loss_scale), _p(log_sigma), _p(dlog_sigma),
+                                             _p(_req(grid_cl, 'grid_cl')), _p(_req(mlp_flat, 'mlp')), _p(grad_grid_cl),
+                                             _p(grad_mlp), _p(loss_sum), 1 if accumulate_mlp else 0, _p(workspace),
+                                             workspace.numel() * 4, _stream()), 'lfgc_train_step_weighted')
+        return
     L.check(lib.lfgc_train_step(ct.byref(geom.model_desc), _p(volume), shape3, int(n), int(seed),
                                 int(sample_offset), _p(step_dev), int(step_stride), _p(explicit_idx), _p(coords),
                                 _p(targets), float(loss_scale), _p(_req(grid_cl, 'grid_cl')),
@@ -243,17 +255,75 @@ def train_step(geom: Geometry, volume, n: int, seed: int, sample_offset: int, lo
 # sampler, ground truth, reconstruction, statistics, optimiser
 # --------------------------------------------------------------------------------------------------------------------
 
+def plain_mlp_param_count(H: int, L_: int) -> int:
+    return 3 * H + H + (L_ - 1) * (H * H + H) + H + 1
+
+
+def plain_mlp_forward(H: int, n_layers: int, x, mlp_flat, out=None):
+    """Variance_Model forward (lfgc_plain_mlp_forward): x (n,3) -> (n,)."""
+    lib = L.load()
+    _req(x, 'x')
+    _req(mlp_flat, 'mlp')
+    n = x.shape[0]
+    if out is None:
+        out = torch.empty(n, device=x.device, dtype=torch.float32)
+    L.check(lib.lfgc_plain_mlp_forward(int(H), int(n_layers), _p(x), int(n), _p(mlp_flat), _p(out), _stream()),
+            'lfgc_plain_mlp_forward')
+    return out
+
+
+def plain_mlp_workspace_floats(H: int, n_layers: int) -> int:
+    return int(L.load().lfgc_plain_mlp_workspace_bytes(int(H), int(n_layers))) // 4
+
+
+def plain_mlp_backward(H: int, n_layers: int, x, grad_out, mlp_flat, grad_mlp=None, accumulate=False, workspace=None):
+    """Parameter gradients of the Variance_Model for d(loss)/d(out) = grad_out (lfgc_plain_mlp_backward)."""
+    lib = L.load()
+    _req(x, 'x')
+    _req(grad_out, 'grad_out')
+    _req(mlp_flat, 'mlp')
+    if grad_mlp is None:
+        grad_mlp = torch.empty(plain_mlp_param_count(H, n_layers), device=x.device, dtype=torch.float32)
+    if workspace is None:
+        workspace = torch.empty(plain_mlp_workspace_floats(H, n_layers), device=x.device, dtype=torch.float32)
+    L.check(lib.lfgc_plain_mlp_backward(int(H), int(n_layers), _p(x), int(x.shape[0]), _p(grad_out), _p(mlp_flat),
+                                        _p(grad_mlp), 1 if accumulate else 0, _p(workspace), workspace.numel() * 4,
+                                        _stream()), 'lfgc_plain_mlp_backward')
+    return grad_mlp
+
+
+def variational_dkl_grad(mask_params, mask_grads, layer_sizes, w_dkl, step_dev, ramp: float, w_max: float, scale: float):
+    """grad += w_dkl * scale * d DKL/d(log_thetas, log_var), with the per-step ramp of w_dkl on the device
+    (lfgc_variational_dkl_grad).  ``w_dkl`` is a float64[2] device tensor."""
+    lib = L.load()
+    _req(mask_params, 'mask_params')
+    _req(mask_grads, 'mask_grads')
+    _req(w_dkl, 'w_dkl', torch.float64)
+    sizes = (ct.c_int64 * len(layer_sizes))(*[int(v) for v in layer_sizes])
+    L.check(lib.lfgc_variational_dkl_grad(_p(mask_params), _p(mask_grads), len(layer_sizes), sizes, _p(w_dkl),
+                                          _p(step_dev), float(ramp), float(w_max), float(scale), _stream()),
+            'lfgc_variational_dkl_grad')
+
+
 def sample(volume_shape, n: int, seed: int = 0, sample_offset: int = 0, volume=None, explicit_idx=None,
-           want_raw=True, want_norm=True, want_gt=False, device=None):
+           want_raw=True, want_norm=True, want_gt=False, device=None, step_dev=None, step_stride: int = 0, out=None):
     lib = L.load()
     device = device or (volume.device if volume is not None else torch.device('cuda'))
-    raw = torch.empty((n, 3), device=device, dtype=torch.float32) if want_raw else None
-    norm = torch.empty((n, 3), device=device, dtype=torch.float32) if want_norm else None
-    gt = torch.empty(n, device=device, dtype=torch.float32) if want_gt else None
+    if out is not None:
+        raw, norm, gt = out
+    else:
+        raw = torch.empty((n, 3), device=device, dtype=torch.float32) if want_raw else None
+        norm = torch.empty((n, 3), device=device, dtype=torch.float32) if want_norm else None
+        gt = torch.empty(n, device=device, dtype=torch.float32) if want_gt else None
     if explicit_idx is not None:
         _req(explicit_idx, 'explicit_idx', torch.int64)
     if volume is not None:
         _req(volume, 'volume')
+    if step_dev is not None:
+        L.check(lib.lfgc_sample_stream(_p(volume), L.int3(volume_shape), int(n), int(seed), int(sample_offset),
+                                       _p(step_dev), int(step_stride), _p(explicit_idx), _p(raw), _p(norm), _p(gt),
+                                       _stream()), 'lfgc_sample_stream')
+        return raw, norm, gt
     L.check(lib.lfgc_sample(_p(volume), L.int3(volume_shape), int(n), int(seed), int(sample_offset), _p(explicit_idx),
                             _p(raw), _p(norm), _p(gt), _stream()), 'lfgc_sample')
     return raw, norm, gt

@@ -42,12 +42,19 @@ class FastTrainer:
 
     def __init__(self, model: Feature_Grid_Model, volume: torch.Tensor, batch: int, lr: float = 0.008, seed: int = 0,
                  rank: int = 0, world_size: int = 1, process_group=None, weight_l1: float = 0.0,
-                 weight_l2: float = 0.0, use_graph: bool = True, betas=(0.9, 0.999), eps: float = 1e-8):
+                 weight_l2: float = 0.0, use_graph: bool = True, betas=(0.9, 0.999), eps: float = 1e-8,
+                 variational: Optional[dict] = None):
+        """``variational`` switches the loss to VariationalDropoutLoss (reference Variational_Dropout_Layer.py:33-69,
+        training/training.py:116-128): dict(n_voxels, weight_dkl, weight_weights, weight_dkl_multiplier,
+        weight_dkl_max=30.0, and either variance_model=<Variance_Model> (dynamic) or log_sigma=<float> (static))."""
         if not volume.is_cuda:
             raise L.LfgcError('FastTrainer needs the volume on the GPU')
-        if any(isinstance(d, VariationalDropout) and d.d_mask is None for d in model.drop):
-            raise NotImplementedError('variational dropout trains through the nn.Module path (its likelihood loss is '
-                                      'not fused yet); FastTrainer covers no-mask, Smallify and straight-through masks')
+        if variational is None and any(isinstance(d, VariationalDropout) and d.d_mask is None for d in model.drop):
+            raise L.LfgcError('a model with live variational-dropout masks needs the variational loss: pass '
+                              'variational=dict(n_voxels=..., weight_dkl=..., weight_weights=..., '
+                              'weight_dkl_multiplier=..., variance_model=... | log_sigma=...)')
+        self.var_cfg = dict(variational) if variational is not None else None
+        self.var_model = self.var_cfg.get('variance_model') if self.var_cfg else None
         self.model = model
         self.volume = volume.contiguous().float()
         self.batch = int(batch)
@@ -67,7 +74,8 @@ class FastTrainer:
             if isinstance(d, DropoutLayer):
                 self.mask_params += [p for p in d.parameters()]
         self.mlp_params = model._mlp_params()
-        every = self.coeff_params + self.mask_params + self.mlp_params
+        self.var_params = self.var_model._params() if self.var_model is not None else []
+        every = self.coeff_params + self.mask_params + self.mlp_params + self.var_params
         # sections start on 16-byte boundaries (the kernels use 128-bit loads where the alignment allows)
         def pad4(n):
             return (n + 3) // 4 * 4
@@ -75,11 +83,15 @@ class FastTrainer:
         self.n_mask_elems = sum(p.numel() for p in self.mask_params)
         self.mask_off = pad4(self.n_coeff_elems)
         self.mlp_off = self.mask_off + pad4(self.n_mask_elems)
-        total = self.mlp_off + sum(p.numel() for p in self.mlp_params)
+        self.n_mlp_elems = sum(p.numel() for p in self.mlp_params)
+        self.var_off = self.mlp_off + pad4(self.n_mlp_elems)
+        total = self.var_off + sum(p.numel() for p in self.var_params) if self.var_params \
+            else self.mlp_off + self.n_mlp_elems
         with torch.no_grad():
             self.flat_p = torch.zeros(total, device=self.device, dtype=torch.float32)
             self._slices = []
-            for group, off in ((self.coeff_params, 0), (self.mask_params, self.mask_off), (self.mlp_params, self.mlp_off)):
+            for group, off in ((self.coeff_params, 0), (self.mask_params, self.mask_off), (self.mlp_params, self.mlp_off),
+                               (self.var_params, self.var_off)):
                 for p in group:
                     n = p.numel()
                     self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
@@ -90,14 +102,18 @@ class FastTrainer:
         self.flat_m = torch.zeros_like(self.flat_p)
         self.flat_v = torch.zeros_like(self.flat_p)
         # keep the model's own MLP pack coherent with the shared buffer
-        pack = model._mlp_pack
-        pack.flat = self.flat_p[self.mlp_off:]
-        pack._layout = []
-        o = 0
-        for p in self.mlp_params:
-            pack._layout.append((o, p.numel()))
-            o += p.numel()
-        self.mlp_flat = pack.flat
+        def adopt(pack, params, off, count):
+            pack.flat = self.flat_p[off:off + count]
+            pack._layout = []
+            o = 0
+            for p in params:
+                pack._layout.append((o, p.numel()))
+                o += p.numel()
+            return pack.flat
+        self.mlp_flat = adopt(model._mlp_pack, self.mlp_params, self.mlp_off, self.n_mlp_elems)
+        if self.var_params:
+            self.var_flat = adopt(self.var_model._pack, self.var_params, self.var_off,
+                                  sum(p.numel() for p in self.var_params))
         self._grad_view = {}
         for p, (o, n) in zip(every, self._slices):
             self._grad_view[id(p)] = self.flat_g[o:o + n].view(p.shape)
@@ -116,6 +132,30 @@ class FastTrainer:
         # staging buffers of the host-fed step (step_host)
         self._in_coords = torch.zeros((self.batch, 3), device=self.device, dtype=torch.float32)
         self._in_targets = torch.zeros(self.batch, device=self.device, dtype=torch.float32)
+        self._pipe = None   # lazily built state of step_host_pipelined
+        if self.var_cfg is not None:
+            cfg = self.var_cfg
+            self.var_scale = float(cfg['n_voxels']) / float(self.batch * self.world)   # batch_scale of the reference
+            self.w_dkl = torch.full((2,), float(cfg['weight_dkl']), device=self.device, dtype=torch.float64)
+            self._s_coords = torch.zeros((self.batch, 3), device=self.device, dtype=torch.float32)
+            self._s_gt = torch.zeros(self.batch, device=self.device, dtype=torch.float32)
+            self._dlog_sigma = torch.zeros(self.batch, device=self.device, dtype=torch.float32)
+            if self.var_model is not None:
+                self._log_sigma = torch.zeros(self.batch, device=self.device, dtype=torch.float32)
+                self._var_ws = torch.empty(ops.plain_mlp_workspace_floats(self.var_model.width, self.var_model.n_layers),
+                                           device=self.device, dtype=torch.float32)
+            else:
+                self._log_sigma = torch.full((self.batch,), float(cfg['log_sigma']), device=self.device,
+                                             dtype=torch.float32)
+            self._var_layers = [d for d in model.drop if isinstance(d, VariationalDropout) and d.d_mask is None]
+            # the DKL kernel walks the mask section as [log_thetas_i | log_var_i] per layer: check that is what we packed
+            sizes, off = [], self.mask_off
+            for d in self._var_layers:
+                assert d.log_thetas.data_ptr() == self.flat_p.data_ptr() + 4 * off
+                assert d.log_var.data_ptr() == self.flat_p.data_ptr() + 4 * (off + d.log_thetas.numel())
+                sizes.append(d.log_thetas.numel())
+                off += 2 * d.log_thetas.numel()
+            self._var_sizes = sizes
 
     # ------------------------------------------------------------------------------------------------------------
     def grad_of(self, p):
@@ -123,18 +163,40 @@ class FastTrainer:
 
     def _step_body(self, host_fed=False):
         model, geom = self.model, self.geom
+        in_coords, in_targets = self._in_coords, self._in_targets
+        if isinstance(host_fed, tuple):   # ('pipe', b): the pipelined host-fed step reads staging buffer pair b
+            in_coords, in_targets = self._pipe['coords'][host_fed[1]], self._pipe['targets'][host_fed[1]]
         specs = model.mask_specs()
         mults, auxs = _multipliers(specs)
         coeffs = [p.data for p in self.coeff_params]
         # the synthesis also clears the grid-gradient accumulator; the fused kernel overwrites loss_sum
         ops.decode_fwd(geom, coeffs, mults, scratch=self.scratch, out=self.grid_cl, also_zero=self.grad_grid)
         n_global = self.batch * self.world
-        ops.train_step(geom, self.volume, self.batch, self.seed,
-                       parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
-                       parallel.loss_scale(self.batch, self.world), self.grid_cl,
-                       self.mlp_flat, self.grad_grid, self.flat_g[self.mlp_off:], self.loss_sum, self.workspace,
-                       step_dev=self.step_dev, step_stride=n_global,
-                       coords=self._in_coords if host_fed else None, targets=self._in_targets if host_fed else None)
+        if self.var_cfg is None:
+            ops.train_step(geom, self.volume, self.batch, self.seed,
+                           parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
+                           parallel.loss_scale(self.batch, self.world), self.grid_cl,
+                           self.mlp_flat, self.grad_grid, self.flat_g[self.mlp_off:], self.loss_sum, self.workspace,
+                           step_dev=self.step_dev, step_stride=n_global,
+                           coords=in_coords if host_fed else None, targets=in_targets if host_fed else None)
+        else:
+            # variational likelihood: the samples are materialised so that the Variance_Model sees the positions
+            if not host_fed:
+                in_coords, in_targets = self._s_coords, self._s_gt
+                ops.sample(self.volume.shape, self.batch, seed=self.seed,
+                           sample_offset=parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
+                           volume=self.volume, step_dev=self.step_dev, step_stride=n_global,
+                           out=(None, in_coords, in_targets))
+            vm = self.var_model
+            if vm is not None:
+                ops.plain_mlp_forward(vm.width, vm.n_layers, in_coords, self.var_flat, out=self._log_sigma)
+            ops.train_step(geom, None, self.batch, self.seed, 0, 0.5 * self.var_scale, self.grid_cl, self.mlp_flat,
+                           self.grad_grid, self.flat_g[self.mlp_off:self.mlp_off + self.n_mlp_elems], self.loss_sum,
+                           self.workspace, coords=in_coords, targets=in_targets, log_sigma=self._log_sigma,
+                           dlog_sigma=self._dlog_sigma if vm is not None else None)
+            if vm is not None:
+                ops.plain_mlp_backward(vm.width, vm.n_layers, in_coords, self._dlog_sigma, self.var_flat,
+                                       grad_mlp=self.flat_g[self.var_off:], workspace=self._var_ws)
         want = [s is not None and len(s.grad_params) > 0 for s in specs]
         _, gmults = ops.decode_bwd(geom, self.grad_grid, coeffs, auxs, want, scratch=self.scratch,
                                    grad_coeffs=[self.grad_of(p) for p in self.coeff_params])
@@ -148,6 +210,19 @@ class FastTrainer:
                 self.grad_of(spec.grad_params[1]).copy_(g1)
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_g, group=self.group)
+        if self.var_cfg is not None:
+            # sample-independent terms of VariationalDropoutLoss, added once after the reduction: KL of the live masks
+            # (weight ramped on the device) and weight_weights * sum coeff^2, both times batch_scale
+            cfg = self.var_cfg
+            if self._var_sizes:
+                a = self.mask_off
+                b = a + 2 * sum(self._var_sizes)
+                ops.variational_dkl_grad(self.flat_p[a:b], self.flat_g[a:b], self._var_sizes, self.w_dkl, self.step_dev,
+                                         1.0 + float(cfg['weight_dkl_multiplier']), float(cfg.get('weight_dkl_max', 30.0)),
+                                         self.var_scale)
+            ww = float(cfg['weight_weights']) * self.var_scale
+            if ww > 0.0 and self.n_coeff_elems:
+                ops.add_l2_grad(self.flat_g[:self.n_coeff_elems], self.flat_p[:self.n_coeff_elems], ww)
         # sample-independent regularisers (SmallifyLoss): added once, after the reduction
         if self.weight_l2 > 0.0 and self.n_coeff_elems:
             ops.add_l2_grad(self.flat_g[:self.n_coeff_elems], self.flat_p[:self.n_coeff_elems], self.weight_l2)
@@ -163,6 +238,7 @@ class FastTrainer:
         state = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.step_dev.clone())
         trackers = [(d.tracker.EMA.clone(), d.tracker.EMAVar.clone()) for d in self.model.drop
                     if isinstance(d, SmallifyDropout)]
+        w_dkl = self.w_dkl.clone() if self.var_cfg is not None else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -183,6 +259,8 @@ class FastTrainer:
             self.flat_m.copy_(state[1])
             self.flat_v.copy_(state[2])
             self.step_dev.copy_(state[3])
+            if w_dkl is not None:
+                self.w_dkl.copy_(w_dkl)
             it = iter(trackers)
             for d in self.model.drop:
                 if isinstance(d, SmallifyDropout):
@@ -213,6 +291,50 @@ class FastTrainer:
         self._in_coords.copy_(coords.view(self.batch, 3), non_blocking=True)
         self._in_targets.copy_(targets.view(self.batch), non_blocking=True)
         self._run(True)
+
+    def step_host_pipelined(self, coords, targets):
+        """``step_host`` with the transfers taken off the critical path: the H2D copies of step i run on a copy stream
+        into one of two staging buffer pairs while step i-1 computes, and every step's loss is copied to pinned host
+        memory on the compute stream.  Returns the mean squared error of the PREVIOUS call's step (None on the first
+        call); ``flush_host_pipeline()`` returns the last one.  Same arithmetic as ``step_host``."""
+        if self._pipe is None:
+            self._pipe = dict(
+                coords=[torch.zeros((self.batch, 3), device=self.device) for _ in range(2)],
+                targets=[torch.zeros(self.batch, device=self.device) for _ in range(2)],
+                loss=[torch.zeros(1).pin_memory() for _ in range(2)],
+                ready=[torch.cuda.Event() for _ in range(2)], consumed=[torch.cuda.Event() for _ in range(2)],
+                done=[torch.cuda.Event() for _ in range(2)], stream=torch.cuda.Stream(), i=0)
+            for b in range(2):
+                self.capture(('pipe', b))
+        P = self._pipe
+        b = P['i'] & 1
+        cur = torch.cuda.current_stream()
+        if P['i'] >= 2:
+            P['stream'].wait_event(P['consumed'][b])      # the step that read this buffer pair has run
+        with torch.cuda.stream(P['stream']):
+            P['coords'][b].copy_(coords.view(self.batch, 3), non_blocking=True)
+            P['targets'][b].copy_(targets.view(self.batch), non_blocking=True)
+            P['ready'][b].record()
+        cur.wait_event(P['ready'][b])
+        self._run(('pipe', b))
+        P['consumed'][b].record(cur)
+        P['loss'][b].copy_(self.loss_sum, non_blocking=True)
+        P['done'][b].record(cur)
+        prev = None
+        if P['i'] >= 1:
+            P['done'][b ^ 1].synchronize()
+            prev = float(P['loss'][b ^ 1]) / self.batch
+        P['i'] += 1
+        return prev
+
+    def flush_host_pipeline(self):
+        """Loss of the last ``step_host_pipelined`` call (waits for it)."""
+        P = self._pipe
+        if P is None or P['i'] == 0:
+            return None
+        b = (P['i'] - 1) & 1
+        P['done'][b].synchronize()
+        return float(P['loss'][b]) / self.batch
 
     def set_lr(self, lr: float):
         self.lr_dev.fill_(float(lr))
@@ -251,8 +373,21 @@ def solve_phase(model, volume, n_voxels, args, max_pass, lr, decay: bool, seed=0
     """The reference's pass accounting (training.py:87,112-114,178): stop once int(volume_passes) >= max_pass."""
     batch = int(args['batch_size']) * int(args['sample_size'])
     w1, w2 = _regulariser_weights(args) if regularise else (0.0, 0.0)
+    variational = None
+    drop = args.get('drop_type') or ''
+    if regularise and 'variational' in drop:
+        # reference training/training.py:80-84,116-128,205-209: VariationalDropoutLoss, plus a fresh Variance_Model
+        # joining the optimiser for the 'dynamic' flavour, else the constant args['variational_sigma']
+        from ..model.Variational_Dropout_Layer import Variance_Model
+        variational = dict(n_voxels=n_voxels, weight_dkl=float(args['lambda_drop_loss']),
+                           weight_weights=float(args['lambda_weight_loss']),
+                           weight_dkl_multiplier=float(args['weight_dkl_multiplier']))
+        if 'dynamic' in drop:
+            variational['variance_model'] = Variance_Model().to(volume.device).train()
+        else:
+            variational['log_sigma'] = float(args['variational_sigma'])
     trainer = FastTrainer(model, volume, batch // world if world > 1 else batch, lr=lr, seed=seed, rank=rank,
-                          world_size=world, process_group=group, weight_l1=w1, weight_l2=w2)
+                          world_size=world, process_group=group, weight_l1=w1, weight_l2=w2, variational=variational)
     sched = NeurcompDecay(trainer, lr, int(args['pass_decay']), float(args['lr_decay'])) if decay else None
     seen = 0.0
     passes = 0.0

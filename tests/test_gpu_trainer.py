@@ -125,3 +125,31 @@ def test_host_fed_step_equals_device_sampled_step():
         tb.step_host(norm.cpu().pin_memory(), gt.cpu().pin_memory())
         assert abs(ta.last_loss() - tb.last_loss()) <= 1e-5 * abs(ta.last_loss())
     assert float((ta.flat_p - tb.flat_p).abs().max()) <= 1e-5 * float(ta.flat_p.abs().max())
+
+
+def test_pipelined_host_fed_step_equals_serial_one():
+    """step_host_pipelined (copy stream + two staging buffer pairs + deferred loss read) == step_host, step by step."""
+    from latent_feature_grid_compression_b200 import ops
+    from latent_feature_grid_compression_b200.training.fast_loop import FastTrainer
+    vol = _volume()
+    n, steps, seed = 3000, 7, 5
+    a = _make('', 4)
+    b = _make('', 4)
+    b.load_state_dict(copy.deepcopy(a.state_dict()))
+    ta = FastTrainer(a, vol, n, lr=0.008, seed=seed)
+    tb = FastTrainer(b, vol, n, lr=0.008, seed=seed)
+    serial, piped = [], []
+    for s in range(steps):
+        raw, norm, gt = ops.sample(vol.shape, n, seed=seed, sample_offset=s * n, volume=vol, want_gt=True)
+        hc, hg = norm.cpu().pin_memory(), gt.cpu().pin_memory()
+        ta.step_host(hc, hg)
+        serial.append(ta.last_loss())
+        prev = tb.step_host_pipelined(hc, hg)
+        assert (prev is None) == (s == 0)
+        if prev is not None:
+            piped.append(prev)
+    piped.append(tb.flush_host_pipeline())
+    assert len(piped) == steps
+    for x, y in zip(serial, piped):
+        assert abs(x - y) <= 1e-6 * abs(x)
+    assert float((ta.flat_p - tb.flat_p).abs().max()) <= 1e-6 * float(ta.flat_p.abs().max())
