@@ -2,6 +2,7 @@
 #include "lfgc_common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace lfgc {
 
@@ -13,6 +14,14 @@ char* last_error_buffer() {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("LFGC_PDL");   // opt-in: measured on B200, graph-replayed step 82.0 us with PDL edges
+        return e && e[0] == '1';              // against 79.9 us without (the graph already hides the launch latency)
+    }();
+    return on;
+}
 
 static int g_sm_count[64];
 static int g_smem_optin[64];

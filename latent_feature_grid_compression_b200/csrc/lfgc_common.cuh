@@ -43,6 +43,31 @@ inline int fail(int code, const char* fmt, ...) {
         ::lfgc::count_launch();                                                                     \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// The kernels of one training step form a chain of short dependent launches (synthesis levels -> fused training kernel
+// -> partial reduction -> adjoint levels -> Adam).  Every kernel on that chain starts with LFGC_PDL_PROLOGUE():
+// griddepcontrol.wait (all prerequisite grids have completed and their writes are visible) followed by
+// griddepcontrol.launch_dependents, and is launched with the programmatic-stream-serialization attribute, so the
+// launch latency and block scheduling of kernel N+1 overlap kernel N instead of following it.  The trigger comes
+// after the wait on purpose: completion is then transitive along the chain.  Launched without the attribute (the
+// default: inside a CUDA graph the edges gained nothing, see api.cu) the two instructions are no-ops.
+bool pdl_enabled();        // api.cu: LFGC_PDL=1 environment switch (off by default, see there)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int sm_count();            // cached per device
 int max_smem_optin();      // cached per device (bytes)
 
@@ -50,6 +75,12 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // ---- device helpers ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+#define LFGC_PDL_PROLOGUE()                                      \
+    do {                                                         \
+        asm volatile("griddepcontrol.wait;" ::: "memory");       \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+    } while (0)
 
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
     // vectorised fp32 reduction straight into L2 (sm_90+): one 16-byte atomic per 4 channels

@@ -10,15 +10,18 @@ namespace lfgc {
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, const float* __restrict__ lr_ptr,
                             int32_t* __restrict__ step_ptr, float b1, float b2, float eps, float gscale) {
+    LFGC_PDL_PROLOGUE();
     __shared__ float s_step_size, s_bc2_sqrt;
     __shared__ int s_step;
     if (threadIdx.x == 0) {
         const int step = *reinterpret_cast<volatile int32_t*>(step_ptr) + 1;
         s_step = step;
-        const double bc1 = 1.0 - pow((double)b1, (double)step);
-        const double bc2 = 1.0 - pow((double)b2, (double)step);
-        s_step_size = (float)((double)*lr_ptr / bc1);
-        s_bc2_sqrt = (float)sqrt(bc2);
+        // bias corrections 1 - beta^step as -expm1(step * log(beta)): fp32 keeps ~1e-7 relative accuracy without the
+        // cancellation of 1 - pow() and without the slow fp64 pipe (one thread per block sits on this latency)
+        const float bc1 = -expm1f((float)step * logf(b1));
+        const float bc2 = -expm1f((float)step * logf(b2));
+        s_step_size = *lr_ptr / bc1;
+        s_bc2_sqrt = sqrtf(bc2);
     }
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,10 +48,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 __global__ void add_l2_grad_kernel(float* __restrict__ g, const float* __restrict__ p, int64_t n, float w2) {
+    LFGC_PDL_PROLOGUE();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) g[i] = fmaf(w2, p[i], g[i]);
 }
 __global__ void add_l1_grad_kernel(float* __restrict__ g, const float* __restrict__ p, int64_t n, float w) {
+    LFGC_PDL_PROLOGUE();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const float x = p[i];
@@ -72,6 +77,7 @@ __global__ void variational_dkl_grad_kernel(const float* __restrict__ mask_p, fl
                                             const __grid_constant__ DklSegments seg, double* __restrict__ w_dkl,
                                             const int32_t* __restrict__ step_ptr, double ramp, double w_max,
                                             float scale) {
+    LFGC_PDL_PROLOGUE();
     const int step = step_ptr ? *step_ptr : 0;
     const double w_old = w_dkl[step & 1];
     const double w_new = w_old < w_max ? w_old * ramp : w_old;
@@ -112,7 +118,7 @@ extern "C" int lfgc_variational_dkl_grad(const float* mask_params, float* mask_g
         seg.end[i] = acc;
     }
     const long long blocks = acc == 0 ? 1 : (acc + 255) / 256;
-    variational_dkl_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask_params, mask_grads, seg, w_dkl,
+    (void)launch_pdl(variational_dkl_grad_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, mask_params, mask_grads, seg, w_dkl,
                                                                                   step_count, ramp, w_max, scale);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
@@ -124,7 +130,7 @@ extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n
     if (!p || !g || !m || !v || !lr || !step_count || n < 0) return fail(LFGC_E_INVALID, "adam: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t blocks = n == 0 ? 1 : (n + 255) / 256;
-    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale);
+    (void)launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), st, p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }
@@ -132,7 +138,7 @@ extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n
 extern "C" int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream) {
     if (!g || !p || n < 0) return fail(LFGC_E_INVALID, "add_l2_grad: bad arguments");
     if (n == 0) return LFGC_OK;
-    add_l2_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, p, n, 2.0f * weight);
+    (void)launch_pdl(add_l2_grad_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, g, p, n, 2.0f * weight);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }
@@ -140,7 +146,7 @@ extern "C" int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weigh
 extern "C" int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* stream) {
     if (!g || !p || n < 0) return fail(LFGC_E_INVALID, "add_l1_grad: bad arguments");
     if (n == 0) return LFGC_OK;
-    add_l1_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, p, n, weight);
+    (void)launch_pdl(add_l1_grad_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, g, p, n, weight);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }

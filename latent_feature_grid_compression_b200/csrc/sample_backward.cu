@@ -78,6 +78,7 @@ __device__ __forceinline__ void warp_gemm_feat(const float* __restrict__ dz, con
 
 template <int HP, int FUSED>
 __global__ void __launch_bounds__(kThreads, 1) sample_backward_kernel(const __grid_constant__ BwdArgs A) {
+    LFGC_PDL_PROLOGUE();
     constexpr int NO = HP / 4;        // outputs per lane in the sample-major GEMMs
     constexpr int RPW = HP / 4;       // dW rows per warp
     constexpr int RPL = RPW / 4;      // dW rows per lane
@@ -360,25 +361,33 @@ __global__ void __launch_bounds__(kThreads, 1) sample_backward_kernel(const __gr
     for (int e = threadIdx.x; e < A.pstride; e += blockDim.x) dst[e] = accum[e];
 }
 
-// grad[i] (+)= sum over CTA slices; block = 32 entries x 8 slice lanes (fixed summation order: deterministic).
+// grad[i] (+)= sum over CTA slices; block = 32 entries x 32 slice lanes (fixed summation order: deterministic).
 // Entry pcount of every slice is the loss partial; its sum goes to loss_out (overwritten).
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nslices,
-                                                              int pstride, int pcount, float* __restrict__ grad,
-                                                              int accumulate, float* __restrict__ loss_out) {
-    __shared__ float red[8][33];
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partial, int nslices,
+                                                               int pstride, int pcount, float* __restrict__ grad,
+                                                               int accumulate, float* __restrict__ loss_out) {
+    LFGC_PDL_PROLOGUE();
+    __shared__ float red[32][33];
     const int px = threadIdx.x & 31, sy = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + px;
     float s = 0.0f;
     if (i <= pcount) {
-#pragma unroll 4
-        for (int b = sy; b < nslices; b += 8) s += partial[(size_t)b * pstride + i];
+        // independent loads first (one L2 round trip for up to 4 x 32 slices), then the ordered sum
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int b = sy + 32 * u;
+            v[u] = b < nslices ? partial[(size_t)b * pstride + i] : 0.0f;
+        }
+        s = (v[0] + v[1]) + (v[2] + v[3]);
+        for (int b = sy + 128; b < nslices; b += 32) s += partial[(size_t)b * pstride + i];
     }
     red[sy][px] = s;
     __syncthreads();
     if (sy == 0 && i <= pcount) {
         float t = 0.0f;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) t += red[r][px];
+        for (int r = 0; r < 32; ++r) t += red[r][px];
         if (i < pcount) grad[i] = accumulate ? grad[i] + t : t;
         else if (loss_out) loss_out[0] = t;
     }
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 
 void launch_reduce_partials(const float* partial, int nslices, int pstride, int pcount, float* grad, int accumulate,
                             float* loss_out, cudaStream_t st) {
-    reduce_partials_kernel<<<(pcount + 1 + 31) / 32, 256, 0, st>>>(partial, nslices, pstride, pcount, grad, accumulate,
+    (void)launch_pdl(reduce_partials_kernel, dim3((pcount + 1 + 31) / 32), dim3(1024), (size_t)(0), st, partial, nslices, pstride, pcount, grad, accumulate,
                                                                   loss_out);
 }
 
@@ -419,7 +428,7 @@ static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* wo
         return fail(LFGC_E_WORKSPACE, "backward workspace too small: %zu < %zu", workspace_bytes,
                     (size_t)grid * A.pstride * sizeof(float));
     A.partial = reinterpret_cast<float*>(workspace);
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(A);
+    (void)launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)(smem), st, A);
     LFGC_LAUNCH_OK();
     launch_reduce_partials(A.partial, (int)grid, A.pstride, A.pcount, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
     LFGC_LAUNCH_OK();

@@ -232,6 +232,7 @@ __device__ __forceinline__ int mn_off(int s, int j) { return s * 128 + ((((j >> 
 
 template <int FUSED, int TPS>
 __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid_constant__ BwdArgs A, const int K0p) {
+    LFGC_PDL_PROLOGUE();
     constexpr int CW = HP / TPS;   // hidden columns per thread
     constexpr int NT = TILE * TPS;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -658,7 +659,7 @@ static int launch_tps(BwdArgs& A, int K0p, float* grad_mlp, int accumulate, void
     const size_t need = (size_t)grid * A.pstride * sizeof(float);
     if (workspace_bytes < need) return fail(LFGC_E_WORKSPACE, "backward workspace too small: %zu < %zu", workspace_bytes, need);
     A.partial = reinterpret_cast<float*>(workspace);
-    kern<<<(unsigned)grid, TILE * TPS, Lo.total, st>>>(A, K0p);
+    (void)launch_pdl(kern, dim3((unsigned)grid), dim3(TILE * TPS), (size_t)(Lo.total), st, A, K0p);
     LFGC_LAUNCH_OK();
     launch_reduce_partials(A.partial, (int)grid, A.pstride, A.pcount, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
     LFGC_LAUNCH_OK();

@@ -210,6 +210,7 @@ __device__ __forceinline__ void dw_block(const float* __restrict__ dzp, const fl
 // 8 warps -> 255, 12 -> 168, 16 -> 128.
 template <int FUSED, int NC0, int NW, int ACT>
 __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_constant__ BwdArgs A) {
+    LFGC_PDL_PROLOGUE();
     extern __shared__ __align__(16) float smem[];
     PHASE_DECL
     const SampleParams& P = A.P;
@@ -230,8 +231,30 @@ __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_co
     float* AUX = smem + Lo.AUX;
 
     const int H = P.H, in0 = P.in0, L = P.L;
-    load_fwd_weights<HP>(P, A.mlp, Wt, bias, Wf, smem + Lo.bf);
-    load_bwd_weights<HP>(P, A.mlp, Wb, W0f);
+    // Parameter staging: one pass of independent 16-byte loads brings the packed block into shared memory (a single L2
+    // round trip instead of one per loop iteration of the transposing loaders), the layouts are then built from there.
+    // The copy lives in the dz double buffer, which is dead until the first tile's backward pass.
+    if ((A.pcount + 3) / 4 * 4 <= 2 * HP * S && (reinterpret_cast<uintptr_t>(A.mlp) & 15) == 0) {
+        float* stage = DZ;
+        const int n4 = A.pcount >> 2;
+        constexpr int NT = 32 * NW;
+        float4 v[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            if ((int)threadIdx.x + i * NT < n4) v[i] = __ldg(reinterpret_cast<const float4*>(A.mlp) + threadIdx.x + i * NT);
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            if ((int)threadIdx.x + i * NT < n4) reinterpret_cast<float4*>(stage)[threadIdx.x + i * NT] = v[i];
+        for (int e4 = threadIdx.x + 6 * NT; e4 < n4; e4 += NT)
+            reinterpret_cast<float4*>(stage)[e4] = __ldg(reinterpret_cast<const float4*>(A.mlp) + e4);
+        if ((int)threadIdx.x < (A.pcount & 3)) stage[4 * n4 + threadIdx.x] = __ldg(A.mlp + 4 * n4 + threadIdx.x);
+        __syncthreads();
+        load_fwd_weights<HP, true>(P, stage, Wt, bias, Wf, smem + Lo.bf);
+        load_bwd_weights<HP, true>(P, stage, Wb, W0f);
+    } else {
+        load_fwd_weights<HP>(P, A.mlp, Wt, bias, Wf, smem + Lo.bf);
+        load_bwd_weights<HP>(P, A.mlp, Wb, W0f);
+    }
     for (int e = threadIdx.x; e < NW * kBaccStride; e += blockDim.x) bacc[e] = 0.0f;
     for (int e = P.in0p * S + threadIdx.x; e < x_rows(P) * S; e += blockDim.x) X[e] = 0.0f;  // pad rows of the input block
     __syncthreads();
@@ -554,7 +577,7 @@ static int launch_nw(BwdArgs& A, float* grad_mlp, int accumulate, void* workspac
     const size_t need = (size_t)grid * KGmax * A.pstride * sizeof(float);
     if (workspace_bytes < need) return fail(LFGC_E_WORKSPACE, "backward workspace too small: %zu < %zu", workspace_bytes, need);
     A.partial = reinterpret_cast<float*>(workspace);
-    kern<<<(unsigned)grid, 32 * NW, smem, st>>>(A);
+    (void)launch_pdl(kern, dim3((unsigned)grid), dim3(32 * NW), (size_t)(smem), st, A);
     LFGC_LAUNCH_OK();
     launch_reduce_partials(A.partial, (int)grid * KGmax, A.pstride, A.pcount, grad_mlp, accumulate,
                            FUSED ? A.loss_sum : nullptr, st);

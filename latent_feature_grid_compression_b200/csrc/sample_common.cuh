@@ -113,7 +113,13 @@ __device__ __forceinline__ int mlp_wf_off(int L, int in0, int H) { return mlp_w_
 
 // Stage the MLP parameters into shared memory.  Global reads run along the packed buffer (coalesced; 16-byte
 // vectors where the layer's block is aligned), the transposition happens on the shared-memory side.
-template <int HP>
+// SRC_SMEM: `mlp` points at a copy of the packed block in shared memory (plain loads) instead of global memory (__ldg).
+template <bool SRC_SMEM>
+__device__ __forceinline__ float ld_param(const float* p) { return SRC_SMEM ? *p : __ldg(p); }
+template <bool SRC_SMEM>
+__device__ __forceinline__ float4 ld_param4(const float4* p) { return SRC_SMEM ? *p : __ldg(p); }
+
+template <int HP, bool SRC_SMEM = false>
 __device__ __forceinline__ void load_fwd_weights(const SampleParams& P, const float* __restrict__ mlp, float* Wt,
                                                  float* bias, float* Wf, float* bf) {
     const int H = P.H, in0 = P.in0;
@@ -130,7 +136,7 @@ __device__ __forceinline__ void load_fwd_weights(const SampleParams& P, const fl
         if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
             const int n4 = (H * K) >> 2;
             for (int e4 = threadIdx.x; e4 < n4; e4 += blockDim.x) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(W) + e4);
+                const float4 v = ld_param4<SRC_SMEM>(reinterpret_cast<const float4*>(W) + e4);
                 const int e = e4 << 2;
                 const int j = e / K, k = e - j * K;
                 dst[(k + 0) * HP + j] = v.x;
@@ -141,20 +147,20 @@ __device__ __forceinline__ void load_fwd_weights(const SampleParams& P, const fl
         } else {
             for (int e = threadIdx.x; e < H * K; e += blockDim.x) {
                 const int j = e / K, k = e - j * K;
-                dst[k * HP + j] = __ldg(W + e);
+                dst[k * HP + j] = ld_param<SRC_SMEM>(W + e);
             }
         }
         const float* b = mlp + mlp_b_off(l, in0, H);
-        for (int j = threadIdx.x; j < HP; j += blockDim.x) bias[l * HP + j] = j < H ? __ldg(b + j) : 0.0f;
+        for (int j = threadIdx.x; j < HP; j += blockDim.x) bias[l * HP + j] = j < H ? ld_param<SRC_SMEM>(b + j) : 0.0f;
     }
     const float* wf = mlp + mlp_wf_off(P.L, in0, H);
-    for (int j = threadIdx.x; j < HP; j += blockDim.x) Wf[j] = j < H ? __ldg(wf + j) : 0.0f;
-    if (threadIdx.x == 0) *bf = __ldg(wf + H);
+    for (int j = threadIdx.x; j < HP; j += blockDim.x) Wf[j] = j < H ? ld_param<SRC_SMEM>(wf + j) : 0.0f;
+    if (threadIdx.x == 0) *bf = ld_param<SRC_SMEM>(wf + H);
 }
 
 // Backward-layout weights: Wb_l[j][k] = W_l[j][k] (l >= 1, row stride HP) and the layer-0 feature columns
 // W0f[j][c] = W_0[j][3+6F+c] (row stride Cp); pads are zero.
-template <int HP>
+template <int HP, bool SRC_SMEM = false>
 __device__ __forceinline__ void load_bwd_weights(const SampleParams& P, const float* __restrict__ mlp, float* Wb,
                                                  float* W0f) {
     const int H = P.H, in0 = P.in0;
@@ -164,17 +170,17 @@ __device__ __forceinline__ void load_bwd_weights(const SampleParams& P, const fl
         float* dst = Wb + (l - 1) * HP * HP;
         if (H == HP && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
             for (int e4 = threadIdx.x; e4 < (HP * HP) >> 2; e4 += blockDim.x)
-                reinterpret_cast<float4*>(dst)[e4] = __ldg(reinterpret_cast<const float4*>(W) + e4);
+                reinterpret_cast<float4*>(dst)[e4] = ld_param4<SRC_SMEM>(reinterpret_cast<const float4*>(W) + e4);
         } else {
             for (int e = threadIdx.x; e < HP * HP; e += blockDim.x) {
                 const int j = e / HP, k = e % HP;
-                dst[e] = (j < H && k < H) ? __ldg(W + j * H + k) : 0.0f;
+                dst[e] = (j < H && k < H) ? ld_param<SRC_SMEM>(W + j * H + k) : 0.0f;
             }
         }
     }
     for (int e = threadIdx.x; e < HP * P.Cp; e += blockDim.x) {
         const int j = e / P.Cp, c = e % P.Cp;
-        W0f[e] = (j < H && c < P.C) ? __ldg(mlp + j * in0 + 3 + 6 * P.F + c) : 0.0f;
+        W0f[e] = (j < H && c < P.C) ? ld_param<SRC_SMEM>(mlp + j * in0 + 3 + 6 * P.F + c) : 0.0f;
     }
 }
 

@@ -42,6 +42,7 @@ __host__ __device__ constexpr int fwd_act_rows(int in0p) { return in0p > HP ? in
 
 template <int HP, int MODE, int ACT>
 __global__ void __launch_bounds__(kThreads, HP == 32 ? 6 : 2) sample_forward_kernel(const __grid_constant__ FwdArgs A) {
+    LFGC_PDL_PROLOGUE();
     constexpr int S = kTile;
     constexpr int NO = HP / 4;
     extern __shared__ __align__(16) float smem[];
@@ -159,7 +160,7 @@ static int launch_forward(const FwdArgs& A, cudaStream_t st) {
     const int64_t ntiles = (A.n + kTile - 1) / kTile;
     int64_t grid = (int64_t)sm_count() * occ;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(A);
+    (void)launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)(smem), st, A);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }

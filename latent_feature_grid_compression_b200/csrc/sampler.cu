@@ -22,6 +22,7 @@ struct SampleArgs {
 };
 
 __global__ void sample_kernel(const __grid_constant__ SampleArgs A) {
+    LFGC_PDL_PROLOGUE();
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n) return;
     uint64_t base = A.offset;
@@ -158,7 +159,7 @@ extern "C" int lfgc_sample_stream(const float* volume, const int32_t R[3], int64
     A.raw = raw_out;
     A.norm = norm_out;
     A.gt = gt_out;
-    sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A);
+    (void)launch_pdl(sample_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, A);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }

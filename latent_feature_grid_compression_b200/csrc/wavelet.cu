@@ -16,6 +16,7 @@ namespace lfgc {
 __global__ void mask_multiplier_kernel(int mode, int64_t n, const float* __restrict__ p0,
                                        const float* __restrict__ p1, const float* __restrict__ noise,
                                        float threshold, float* __restrict__ mult, float* __restrict__ aux) {
+    LFGC_PDL_PROLOGUE();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float m, a;
@@ -44,6 +45,7 @@ __global__ void mask_param_grad_kernel(int mode, int64_t n, const float* __restr
                                        const float* __restrict__ p1, const float* __restrict__ noise,
                                        const float* __restrict__ gmult, float* __restrict__ g0,
                                        float* __restrict__ g1, int accumulate) {
+    LFGC_PDL_PROLOGUE();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float gm = gmult[i];
@@ -65,6 +67,7 @@ __global__ void mask_param_grad_kernel(int mode, int64_t n, const float* __restr
 
 __global__ void smallify_ema_kernel(const float* __restrict__ betas, float* __restrict__ ema,
                                     float* __restrict__ emavar, int64_t n, float momentum) {
+    LFGC_PDL_PROLOGUE();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float b = betas[i];
@@ -103,6 +106,7 @@ struct LevelArgs {
 // instead of one dependent load per loop iteration; out-of-range positions are clamped and get weight zero.
 template <int NT>
 __global__ void idwt_level_kernel(LevelArgs A) {
+    LFGC_PDL_PROLOGUE();
     constexpr int NP = NT / 2;
     const int64_t nvox = (int64_t)A.t[0] * A.t[1] * A.t[2];
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,6 +167,7 @@ __global__ void idwt_level_kernel(LevelArgs A) {
 
 // any (even) filter length: plain loops
 __global__ void idwt_level_generic_kernel(LevelArgs A) {
+    LFGC_PDL_PROLOGUE();
     const int64_t nvox = (int64_t)A.t[0] * A.t[1] * A.t[2];
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nvox * A.Cs) return;
@@ -209,16 +214,17 @@ __global__ void idwt_level_generic_kernel(LevelArgs A) {
 
 static void launch_idwt_level(const LevelArgs& A, int64_t total, cudaStream_t st) {
     const unsigned blocks = (unsigned)((total + 127) / 128);
-    if (A.ntaps == 2) idwt_level_kernel<2><<<blocks, 128, 0, st>>>(A);
-    else if (A.ntaps == 4) idwt_level_kernel<4><<<blocks, 128, 0, st>>>(A);
-    else if (A.ntaps == 6) idwt_level_kernel<6><<<blocks, 128, 0, st>>>(A);
-    else idwt_level_generic_kernel<<<blocks, 128, 0, st>>>(A);
+    if (A.ntaps == 2) (void)launch_pdl(idwt_level_kernel<2>, dim3(blocks), dim3(128), (size_t)(0), st, A);
+    else if (A.ntaps == 4) (void)launch_pdl(idwt_level_kernel<4>, dim3(blocks), dim3(128), (size_t)(0), st, A);
+    else if (A.ntaps == 6) (void)launch_pdl(idwt_level_kernel<6>, dim3(blocks), dim3(128), (size_t)(0), st, A);
+    else (void)launch_pdl(idwt_level_generic_kernel, dim3(blocks), dim3(128), (size_t)(0), st, A);
 }
 
 // n_coeff == 1 (grid too small for a wavelet level): masked NCDHW -> channels-last copy
 __global__ void copy_to_channels_last_kernel(const float* __restrict__ src, const float* __restrict__ mult,
                                              float* __restrict__ dst, float* __restrict__ also_zero, int C, int Cp,
                                              int64_t nvox) {
+    LFGC_PDL_PROLOGUE();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nvox * Cp) return;
     if (also_zero) also_zero[idx] = 0.0f;
@@ -255,6 +261,7 @@ struct LevelBwdArgs {
 // with warp shuffles when C divides the warp, then one atomic per (k, b).
 template <int NT>
 __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
+    LFGC_PDL_PROLOGUE();
     const int64_t dvol = (int64_t)A.d[0] * A.d[1] * A.d[2];
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = idx < 8 * dvol * A.C;
@@ -346,9 +353,9 @@ __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
 
 static void launch_idwt_level_bwd(const LevelBwdArgs& A, int64_t total, cudaStream_t st) {
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (A.ntaps == 2) idwt_level_bwd_kernel<2><<<blocks, 256, 0, st>>>(A);
-    else if (A.ntaps == 4) idwt_level_bwd_kernel<4><<<blocks, 256, 0, st>>>(A);
-    else idwt_level_bwd_kernel<0><<<blocks, 256, 0, st>>>(A);
+    if (A.ntaps == 2) (void)launch_pdl(idwt_level_bwd_kernel<2>, dim3(blocks), dim3(256), (size_t)(0), st, A);
+    else if (A.ntaps == 4) (void)launch_pdl(idwt_level_bwd_kernel<4>, dim3(blocks), dim3(256), (size_t)(0), st, A);
+    else (void)launch_pdl(idwt_level_bwd_kernel<0>, dim3(blocks), dim3(256), (size_t)(0), st, A);
 }
 
 // n_coeff == 1: adjoint of the masked transpose
@@ -356,6 +363,7 @@ __global__ void copy_from_channels_last_bwd_kernel(const float* __restrict__ gcl
                                                    const float* __restrict__ gmul, float* __restrict__ gcoeff,
                                                    float* __restrict__ gmult, int C, int Cp, int64_t nvox,
                                                    int accumulate) {
+    LFGC_PDL_PROLOGUE();
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nvox) return;
     float msum = 0.0f;
@@ -457,7 +465,7 @@ extern "C" int lfgc_mask_multiplier(int mode, int64_t n, const float* p0, const 
     if (mode == LFGC_MASK_VARIATIONAL && (!p1 || !noise)) return fail(LFGC_E_INVALID, "variational mask needs p1 and noise");
     if (mode == LFGC_MASK_BERNOULLI && !noise) return fail(LFGC_E_INVALID, "bernoulli mask needs noise");
     if (n == 0) return LFGC_OK;
-    mask_multiplier_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mode, n, p0, p1, noise,
+    (void)launch_pdl(mask_multiplier_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, mode, n, p0, p1, noise,
                                                                                          threshold, mult_out, aux_out);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
@@ -470,7 +478,7 @@ extern "C" int lfgc_mask_param_grad(int mode, int64_t n, const float* p0, const 
     if (mode < 0 || mode > LFGC_MASK_BERNOULLI) return fail(LFGC_E_INVALID, "mask mode %d", mode);
     if (!g0 || !p0) return fail(LFGC_E_INVALID, "mask_param_grad: p0/g0 null");
     if (mode == LFGC_MASK_VARIATIONAL && (!p1 || !g1 || !noise)) return fail(LFGC_E_INVALID, "variational grad needs p1,g1,noise");
-    mask_param_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mode, n, p0, p1, noise, gmult,
+    (void)launch_pdl(mask_param_grad_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, mode, n, p0, p1, noise, gmult,
                                                                                          g0, g1, accumulate);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
@@ -480,7 +488,7 @@ extern "C" int lfgc_smallify_ema(const float* betas, float* ema, float* emavar, 
                                  void* stream) {
     if (!betas || !ema || !emavar || n < 0) return fail(LFGC_E_INVALID, "smallify_ema: bad arguments");
     if (n == 0) return LFGC_OK;
-    smallify_ema_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(betas, ema, emavar, n, momentum);
+    (void)launch_pdl(smallify_ema_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, betas, ema, emavar, n, momentum);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }
@@ -499,7 +507,7 @@ extern "C" int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* c
     cudaStream_t st = (cudaStream_t)stream;
     if (w->n_coeff == 1) {
         const int64_t nvox = (int64_t)w->dims[0][0] * w->dims[0][1] * w->dims[0][2];
-        copy_to_channels_last_kernel<<<(unsigned)((nvox * Cp + 255) / 256), 256, 0, st>>>(coeff[0], mult ? mult[0] : nullptr,
+        (void)launch_pdl(copy_to_channels_last_kernel, dim3((unsigned)((nvox * Cp + 255) / 256)), dim3(256), (size_t)(0), st, coeff[0], mult ? mult[0] : nullptr,
                                                                                         grid_cl, also_zero, w->C, Cp, nvox);
         LFGC_LAUNCH_OK();
         return LFGC_OK;
@@ -548,7 +556,7 @@ extern "C" int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_gri
     cudaStream_t st = (cudaStream_t)stream;
     if (w->n_coeff == 1) {
         const int64_t nvox = (int64_t)w->dims[0][0] * w->dims[0][1] * w->dims[0][2];
-        copy_from_channels_last_bwd_kernel<<<(unsigned)((nvox + 127) / 128), 128, 0, st>>>(
+        (void)launch_pdl(copy_from_channels_last_bwd_kernel, dim3((unsigned)((nvox + 127) / 128)), dim3(128), (size_t)(0), st, 
             grad_grid_cl, coeff[0], gmul ? gmul[0] : nullptr, grad_coeff[0], grad_mult ? grad_mult[0] : nullptr, w->C,
             Cp, nvox, accumulate);
         LFGC_LAUNCH_OK();
