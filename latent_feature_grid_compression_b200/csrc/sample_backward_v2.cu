@@ -539,8 +539,8 @@ __global__ void __launch_bounds__(32 * NW, 1) backward_v2_kernel(const __grid_co
         if (threadIdx.x == 0) d[A.pcount] = k == 0 ? bacc[LMAX * HP + HP + 1] : 0.0f;  // loss partial
         for (int l = 0; l < L; ++l)
             for (int j = threadIdx.x; j < H; j += blockDim.x) d[mlp_b_off(l, in0, H) + j] = k == 0 ? bacc[l * HP + j] : 0.0f;
-        for (int j = threadIdx.x; j < H + 1; j += blockDim.x)
-            d[mlp_wf_off(L, in0, H) + j] = k == 0 ? bacc[LMAX * HP + j] : 0.0f;
+        for (int j = threadIdx.x; j < H + 1; j += blockDim.x)   // Wf gradient (H entries), then the bf gradient (slot HP)
+            d[mlp_wf_off(L, in0, H) + j] = k == 0 ? bacc[LMAX * HP + (j < H ? j : HP)] : 0.0f;
     }
     PHASE_MARK(9)  // flush
     PHASE_FLUSH()

@@ -352,3 +352,29 @@ def test_training_trajectory_through_module_api(tag):
         for i, d in enumerate(model.drop):
             assert np.allclose(d.tracker.EMA.cpu().numpy(), g['EMA.%d' % i], atol=1e-6)
             assert np.allclose(d.tracker.EMAVar.cpu().numpy(), g['EMAVar.%d' % i], atol=1e-6)
+
+
+@pytest.mark.parametrize('C,G,H,Lyr,F,n', [(8, 15, 20, 3, 2, 5000), (4, 9, 4, 2, 1, 700), (24, 12, 31, 4, 2, 3000),
+                                         (5, 15, 12, 1, 3, 1500)])
+def test_narrow_hidden_widths_against_oracle(C, G, H, Lyr, F, n):
+    """n_hidden_size below the 32-wide register tile (the NAS range is 4..32, Multi_Objective_NAS.py:127-132): forward
+    and every parameter gradient against the numpy oracle."""
+    from latent_feature_grid_compression_b200.model.model_utils import setup_model
+    from oracle import fvsrn_numpy as O
+    torch.manual_seed(C * 100 + H)
+    model = setup_model(3, H, 1, Lyr, 'fourier', F, '', 0.1, 0.9, 'db2', C, G, '').cuda().train()
+    with torch.no_grad():
+        for lyr in model.net_layers:
+            lyr.bias.uniform_(-0.5, 0.5)
+    coords = (torch.rand(n, 3, device='cuda') * 2.1 - 1.05).requires_grad_(True)
+    w = torch.randn(n, 1, device='cuda')
+    y = model(coords)
+    (y * w).sum().backward()
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    spec = O.Spec(C, G, H, Lyr, F, 'db2', '')
+    yo, ctx = O.model_forward(sd, spec, coords.detach().cpu().numpy(), training=True, keep=True)
+    go = O.model_backward(w.cpu().numpy(), ctx, spec)
+    assert relerr(y.detach().cpu().numpy(), yo) < FWD_TOL
+    for name, p in model.named_parameters():
+        ref = go[name]
+        assert float(np.abs(p.grad.cpu().numpy() - ref).max()) <= GRAD_TOL * float(np.abs(ref).max()), name
