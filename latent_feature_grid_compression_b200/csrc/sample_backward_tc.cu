@@ -5,22 +5,34 @@
 // about a quarter of the instructions of the FFMA2 kernel (sample_backward_v2.cu).
 //
 //   tile = 128 samples = the 128 TMEM lanes; TPS threads share one sample (thread (s, q) owns 32/TPS of the 32 hidden
-//   columns), so a CTA is 128*TPS threads.  The kernel owns all 512 TMEM columns of its SM (one CTA per SM):
+//   columns), so a CTA is 128*TPS threads.  The kernel owns all 512 TMEM columns of its SM (one CTA per SM).
+//
+//   Activations never touch shared memory on the forward path: the A operand of every sample-major contraction is
+//   read by the tensor core straight from TMEM (tcgen05.mma with [a_tmem]; an SS-mode MMA of this shape moves 5 KB of
+//   shared memory per instruction and is paced by that, not by the math).  Each layer input lives in TMEM as its tf32
+//   "hi" part and the exact remainder "lo" (hi + lo == the fp32 value), written with tcgen05.st by the thread that
+//   produced it, so the pair is operand and stash at once:
 //       [  0, 32)  working accumulator: z_l in the forward, dh_l / d(features) in the backward
-//       [ 32, 96)  h_0, the layer-0 input row (fp32)      [ 96,192)  h_1 .. h_3 (fp32)
-//       [192,320)  S'(z_l) of every layer                   [320,448)  dW_l^T accumulators, one 32-column block per layer
-//   Forward, layer l:      z_l = h_l W_l^T          A = h_l  K-major panels (hi/lo), B = W_l  K-major panels
-//   Backward, layer l:     dh_l = dz_l W_l          A = dz_l K-major panels,         B = W_l^T K-major panels
-//                          dW_l^T += [h_l | 1]^T dz_l   A = h_l  MN-major,             B = dz_l MN-major, K = the 128 samples
-//   The weight-gradient accumulators stay in TMEM across the whole persistent loop and leave the SM once.  The ones
-//   column appended to h_l (row 63 of the accumulator) makes the bias gradient part of the same MMA.
+//       [ 32,224)  h_1, h_2, h_3 as (hi | lo), 64 columns each; the layer-0 input (K0p <= 56 columns) borrows the
+//                  h_2 (hi) and h_3 (lo) slots, which are free until layers 2 / 3 are reached
+//       [224,288)  dz_l (hi | lo)                [288,352)  layer-0 input, fp32 (re-split for dW_0 in the backward)
+//       [352,480)  dW_l^T accumulators, one 32-column block per layer, kept across the whole persistent loop
+//   Forward, layer l:      z_l = h_l W_l^T          A = h_l (TMEM),            B = W_l   K-major panels (smem)
+//   Backward, layer l:     dh_l = dz_l W_l          A = dz_l (TMEM),           B = W_l^T K-major panels (smem)
+//                          dW_l^T += [h_l | 1]^T dz_l   A = h_l MN-major (smem), B = dz_l MN-major (smem), K = samples
+//   S'(z_l) stays in registers between the forward and the backward (32/TPS per layer and thread).
+//   The weight-gradient MMAs are committed to their own mbarrier and only waited for when their operand buffers are
+//   about to be overwritten, so they run behind the dz epilogue of the layer and the input stage of the next tile.
+//   The ones column appended to h_l (row 63 of the accumulator) makes the bias gradient part of the same MMA.
+//
+//   Weight-gradient operands: the A block is [h hi g0 | h hi g1 | h lo g0 | h lo g1] (four 32-column groups), read
+//   as ONE M = 128 operand, so the "hi" MMA already yields hi*dz in rows 0..63 and lo*dz in rows 64..127; two MMAs per
+//   K step (B = dz hi, B = dz lo) give hi*hi + lo*hi + hi*lo (+ the negligible lo*lo), and the flush adds rows r, r+64.
 //
 //   tf32 operands read MN-major (contraction over the samples) only work in the SWIZZLE_128B_BASE32B layout on sm_100a
 //   (measured, dbg/umma_addr.cu: every other layout type returns zeros for kind::tf32 with a transposed operand):
 //       element (mn, k) at (mn/32)*LBO + (k/4)*SBO + (k%4)*128 + (((mn%32)/8) ^ (k%4))*32 + (mn%8)*4
-//   i.e. a row-major [sample][32 columns] block whose 32-byte chunks are XOR-swizzled by (sample & 3).  The K-major
-//   operands use the unswizzled 16-byte "chunk panel" layout of sample_forward_tc.cu, so h_l and dz_l are written in
-//   both formats (the forward only in the K-major one; h_l is re-split from its fp32 copy in TMEM in the backward).
+//   i.e. a row-major [sample][32 columns] block whose 32-byte chunks are XOR-swizzled by (sample & 3).
 //
 // Layer-0 columns are permuted as in the forward kernel: k = [features (Cp) | xyz | Fourier | zero pad to K0p].
 #include "sample_backward.cuh"
@@ -44,13 +56,14 @@ namespace btc {
 constexpr int HP = 32;
 constexpr int TILE = 128;
 constexpr int LMAX = 4;
-constexpr int kPanelA = TILE * 16;   // bytes per K chunk (4 columns) of a K-major activation operand
 constexpr int kPanelW = HP * 16;     // bytes per K chunk of a forward weight operand (32 rows)
 constexpr int kBlkMN = TILE * 128;   // bytes of one MN-major [128 samples][32 columns] block
 constexpr int kOnesRow = 63;         // accumulator row that receives the bias gradient (column 31 of MN group 1)
 
 // TMEM column map
-constexpr int cAcc = 0, cH0 = 32, cH1 = 96, cS = 192, cW = 320, kTmemCols = 512;
+constexpr int cAcc = 0, cA1 = 32, cDz = 224, cH0 = 288, cW = 352, kTmemCols = 512;
+__host__ __device__ constexpr int colA_hi(int l) { return l == 0 ? cA1 + 64 : cA1 + 64 * (l - 1); }
+__host__ __device__ constexpr int colA_lo(int l) { return l == 0 ? cA1 + 128 : cA1 + 64 * (l - 1) + 32; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -192,10 +205,40 @@ __device__ __forceinline__ void tmem_st<16>(uint32_t taddr, const float (&v)[16]
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// A operand from TMEM (lane = sample, 8 consecutive 32-bit columns per K = 8 step), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(id), "r"(accumulate)
+        : "memory");
+}
+// One lane of a converged warp (elect.sync).  Issuing tcgen05.mma under `if (threadIdx.x == 0)` makes the compiler wrap
+// every MMA in an ELECT / BRA.U.ANY serialisation loop (~60 cycles per instruction, measured); under a warp-uniform
+// branch + elect.sync it emits the bare UTCMMA sequence.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // ---- shared-memory layout (bytes) ---------------------------------------------------------------------------------------
 struct Layout {
-    int ctrl, bias, wf, yx, Hm, Hk, Dk, Wf, Wb, total;
-    int chunksA;   // K chunks of the K-major activation operand = max(K0p, HP) / 4
+    int ctrl, bias, wf, yx, Hm, Dm, Wf, Wb, total;
     int Np0;       // rows of the layer-0 backward weight operand (feature columns, multiple of 16)
     int wb0;       // bytes of the layer-0 backward weight operand (one of hi / lo)
     int wfBytes, wbBytes;  // bytes of one of hi / lo
@@ -203,24 +246,18 @@ struct Layout {
 
 __host__ __device__ inline Layout make_layout(const SampleParams& P, int K0p, int tps) {
     Layout o;
-    o.chunksA = (K0p > HP ? K0p : HP) / 4;
     o.Np0 = (P.Cp + 15) & ~15;
     o.wb0 = (HP / 4) * o.Np0 * 16;
     o.wfBytes = (K0p + (P.L - 1) * HP) / 4 * kPanelW;
     o.wbBytes = o.wb0 + (P.L - 1) * (HP / 4) * kPanelW;
     int p = 0;
-    o.ctrl = p; p += 64;                      // [0,8) mbarrier, [8,12) TMEM base
+    o.ctrl = p; p += 64;                      // mbarriers: [0,8) forward / dh, [8,16) dW; [24,28) TMEM base
     o.bias = p; p += LMAX * HP * 4;
     o.wf = p;   p += (HP + 4) * 4;
     o.yx = p;   p += tps * TILE * 4;          // partial outputs of the threads sharing a sample
     p = (p + 1023) & ~1023;
     o.Hm = p;   p += 4 * kBlkMN;              // MN-major [h hi g0 | h hi g1 (+ones) | h lo g0 | h lo g1]
-    o.Hk = p;                                 // K-major h_l (hi | lo), forward only; the backward's MN-major dz (hi | lo)
-    {                                         // lives in the same bytes
-        const int hk = 2 * o.chunksA * kPanelA, dm = 2 * kBlkMN;
-        p += hk > dm ? hk : dm;
-    }
-    o.Dk = p;   p += 2 * (HP / 4) * kPanelA;  // K-major dz_l (hi | lo); also the end-of-kernel reduction scratch
+    o.Dm = p;   p += 2 * kBlkMN;              // MN-major dz_l (hi | lo); parameter staging at start-up, flush scratch
     o.Wf = p;   p += 2 * o.wfBytes;
     o.Wb = p;   p += 2 * o.wbBytes;
     o.total = p;
@@ -243,18 +280,15 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     float* wfs = reinterpret_cast<float*>(smem + Lo.wf);
     float* yx = reinterpret_cast<float*>(smem + Lo.yx);
     unsigned char* Hm = smem + Lo.Hm;
-    unsigned char* HkHi = smem + Lo.Hk;
-    unsigned char* HkLo = HkHi + Lo.chunksA * kPanelA;
-    unsigned char* DmHi = smem + Lo.Hk;       // aliases the forward operand (dead once the last forward MMA completed)
+    unsigned char* DmHi = smem + Lo.Dm;
     unsigned char* DmLo = DmHi + kBlkMN;
-    unsigned char* DkHi = smem + Lo.Dk;
-    unsigned char* DkLo = DkHi + (HP / 4) * kPanelA;
     unsigned char* WfHi = smem + Lo.Wf;
     unsigned char* WfLo = WfHi + Lo.wfBytes;
     unsigned char* WbHi = smem + Lo.Wb;
     unsigned char* WbLo = WbHi + Lo.wbBytes;
-    const uint32_t bar = smem_u32(smem + Lo.ctrl);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Lo.ctrl + 8);
+    const uint32_t barA = smem_u32(smem + Lo.ctrl);        // forward layers and dh
+    const uint32_t barB = barA + 8;                        // weight-gradient MMAs
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Lo.ctrl + 24);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp >> 2;                  // which share of the columns
@@ -266,45 +300,66 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
 
     // ---- one-time setup ------------------------------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barA), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barB), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    for (int e = Lo.Hm / 4 + threadIdx.x; e < Lo.total / 4; e += NT) reinterpret_cast<float*>(smem)[e] = 0.0f;
-    __syncthreads();
-    // ones column (column 31 of group 1 of the hi block): bias gradient row of every dW accumulator
-    for (int r = threadIdx.x; r < TILE; r += NT) *reinterpret_cast<float*>(Hm + kBlkMN + mn_off(r, 31)) = 1.0f;
-    for (int l = 0; l < L; ++l) {
-        const int K = l == 0 ? in0 : H;
-        const float* W = A.mlp + mlp_w_off(l, in0, H);
-        const int fbase = (l == 0 ? 0 : (K0p + (l - 1) * HP) / 4) * kPanelW;
-        const int bbase = l == 0 ? 0 : Lo.wb0 + (l - 1) * (HP / 4) * kPanelW;
-        const int brows = l == 0 ? Lo.Np0 : HP;
-        for (int e = threadIdx.x; e < H * K; e += NT) {
-            const int j = e / K, r = e - j * K;
-            int k = r;
-            if (l == 0) k = r < nfix ? Cp + r : r - nfix;  // permuted layer-0 columns
-            float hi, lo;
-            split_tf32(__ldg(W + e), hi, lo);
-            const int fo = fbase + (k >> 2) * kPanelW + j * 16 + (k & 3) * 4;          // forward: B[n = j][K = k]
-            *reinterpret_cast<float*>(WfHi + fo) = hi;
-            *reinterpret_cast<float*>(WfLo + fo) = lo;
-            if (l > 0 || k < Cp) {                                                     // backward: B[n = k][K = j]
-                const int bo = bbase + (j >> 2) * brows * 16 + k * 16 + (j & 3) * 4;
-                *reinterpret_cast<float*>(WbHi + bo) = hi;
-                *reinterpret_cast<float*>(WbLo + bo) = lo;
-            }
-        }
-        const float* b = A.mlp + mlp_b_off(l, in0, H);
-        for (int j = threadIdx.x; j < HP; j += NT) bias[l * HP + j] = j < H ? __ldg(b + j) : 0.0f;
-    }
     {
-        const float* wf = A.mlp + mlp_wf_off(L, in0, H);
-        for (int j = threadIdx.x; j < HP; j += NT) wfs[j] = j < H ? __ldg(wf + j) : 0.0f;
-        if (threadIdx.x == 0) wfs[HP] = __ldg(wf + H);
+        // zero what must read as zero / finite: the second column group of the MN-major activation block (only the ones
+        // column and the layer-0 columns >= 32 are ever written there) and the weight panels (pad rows / columns)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = threadIdx.x; e < kBlkMN / 16; e += NT) {
+            reinterpret_cast<float4*>(Hm + kBlkMN)[e] = z4;
+            reinterpret_cast<float4*>(Hm + 3 * kBlkMN)[e] = z4;
+        }
+        for (int e = threadIdx.x; e < (Lo.total - Lo.Wf) / 16; e += NT) reinterpret_cast<float4*>(smem + Lo.Wf)[e] = z4;
+        // the packed parameter block, staged through shared memory with independent loads (one L2 round trip)
+        float* stage = reinterpret_cast<float*>(DmHi);
+        if ((reinterpret_cast<uintptr_t>(A.mlp) & 15) == 0) {
+            const int n4 = A.pcount >> 2;
+            for (int e4 = threadIdx.x; e4 < n4; e4 += NT)
+                reinterpret_cast<float4*>(stage)[e4] = __ldg(reinterpret_cast<const float4*>(A.mlp) + e4);
+            if ((int)threadIdx.x < (A.pcount & 3)) stage[4 * n4 + threadIdx.x] = __ldg(A.mlp + 4 * n4 + threadIdx.x);
+        } else {
+            for (int e = threadIdx.x; e < A.pcount; e += NT) stage[e] = __ldg(A.mlp + e);
+        }
+    }
+    __syncthreads();
+    {
+        const float* stage = reinterpret_cast<const float*>(DmHi);
+        // ones column (column 31 of group 1 of the hi block): bias gradient row of every dW accumulator
+        for (int r = threadIdx.x; r < TILE; r += NT) *reinterpret_cast<float*>(Hm + kBlkMN + mn_off(r, 31)) = 1.0f;
+        for (int l = 0; l < L; ++l) {
+            const int K = l == 0 ? in0 : H;
+            const float* W = stage + mlp_w_off(l, in0, H);
+            const int fbase = (l == 0 ? 0 : (K0p + (l - 1) * HP) / 4) * kPanelW;
+            const int bbase = l == 0 ? 0 : Lo.wb0 + (l - 1) * (HP / 4) * kPanelW;
+            const int brows = l == 0 ? Lo.Np0 : HP;
+            for (int e = threadIdx.x; e < H * K; e += NT) {
+                const int j = e / K, r = e - j * K;
+                int k = r;
+                if (l == 0) k = r < nfix ? Cp + r : r - nfix;  // permuted layer-0 columns
+                float hi, lo;
+                split_tf32(W[e], hi, lo);
+                const int fo = fbase + (k >> 2) * kPanelW + j * 16 + (k & 3) * 4;          // forward: B[n = j][K = k]
+                *reinterpret_cast<float*>(WfHi + fo) = hi;
+                *reinterpret_cast<float*>(WfLo + fo) = lo;
+                if (l > 0 || k < Cp) {                                                     // backward: B[n = k][K = j]
+                    const int bo = bbase + (j >> 2) * brows * 16 + k * 16 + (j & 3) * 4;
+                    *reinterpret_cast<float*>(WbHi + bo) = hi;
+                    *reinterpret_cast<float*>(WbLo + bo) = lo;
+                }
+            }
+            const float* b = stage + mlp_b_off(l, in0, H);
+            for (int j = threadIdx.x; j < HP; j += NT) bias[l * HP + j] = j < H ? b[j] : 0.0f;
+        }
+        const float* wf = stage + mlp_wf_off(L, in0, H);
+        for (int j = threadIdx.x; j < HP; j += NT) wfs[j] = j < H ? wf[j] : 0.0f;
+        if (threadIdx.x == 0) wfs[HP] = wf[H];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -313,10 +368,10 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     const uint32_t tmem = *tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's lane quarter
     const float bf = wfs[HP];
-    const uint32_t aHkHi = smem_u32(HkHi), aHkLo = smem_u32(HkLo), aDkHi = smem_u32(DkHi), aDkLo = smem_u32(DkLo);
-    const uint32_t aHmHi = smem_u32(Hm), aHmLo = smem_u32(Hm + 2 * kBlkMN), aDmHi = smem_u32(DmHi), aDmLo = smem_u32(DmLo);
+    const uint32_t aHm = smem_u32(Hm), aDmHi = smem_u32(DmHi), aDmLo = smem_u32(DmLo);
     const uint32_t aWfHi = smem_u32(WfHi), aWfLo = smem_u32(WfLo), aWbHi = smem_u32(WbHi), aWbLo = smem_u32(WbLo);
-    uint32_t parity = 0;
+    uint32_t parA = 0, parB = 0;
+    bool pendingB = false;     // weight-gradient MMAs in flight: their operand buffers must not be overwritten yet
     bool first_tile = true;
 
     float accWf[CW];
@@ -327,17 +382,8 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     uint64_t sample_base = A.sample_offset;
     if (FUSED && A.step_dev) sample_base += (uint64_t)(*A.step_dev) * A.step_stride;
 
-    // K-major store of 4 consecutive columns (chunk c) of this thread's sample, hi and lo
-    auto put_k = [&](unsigned char* hi_base, unsigned char* lo_base, int chunk, const float4& v) {
-        float4 hi, lo;
-        split4(v, hi, lo);
-        *reinterpret_cast<float4*>(hi_base + chunk * kPanelA + s * 16) = hi;
-        *reinterpret_cast<float4*>(lo_base + chunk * kPanelA + s * 16) = lo;
-    };
-    // the same into an MN-major block pair (column j0 = first of the 4 columns, within one 32-column group)
-    auto put_mn = [&](unsigned char* hi_base, unsigned char* lo_base, int j0, const float4& v) {
-        float4 hi, lo;
-        split4(v, hi, lo);
+    // this thread's 4 columns [j0, j0+4) of an MN-major block pair
+    auto put_mn = [&](unsigned char* hi_base, unsigned char* lo_base, int j0, const float4& hi, const float4& lo) {
         const int off = mn_off(s, j0);
         *reinterpret_cast<float4*>(hi_base + off) = hi;
         *reinterpret_cast<float4*>(lo_base + off) = lo;
@@ -371,91 +417,119 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         }
         Corners Kc;
         make_corners(P, cx, cy, cz, Kc);
-        for (int c = q; c < K0p / 4; c += TPS) {
-            float v4[4];
-            if (4 * c < Cp) {
-                float4 v[8];
+        // one K chunk (4 columns) of the layer-0 input: tf32 hi / lo operand columns and the fp32 copy
+        auto emit = [&](int c, const float (&v4)[4]) {
+            float hi[4], lo[4];
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) v[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c);
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 4; ++i) split_tf32(v4[i], hi[i], lo[i]);
+            tmem_st<4>(trow + colA_hi(0) + 4 * c, hi);
+            tmem_st<4>(trow + colA_lo(0) + 4 * c, lo);
+            tmem_st<4>(trow + cH0 + 4 * c, v4);
+        };
+        // feature chunks two at a time: 16 independent 128-bit gathers in flight per thread
+        for (int c = q; 4 * c < Cp; c += 2 * TPS) {
+            const int c2 = c + TPS;
+            const bool two = 4 * c2 < Cp;
+            float4 v[8], u[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) v[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c);
+            if (two) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) u[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c2);
+            }
+            float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                a[0] = fmaf(v[cc].x, Kc.w[cc], a[0]);
+                a[1] = fmaf(v[cc].y, Kc.w[cc], a[1]);
+                a[2] = fmaf(v[cc].z, Kc.w[cc], a[2]);
+                a[3] = fmaf(v[cc].w, Kc.w[cc], a[3]);
+            }
+            emit(c, a);
+            if (two) {
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
-                    a.x = fmaf(v[cc].x, Kc.w[cc], a.x);
-                    a.y = fmaf(v[cc].y, Kc.w[cc], a.y);
-                    a.z = fmaf(v[cc].z, Kc.w[cc], a.z);
-                    a.w = fmaf(v[cc].w, Kc.w[cc], a.w);
+                    b[0] = fmaf(u[cc].x, Kc.w[cc], b[0]);
+                    b[1] = fmaf(u[cc].y, Kc.w[cc], b[1]);
+                    b[2] = fmaf(u[cc].z, Kc.w[cc], b[2]);
+                    b[3] = fmaf(u[cc].w, Kc.w[cc], b[3]);
                 }
-                v4[0] = a.x; v4[1] = a.y; v4[2] = a.z; v4[3] = a.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = 4 * c + i - Cp;   // 0..2 xyz, then per frequency [sin x y z | cos x y z]
-                    float val = 0.0f;
-                    if (r < 3) {
-                        val = r == 0 ? cx : (r == 1 ? cy : cz);
-                    } else if (r < nfix) {
-                        const int f = (r - 3) / 6, m = (r - 3) - 6 * f;
-                        const int ax = m >= 3 ? m - 3 : m;
-                        const float coord = ax == 0 ? cx : (ax == 1 ? cy : cz);
-                        float sn, cs;
-                        sincos_cw(__fmul_rn(coord, P.omega[f]), sn, cs);  // argument rounded to fp32 first
-                        val = m >= 3 ? cs : sn;
-                    }
-                    v4[i] = val;
-                }
+                emit(c2, b);
             }
-            put_k(HkHi, HkLo, c, make_float4(v4[0], v4[1], v4[2], v4[3]));
-            tmem_st<4>(trow + cH0 + 4 * c, v4);
+        }
+        for (int c = (Cp >> 2) + q; c < K0p / 4; c += TPS) {
+            float v4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 4 * c + i - Cp;   // 0..2 xyz, then per frequency [sin x y z | cos x y z]
+                float val = 0.0f;
+                if (r < 3) {
+                    val = r == 0 ? cx : (r == 1 ? cy : cz);
+                } else if (r < nfix) {
+                    const int f = (r - 3) / 6, m = (r - 3) - 6 * f;
+                    const int ax = m >= 3 ? m - 3 : m;
+                    const float coord = ax == 0 ? cx : (ax == 1 ? cy : cz);
+                    float sn, cs;
+                    sincos_cw(__fmul_rn(coord, P.omega[f]), sn, cs);  // argument rounded to fp32 first
+                    val = m >= 3 ? cs : sn;
+                }
+                v4[i] = val;
+            }
+            emit(c, v4);
         }
         tmem_st_wait();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         BT_MARK(1)  // input stage
         __syncthreads();
         BT_MARK(2)  // barriers
 
         // ---- forward ------------------------------------------------------------------------------------------------------------
-        float hs[CW], gs[CW];
-        for (int l = 0; l < L; ++l) {
-            if (threadIdx.x == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int nk = (l == 0 ? K0p : HP) / 8;
-                const uint32_t boff = (uint32_t)((l == 0 ? 0 : (K0p + (l - 1) * HP) / 4) * kPanelW);
-                constexpr uint32_t id = idesc(HP, 0, 0);
-                for (int ks = 0; ks < nk; ++ks) {
-                    const uint64_t ah = desc_k(aHkHi + ks * 2 * kPanelA, kPanelA, 128);
-                    const uint64_t al = desc_k(aHkLo + ks * 2 * kPanelA, kPanelA, 128);
-                    const uint64_t bh = desc_k(aWfHi + boff + ks * 2 * kPanelW, kPanelW, 128);
-                    const uint64_t bl = desc_k(aWfLo + boff + ks * 2 * kPanelW, kPanelW, 128);
-                    mma_tf32(tmem + cAcc, ah, bh, id, ks > 0 ? 1u : 0u);
-                    mma_tf32(tmem + cAcc, al, bh, id, 1u);
-                    mma_tf32(tmem + cAcc, ah, bl, id, 1u);
+        float hs[CW], gs[LMAX - 1][CW], glast[CW];   // S'(z_l): l < L-1 in gs[l], the last layer's in glast
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) {
+            if (l < L) {
+                if (warp == 0 && elect_one()) {   // the MMAs of this layer, issued by one lane (see elect_one)
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int nk = (l == 0 ? K0p : HP) / 8;
+                    const uint32_t boff = (uint32_t)((l == 0 ? 0 : (K0p + (l - 1) * HP) / 4) * kPanelW);
+                    constexpr uint32_t id = idesc(HP, 0, 0);
+                    const uint32_t ah = tmem + colA_hi(l), al = tmem + colA_lo(l);
+                    const uint64_t bh0 = desc_k(aWfHi + boff, kPanelW, 128), bl0 = desc_k(aWfLo + boff, kPanelW, 128);
+                    for (int ks = 0; ks < nk; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * 2 * kPanelW) >> 4);
+                        mma_tf32_ts(tmem + cAcc, ah + 8 * ks, bh0 + adv, id, ks > 0 ? 1u : 0u);
+                        mma_tf32_ts(tmem + cAcc, al + 8 * ks, bh0 + adv, id, 1u);
+                        mma_tf32_ts(tmem + cAcc, ah + 8 * ks, bl0 + adv, id, 1u);
+                    }
+                    mma_commit(barA);
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-            }
-            BT_MARK(3)  // MMA issue
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            BT_MARK(4)  // MMA wait
+                BT_MARK(3)  // MMA issue
+                mbar_wait(barA, parA);
+                parA ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                BT_MARK(4)  // MMA wait
 
-            float z[CW];
-            tmem_ld<CW>(trow + cAcc + col0, z);
-            const float* bl_ = bias + l * HP + col0;
+                float z[CW];
+                tmem_ld<CW>(trow + cAcc + col0, z);
+                const float* bl_ = bias + l * HP + col0;
 #pragma unroll
-            for (int i = 0; i < CW; ++i) snake_and_grad_precise(z[i] + bl_[i], hs[i], gs[i]);
-            if (l + 1 < L) {
-                tmem_st<CW>(trow + cS + l * HP + col0, gs);
-                tmem_st<CW>(trow + cH1 + l * HP + col0, hs);   // h_{l+1}
+                for (int i = 0; i < CW; ++i) {
+                    float g;
+                    snake_and_grad_precise(z[i] + bl_[i], hs[i], g);
+                    if (l + 1 < L) { if (l + 1 < LMAX) gs[l < LMAX - 1 ? l : 0][i] = g; } else glast[i] = g;
+                }
+                if (l + 1 < L) {
+                    float hi[CW], lo[CW];
 #pragma unroll
-                for (int c = 0; c < CW / 4; ++c)
-                    put_k(HkHi, HkLo, col0 / 4 + c, make_float4(hs[4 * c], hs[4 * c + 1], hs[4 * c + 2], hs[4 * c + 3]));
-                tmem_st_wait();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                BT_MARK(5)  // forward epilogue
-                __syncthreads();
-                BT_MARK(2)
+                    for (int i = 0; i < CW; ++i) split_tf32(hs[i], hi[i], lo[i]);
+                    tmem_st<CW>(trow + colA_hi(l + 1) + col0, hi);
+                    tmem_st<CW>(trow + colA_lo(l + 1) + col0, lo);
+                    tmem_st_wait();
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    BT_MARK(5)  // forward epilogue
+                    __syncthreads();
+                    BT_MARK(2)
+                }
             }
         }
 
@@ -467,7 +541,7 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             yx[q * TILE + s] = yp;
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();   // also: every thread has read its z_{L-1} and the forward operand is dead
+        __syncthreads();   // also: every thread has read its z_{L-1}
         float dy;
         {
             float y = bf;
@@ -486,114 +560,154 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         if (q == 0) accbf += dy;
         float dz[CW];
 #pragma unroll
-        for (int i = 0; i < CW; ++i) dz[i] = dy * wfs[col0 + i] * gs[i];
+        for (int i = 0; i < CW; ++i) dz[i] = dy * wfs[col0 + i] * glast[i];
         BT_MARK(6)  // output + loss
 
         // ---- backward ----------------------------------------------------------------------------------------------------------
-        for (int l = L - 1; l >= 0; --l) {
-            // dz_l -> both operand formats
 #pragma unroll
-            for (int c = 0; c < CW / 4; ++c) {
-                const float4 v = make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
-                put_k(DkHi, DkLo, col0 / 4 + c, v);
-                put_mn(DmHi, DmLo, col0 + 4 * c, v);
-            }
-            // h_l (fp32 copy in TMEM) -> MN-major operand
-            if (l > 0) {
-                float hv[CW];
-                tmem_ld<CW>(trow + cH1 + (l - 1) * HP + col0, hv);
-#pragma unroll
-                for (int c = 0; c < CW / 4; ++c)
-                    put_mn(Hm, Hm + 2 * kBlkMN, col0 + 4 * c, make_float4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]));
-            } else {
-                for (int c = q; c < K0p / 4; c += TPS) {
-                    float hv[4];
-                    tmem_ld<4>(trow + cH0 + 4 * c, hv);
-                    const int g = (4 * c) >> 5;   // 32-column group
-                    put_mn(Hm + g * kBlkMN, Hm + (2 + g) * kBlkMN, (4 * c) & 31, make_float4(hv[0], hv[1], hv[2], hv[3]));
+        for (int l = LMAX - 1; l >= 0; --l) {
+            if (l < L) {
+                if (pendingB) {   // the previous weight-gradient MMAs still read the operand buffers written below
+                    mbar_wait(barB, parB);
+                    parB ^= 1u;
+                    pendingB = false;
                 }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            BT_MARK(7)  // backward operand staging
-            __syncthreads();
-            BT_MARK(2)
-            if (threadIdx.x == 0) {
+                BT_MARK(11)  // dW wait
+                // dz_l: TMEM operand of dh_l (hi | lo) and MN-major operand of dW_l
+                {
+                    float hi[CW], lo[CW];
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) split_tf32(dz[i], hi[i], lo[i]);
+                    tmem_st<CW>(trow + cDz + col0, hi);
+                    tmem_st<CW>(trow + cDz + HP + col0, lo);
+#pragma unroll
+                    for (int c = 0; c < CW / 4; ++c)
+                        put_mn(DmHi, DmLo, col0 + 4 * c, make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]),
+                               make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]));
+                }
+                // h_l -> MN-major operand (group 0; the layer-0 input also fills its columns >= 32 of group 1)
+                if (l > 0) {
+                    float hi[CW], lo[CW];
+                    tmem_ld<CW>(trow + colA_hi(l) + col0, hi);
+                    tmem_ld<CW>(trow + colA_lo(l) + col0, lo);
+#pragma unroll
+                    for (int c = 0; c < CW / 4; ++c)
+                        put_mn(Hm, Hm + 2 * kBlkMN, col0 + 4 * c, make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]),
+                               make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]));
+                } else {
+                    for (int c = q; c < K0p / 4; c += TPS) {
+                        float hv[4], hi[4], lo[4];
+                        tmem_ld<4>(trow + cH0 + 4 * c, hv);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_tf32(hv[i], hi[i], lo[i]);
+                        const int g = (4 * c) >> 5;   // 32-column group
+                        put_mn(Hm + g * kBlkMN, Hm + (2 + g) * kBlkMN, (4 * c) & 31, make_float4(hi[0], hi[1], hi[2], hi[3]),
+                               make_float4(lo[0], lo[1], lo[2], lo[3]));
+                    }
+                }
+                tmem_st_wait();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                BT_MARK(7)  // backward operand staging
+                __syncthreads();
+                BT_MARK(2)
+                if (warp == 0 && elect_one()) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // dh_l = dz_l W_l  (layer 0: only the feature columns)
+                    {
+                        const uint32_t id = l > 0 ? idesc(HP, 0, 0) : idesc(Lo.Np0, 0, 0);
+                        const uint32_t rows16 = (uint32_t)(l > 0 ? HP : Lo.Np0) * 16;
+                        const uint32_t boff = (uint32_t)(l > 0 ? Lo.wb0 + (l - 1) * (HP / 4) * kPanelW : 0);
+                        const uint64_t bh0 = desc_k(aWbHi + boff, rows16, 128), bl0 = desc_k(aWbLo + boff, rows16, 128);
+                        for (int ks = 0; ks < HP / 8; ++ks) {
+                            const uint64_t adv = (uint64_t)((ks * 2 * rows16) >> 4);
+                            mma_tf32_ts(tmem + cAcc, tmem + cDz + 8 * ks, bh0 + adv, id, ks > 0 ? 1u : 0u);
+                            mma_tf32_ts(tmem + cAcc, tmem + cDz + HP + 8 * ks, bh0 + adv, id, 1u);
+                            mma_tf32_ts(tmem + cAcc, tmem + cDz + 8 * ks, bl0 + adv, id, 1u);
+                        }
+                        mma_commit(barA);
+                    }
+                    // dW_l^T += [h_l | 1]^T dz_l, contraction over the 128 samples (8 per MMA); rows 0..63 of the accumulator
+                    // collect hi * dz, rows 64..127 lo * dz
+                    {
+                        constexpr uint32_t id = idesc(HP, 1, 1);
+                        const uint32_t d = tmem + cW + l * HP;
+                        const uint64_t a0 = desc_mn(aHm), bh0 = desc_mn(aDmHi), bl0 = desc_mn(aDmLo);
+                        for (int ks = 0; ks < TILE / 8; ++ks) {
+                            const uint64_t adv = (uint64_t)((ks * 1024) >> 4);
+                            mma_tf32(d, a0 + adv, bh0 + adv, id, (first_tile && ks == 0) ? 0u : 1u);
+                            mma_tf32(d, a0 + adv, bl0 + adv, id, 1u);
+                        }
+                        mma_commit(barB);
+                    }
+                }
+                pendingB = true;
+                BT_MARK(3)
+                mbar_wait(barA, parA);
+                parA ^= 1u;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // dh_l = dz_l W_l  (layer 0: only the feature columns)
-                {
-                    const uint32_t id = l > 0 ? idesc(HP, 0, 0) : idesc(Lo.Np0, 0, 0);
-                    const uint32_t rows16 = (uint32_t)(l > 0 ? HP : Lo.Np0) * 16;
-                    const uint32_t boff = (uint32_t)(l > 0 ? Lo.wb0 + (l - 1) * (HP / 4) * kPanelW : 0);
-                    for (int ks = 0; ks < HP / 8; ++ks) {
-                        const uint64_t ah = desc_k(aDkHi + ks * 2 * kPanelA, kPanelA, 128);
-                        const uint64_t al = desc_k(aDkLo + ks * 2 * kPanelA, kPanelA, 128);
-                        const uint64_t bh = desc_k(aWbHi + boff + ks * 2 * rows16, rows16, 128);
-                        const uint64_t bl = desc_k(aWbLo + boff + ks * 2 * rows16, rows16, 128);
-                        mma_tf32(tmem + cAcc, ah, bh, id, ks > 0 ? 1u : 0u);
-                        mma_tf32(tmem + cAcc, al, bh, id, 1u);
-                        mma_tf32(tmem + cAcc, ah, bl, id, 1u);
-                    }
-                }
-                // dW_l^T += [h_l | 1]^T dz_l, contraction over the 128 samples (8 per MMA)
-                {
-                    constexpr uint32_t id = idesc(HP, 1, 1);
-                    const uint32_t d = tmem + cW + l * HP;
-                    for (int ks = 0; ks < TILE / 8; ++ks) {
-                        const uint64_t ah = desc_mn(aHmHi + ks * 1024);
-                        const uint64_t al = desc_mn(aHmLo + ks * 1024);
-                        const uint64_t bh = desc_mn(aDmHi + ks * 1024);
-                        const uint64_t bl = desc_mn(aDmLo + ks * 1024);
-                        mma_tf32(d, ah, bh, id, (first_tile && ks == 0) ? 0u : 1u);
-                        mma_tf32(d, al, bh, id, 1u);
-                        mma_tf32(d, ah, bl, id, 1u);
-                    }
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-            }
-            BT_MARK(3)
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            BT_MARK(4)
-            if (l > 0) {
-                float dh[CW], g[CW];
-                tmem_ld<CW>(trow + cAcc + col0, dh);
-                tmem_ld<CW>(trow + cS + (l - 1) * HP + col0, g);
+                BT_MARK(4)
+                if (l > 0) {
+                    float dh[CW];
+                    tmem_ld<CW>(trow + cAcc + col0, dh);
 #pragma unroll
-                for (int i = 0; i < CW; ++i) dz[i] = dh[i] * g[i];
-                BT_MARK(8)  // dz
-            } else {
-                // scatter d(features) into the grid gradient
-                for (int c = q; 4 * c < Cp; c += TPS) {
-                    float d[4];
-                    tmem_ld<4>(trow + cAcc + 4 * c, d);   // warp-collective: outside the per-sample predicate
-                    if (valid) {
+                    for (int i = 0; i < CW; ++i) dz[i] = dh[i] * gs[l > 0 ? l - 1 : 0][i];
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    BT_MARK(8)  // dz
+                } else {
+                    // scatter d(features) into the grid gradient
+                    for (int c = q; 4 * c < Cp; c += TPS) {
+                        float d[4];
+                        tmem_ld<4>(trow + cAcc + 4 * c, d);   // warp-collective: outside the per-sample predicate
+                        if (valid) {
 #pragma unroll
-                        for (int cc = 0; cc < 8; ++cc) {
-                            const float w = Kc.w[cc];
-                            if (w != 0.0f)
-                                red_add_v4(A.grad_grid + Kc.off[cc] + 4 * c, make_float4(d[0] * w, d[1] * w, d[2] * w, d[3] * w));
+                            for (int cc = 0; cc < 8; ++cc) {
+                                const float w = Kc.w[cc];
+                                if (w != 0.0f)
+                                    red_add_v4(A.grad_grid + Kc.off[cc] + 4 * c, make_float4(d[0] * w, d[1] * w, d[2] * w, d[3] * w));
+                            }
                         }
                     }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    BT_MARK(9)  // scatter
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                BT_MARK(9)  // scatter
             }
         }
         first_tile = false;
     }
 
     // ---- flush: weight-gradient accumulators, final-layer gradient, loss ------------------------------------------------------
+    if (pendingB) {
+        mbar_wait(barB, parB);
+        parB ^= 1u;
+        pendingB = false;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* dst = A.partial + (size_t)blockIdx.x * A.pstride;
+    float* xch = reinterpret_cast<float*>(DmHi);   // [layer][row 0..63][32]: the lo * dz halves (accumulator rows 64..127)
+    if ((warp & 3) >= 2) {
+        const int row = (((warp & 3) - 2) << 5) | lane;
+        for (int l = q; l < L; l += TPS) {
+            float r[32];
+            tmem_ld<32>(trow + cW + l * HP, r);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(xch + (l * 64 + row) * 32 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+    }
+    __syncthreads();
     if ((warp & 3) < 2) {   // accumulator rows 0..63 live in lane quarters 0 and 1
         const int row = ((warp & 3) << 5) | lane;
         for (int l = q; l < L; l += TPS) {
             float r[32];
             tmem_ld<32>(trow + cW + l * HP, r);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(xch + (l * 64 + row) * 32 + j);
+                r[j] += o.x; r[j + 1] += o.y; r[j + 2] += o.z; r[j + 3] += o.w;
+            }
             const int Kin = l == 0 ? in0 : H;
             const int woff = mlp_w_off(l, in0, H);
             int orig = -1;   // column of W_l this accumulator row belongs to
@@ -618,7 +732,7 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         }
     }
     {
-        float* red = reinterpret_cast<float*>(DkHi);   // [128][36]: 32 Wf partials | bf | loss
+        float* red = reinterpret_cast<float*>(Hm);   // [128][36]: 32 Wf partials | bf | loss
 #pragma unroll
         for (int i = 0; i < CW; ++i) red[s * 36 + col0 + i] = accWf[i];
         if (q == 0) {
@@ -626,9 +740,21 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             red[s * 36 + 33] = FUSED ? loss_part : 0.0f;
         }
         __syncthreads();
+        // column sums over the 128 samples: 7 row groups x 36 columns in parallel, then 7 partials per column
+        float* red2 = red + TILE * 36;
+        {
+            const int col = threadIdx.x % 36, rg = threadIdx.x / 36;
+            if (rg < 7 && col < 34) {
+                float t = 0.0f;
+                for (int r = rg; r < TILE; r += 7) t += red[r * 36 + col];
+                red2[rg * 36 + col] = t;
+            }
+        }
+        __syncthreads();
         if (threadIdx.x < 34) {
             float t = 0.0f;
-            for (int r = 0; r < TILE; ++r) t += red[r * 36 + threadIdx.x];
+#pragma unroll
+            for (int g = 0; g < 7; ++g) t += red2[g * 36 + threadIdx.x];
             const int wfo = mlp_wf_off(L, in0, H);
             if (threadIdx.x < 32) {
                 if ((int)threadIdx.x < H) dst[wfo + threadIdx.x] = t;
@@ -651,6 +777,7 @@ static int launch_tps(BwdArgs& A, int K0p, float* grad_mlp, int accumulate, void
                       cudaStream_t st) {
     const Layout Lo = make_layout(A.P, K0p, TPS);
     if (Lo.total > max_smem_optin()) return 1;
+    if ((size_t)A.pcount * sizeof(float) > (size_t)2 * kBlkMN) return 1;   // parameter staging buffer
     auto kern = backward_tc_kernel<FUSED, TPS>;
     LFGC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lo.total));
     const int64_t ntiles = (A.n + TILE - 1) / TILE;

@@ -104,6 +104,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     __trap();
 }
 
+// One lane of a converged warp (elect.sync): under `if (t == 0)` the compiler wraps every tcgen05.mma in an ELECT /
+// BRA.U.ANY serialisation loop (~60 cycles per instruction); under a warp-uniform branch + elect.sync it does not.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 struct Layout {
     int bias, Wf, Bhi, Blo, Ahi, Alo, total;  // byte offsets
 };
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(TILE * G, 1) sample_forward_tc_kernel(const __
         float y = 0.0f;
         for (int l = 0; l < L; ++l) {
             // ---- one thread issues the 3xTF32 MMAs of this layer --------------------------------------------------------
-            if (t == 0) {
+            if (warp == 0 && elect_one()) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const int nk = (l == 0 ? K0p : HP) / 8;
                 const uint32_t boff = (uint32_t)((l == 0 ? 0 : (K0p + (l - 1) * HP) / 4) * kPanelB);
