@@ -403,8 +403,9 @@ template <int HP, int FUSED>
 static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
                            cudaStream_t st) {
     {
+        // tensor-core kernel first (LFGC_BACKWARD_TC=0 forces the FFMA2 kernels); it covers the MSE / backward-only modes
         const char* e = getenv("LFGC_BACKWARD_TC");
-        if (e && e[0] == '1' && !A.log_sigma && !(A.P.flags & kFlagPlainRelu)) {
+        if (!(e && e[0] == '0') && !A.log_sigma && !(A.P.flags & kFlagPlainRelu)) {
             const int rc = launch_backward_tc(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
             if (rc != 1) return rc;
         }

@@ -21,8 +21,8 @@ int launch_forward_tc(const SampleParams& P, const float* coords, const float* c
                       int64_t first, int64_t n, const float* grid, const float* mlp, float* out, cudaStream_t st);
 
 static bool forward_tc_enabled() {
-    const char* e = getenv("LFGC_FORWARD_TC");  // "0" forces the FFMA2 kernel, "1" the tcgen05 kernel
-    return e ? (e[0] != '0') : false;
+    const char* e = getenv("LFGC_FORWARD_TC");  // "0" forces the FFMA2 kernel; default: the tcgen05 kernel where it applies
+    return e ? (e[0] != '0') : true;
 }
 
 struct FwdArgs {
