@@ -58,8 +58,9 @@ def peaks():
     if os.path.exists(path):
         with open(path) as f:
             d = json.load(f)
-        return dict(hbm_gbs=float(d['hbm_gbs']), sm_max_mhz=float(d.get('sm_max_mhz', 1965.0)), source='measured')
-    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source='fallback')
+        return dict(hbm_gbs=float(d['hbm_gbs']), sm_max_mhz=float(d.get('sm_max_mhz', 1965.0)),
+                    bf16_tflops=float(d.get('bf16_tflops', 1654.2)), source='measured')
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, bf16_tflops=1654.2, source='fallback')
 
 
 class ClockSampler:
@@ -323,11 +324,21 @@ def run_native(args):
             traffic = json.load(open(tpath)).get('train_step_dram_bytes_per_launch')
         except Exception:
             traffic = None
-    roofline = dict(bound='fp32', kernel='backward_v2_kernel<FUSED=1> (lfgc_train_step)', achieved=ach_tflops,
+    tc_on = os.environ.get('LFGC_BACKWARD_TC', '1') != '0'
+    kname = 'backward_tc_kernel<FUSED=1,TPS=2> (lfgc_train_step, tcgen05 3xTF32)' if tc_on \
+        else 'backward_v2_kernel<FUSED=1> (lfgc_train_step, FFMA2)'
+    roofline = dict(bound='fp32', kernel=kname, achieved=ach_tflops,
                     peak=fp32_peak, unit='TFLOP/s', frac=ach_tflops / fp32_peak, traffic=traffic,
                     kernel_us=k_ms * 1e3, peak_source='148 SMs x 128 FFMA x 2 x %s sm_max_mhz' % pk['source'],
-                    note='fp32 FFMA-bound (SURVEY 8d): neither HBM nor tensor pipe limits this path; '
-                         'algorithmic FLOPs = 23616/sample')
+                    note='algorithmic FLOPs = 23616/sample (SURVEY 8d).  Neither HBM nor the tensor pipe bounds this path: the '
+                         'contractions run on tcgen05 (tensor pipe 7 % active in ncu, see roofline_tensor), the kernel time '
+                         'is the per-sample fp32 work left on the SM (gather, Fourier, SnakeAlt, hi/lo splits, scatter), '
+                         'so the CUDA-core FFMA2 peak stays the yardstick (it is what the FFMA2 kernel is bounded by)')
+    tf32_peak = pk.get('bf16_tflops', 1654.2) / 2.0
+    roofline_tensor = dict(bound='tensor', achieved=ach_tflops, peak=tf32_peak, unit='TFLOP/s',
+                           frac=ach_tflops / tf32_peak, executed_over_algorithmic=2.6,
+                           peak_source='dense tf32 = measured bf16 cuBLAS peak / 2 (%s)' % pk['source'],
+                           note='3xTF32 executes 3 MMAs per sample-major product and 2 per weight-gradient product')
     hbm_ach = HBM_BYTES_PER_SAMPLE * n / (k_ms * 1e-3) / 1e9
     roofline_hbm = dict(bound='hbm', achieved=hbm_ach, peak=pk['hbm_gbs'], unit='GB/s', frac=hbm_ach / pk['hbm_gbs'],
                         traffic=traffic, peak_source=pk['source'])
@@ -359,7 +370,7 @@ def run_native(args):
                     e2e=e2e, gpu_launches=int(trainer.launches_per_step * steps_per_pass * args.steps),
                     clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'], reasons=clk['reasons'],
                                 samples=clk['samples']),
-                    roofline=roofline, roofline_hbm=roofline_hbm, reconstruct=recon, cpu_baseline=cpu,
+                    roofline=roofline, roofline_hbm=roofline_hbm, roofline_tensor=roofline_tensor, reconstruct=recon, cpu_baseline=cpu,
                     e2e_module_api=e2e_module,
                     extra=dict(us_per_optimiser_step=1e3 * total_ms / (args.steps * steps_per_pass),
                                hot_l2_samples_per_s=steps_per_pass * n * world / (hot_ms * 1e-3),
