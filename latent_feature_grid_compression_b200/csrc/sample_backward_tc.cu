@@ -30,7 +30,7 @@
 //   K step (B = dz hi, B = dz lo) give hi*hi + lo*hi + hi*lo (+ the negligible lo*lo), and the flush adds rows r, r+64.
 //
 //   tf32 operands read MN-major (contraction over the samples) only work in the SWIZZLE_128B_BASE32B layout on sm_100a
-//   (measured, dbg/umma_addr.cu: every other layout type returns zeros for kind::tf32 with a transposed operand):
+//   (measured, profiles/microbench/umma_addr.cu: every other layout type returns zeros for kind::tf32 with a transposed operand):
 //       element (mn, k) at (mn/32)*LBO + (k/4)*SBO + (k%4)*128 + (((mn%32)/8) ^ (k%4))*32 + (mn%8)*4
 //   i.e. a row-major [sample][32 columns] block whose 32-byte chunks are XOR-swizzled by (sample & 3).
 //

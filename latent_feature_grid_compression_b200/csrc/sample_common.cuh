@@ -185,7 +185,7 @@ __device__ __forceinline__ void load_bwd_weights(const SampleParams& P, const fl
 }
 
 // Packed fp32 FMA (sm_100+): d.xy += a * b.xy.  One issue slot for two FMAs; measured on B200: 117 FMA/clk/SM
-// with FFMA2 against 64 FMA/clk/SM with scalar 3-register FFMA (dbg/fma_bench.cu), so every contraction uses it.
+// with FFMA2 against 64 FMA/clk/SM with scalar 3-register FFMA (profiles/microbench/fma_bench.cu), so every contraction uses it.
 __device__ __forceinline__ void ffma2(float2& d, float a, float2 b) {
     unsigned long long ra, rb, rd;
     asm("mov.b64 %0, {%1, %1};" : "=l"(ra) : "f"(a));

@@ -13,7 +13,7 @@
 //   Per layer: one thread issues the 12 MMAs and commits to an mbarrier; all threads wait, read their accumulator row
 //   with tcgen05.ld (32 columns), apply bias + SnakeAlt, split and write the next A operand.
 //   A kernel that allocates TMEM is limited to ONE resident CTA per SM (measured: cudaOccupancy reports 1 for any
-//   kernel containing tcgen05.alloc, dbg/tmem_occ.cu), so latency hiding happens inside the CTA: it holds G
+//   kernel containing tcgen05.alloc, profiles/microbench/tmem_occ.cu), so latency hiding happens inside the CTA: it holds G
 //   independent "tile groups" of 128 threads, each with its own operand buffer, 32 TMEM columns, mbarrier and tile
 //   loop, sharing one copy of the weight panels; while one group waits for its MMAs the others run their epilogues.
 //
