@@ -377,9 +377,33 @@ def run_native(args):
                                wall_s_timed_region=wall, final_mse=final_loss,
                                launches_per_optimiser_step=int(trainer.launches_per_step)))
         print(json.dumps(line), flush=True)
-    if world > 1:
+    _shutdown(world, dist, trainer)
+
+
+def _shutdown(world, dist, trainer):
+    """Leave promptly once the JSON line is out.  Observed on a 2-GPU box: with NCCL collectives captured in CUDA
+    graphs the workers can sit in the process-group / interpreter teardown indefinitely after the result was printed
+    (the launcher then waits for them).  So: release the graphs first, tear down cooperatively under a watchdog, and
+    hard-exit with status 0 -- nothing after the printed line carries information."""
+    import gc
+    import threading
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world <= 1:
+        return
+    threading.Timer(20.0, lambda: os._exit(0)).start()      # watchdog: never outlive the result by more than 20 s
+    try:
+        torch.cuda.synchronize()
+        trainer._graphs.clear()      # CUDA graphs holding captured NCCL kernels go first
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
+    except Exception:
+        pass
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def reconstruct_rate(model, volume, rank, world, dev, fp32_peak, reps=10):
