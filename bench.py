@@ -240,6 +240,17 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # a rank that dies leaves its peers waiting inside a collective: bound the whole run instead of hanging
+        import threading
+        limit = float(os.environ.get('LFGC_BENCH_TIME_LIMIT_S', '420'))
+
+        def _give_up():
+            sys.stderr.write('bench.py: rank %d exceeded %.0f s, aborting\n' % (rank, limit))
+            sys.stderr.flush()
+            os._exit(3)
+        guard = threading.Timer(limit, _give_up)
+        guard.daemon = True
+        guard.start()
         dist.init_process_group('nccl', device_id=dev)
         dist.barrier()
     from latent_feature_grid_compression_b200 import ops
