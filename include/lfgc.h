@@ -256,6 +256,20 @@ int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const flo
 int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 
+/* Everything of one optimiser step that is not per-sample, for mask-free models, in ONE cooperative launch
+ * (grid-wide barriers between the phases instead of kernel boundaries).  phases is a bit mask:
+ *   1  synthesis adjoint (lfgc_decode_bwd without multipliers): grad_grid_cl -> grad_coeff[l] (overwritten)
+ *   2  Adam over the flat buffers (lfgc_adam; step_count[0] is incremented, step_count[1] is not used)
+ *   4  synthesis of the (updated) coefficients (lfgc_decode_fwd without multipliers) -> grid_cl, also_zero cleared
+ * i.e. 1|2|4 replaces lfgc_decode_bwd + lfgc_adam + lfgc_decode_fwd of the NEXT step (training/training.py:137,
+ * torch.optim.Adam.step, model/Feature_Grid_Model.py:102-108); data-parallel callers run 1, all-reduce, then 2|4.
+ * coeff / grad_coeff are HOST arrays of n_coeff DEVICE pointers; scratch as for lfgc_decode_fwd.  Filter lengths 2
+ * and 4 (haar, db2).  Needs a device that supports cooperative launches (every B200 does). */
+int lfgc_step_glue(const lfgc_wavelet_desc* w, int Cp, float* const* coeff, float* const* grad_coeff, float* scratch,
+                   const float* grad_grid_cl, float* grid_cl, float* also_zero, float* p, const float* g, float* m,
+                   float* v, int64_t n, const float* lr, int32_t* step_count, float beta1, float beta2, float eps,
+                   float grad_scale, int phases, void* stream);
+
 /* Gradient of the KL regulariser of VariationalDropoutLoss (model/Variational_Dropout_Layer.py:54-69,115-122) added
  * in place to the mask-parameter gradients, and the per-step ramp of its weight (:57-58).  mask_params / mask_grads
  * point at a buffer holding, per mask layer i, [log_thetas_i (n_i) | log_var_i (n_i)]; layer_sizes is a HOST array

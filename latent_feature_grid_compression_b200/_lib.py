@@ -74,6 +74,8 @@ _SIGNATURES = {
     'lfgc_adam': (C.c_int, [_f, _f, _f, _f, _i64, _f, _f, C.c_float, C.c_float, C.c_float, C.c_float, _f]),
     'lfgc_add_l2_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_add_l1_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
+    'lfgc_step_glue': (C.c_int, [C.POINTER(WaveletDesc), C.c_int, C.POINTER(_f), C.POINTER(_f), _f, _f, _f, _f, _f, _f, _f, _f, _i64, _f, _f,
+                                 C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _f]),
     'lfgc_variational_dkl_grad': (C.c_int, [_f, _f, C.c_int, C.POINTER(C.c_int64), _f, _f, C.c_double, C.c_double,
                                             C.c_float, _f]),
 }

@@ -376,6 +376,19 @@ def adam(p, g, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_sc
                           _p(_req(lr_dev, 'lr')), _p(step_dev), beta1, beta2, eps, grad_scale, _stream()), 'lfgc_adam')
 
 
+def step_glue(geom: Geometry, coeffs, grad_coeffs, scratch, grad_grid_cl, grid_cl, also_zero, p, g, m, v, lr_dev,
+              step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, phases=7):
+    """Synthesis adjoint (1) + Adam (2) + synthesis of the updated coefficients (4) in one cooperative launch
+    (lfgc_step_glue, mask-free models)."""
+    lib = L.load()
+    _req(step_dev, 'step', torch.int32)
+    L.check(lib.lfgc_step_glue(ct.byref(geom.wavelet_desc), geom.Cp, L.ptr_array([_p(c) for c in coeffs]),
+                               L.ptr_array([_p(c) for c in grad_coeffs]), _p(scratch), _p(grad_grid_cl), _p(grid_cl),
+                               _p(also_zero), _p(_req(p, 'p')), _p(_req(g, 'g')), _p(_req(m, 'm')), _p(_req(v, 'v')),
+                               p.numel(), _p(_req(lr_dev, 'lr')), _p(step_dev), beta1, beta2, eps, grad_scale,
+                               int(phases), _stream()), 'lfgc_step_glue')
+
+
 def add_l2_grad(g, p, weight: float):
     L.check(L.load().lfgc_add_l2_grad(_p(_req(g, 'g')), _p(_req(p, 'p')), p.numel(), float(weight), _stream()),
             'lfgc_add_l2_grad')

@@ -133,6 +133,13 @@ class FastTrainer:
         self._in_coords = torch.zeros((self.batch, 3), device=self.device, dtype=torch.float32)
         self._in_targets = torch.zeros(self.batch, device=self.device, dtype=torch.float32)
         self._pipe = None   # lazily built state of step_host_pipelined
+        # opt-in (LFGC_GLUE=1): adjoint + Adam + next step's synthesis in one cooperative launch (lfgc_step_glue); only
+        # for mask-free models without regularisers, haar / db2
+        import os
+        self._glue = (os.environ.get('LFGC_GLUE', '0') == '1' and self.var_cfg is None and not self.mask_params
+                      and all(s is None for s in model.mask_specs()) and self.weight_l1 == 0.0 and self.weight_l2 == 0.0
+                      and (len(self.coeff_params) == 1 or model.filter.filter_length in (2, 4)))
+        self._glue_primed = False
         if self.var_cfg is not None:
             cfg = self.var_cfg
             self.var_scale = float(cfg['n_voxels']) / float(self.batch * self.world)   # batch_scale of the reference
@@ -166,6 +173,8 @@ class FastTrainer:
         in_coords, in_targets = self._in_coords, self._in_targets
         if isinstance(host_fed, tuple):   # ('pipe', b): the pipelined host-fed step reads staging buffer pair b
             in_coords, in_targets = self._pipe['coords'][host_fed[1]], self._pipe['targets'][host_fed[1]]
+        if self._glue:
+            return self._step_body_glue(host_fed, in_coords, in_targets)
         specs = model.mask_specs()
         mults, auxs = _multipliers(specs)
         coeffs = [p.data for p in self.coeff_params]
@@ -232,6 +241,37 @@ class FastTrainer:
         ops.adam(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_dev, self.step_dev, self.betas[0],
                  self.betas[1], self.eps)
 
+    def _prime_glue(self):
+        """The glue step expects the grid of the CURRENT coefficients (and a cleared gradient accumulator) on entry:
+        every step leaves them behind for the next one, this provides them for the first."""
+        coeffs = [p.data for p in self.coeff_params]
+        ops.decode_fwd(self.geom, coeffs, [None] * len(coeffs), scratch=self.scratch, out=self.grid_cl,
+                       also_zero=self.grad_grid)
+        self._glue_primed = True
+
+    def _step_body_glue(self, host_fed, in_coords, in_targets):
+        geom = self.geom
+        n_global = self.batch * self.world
+        ops.train_step(geom, self.volume, self.batch, self.seed,
+                       parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
+                       parallel.loss_scale(self.batch, self.world), self.grid_cl,
+                       self.mlp_flat, self.grad_grid, self.flat_g[self.mlp_off:], self.loss_sum, self.workspace,
+                       step_dev=self.step_dev, step_stride=n_global,
+                       coords=in_coords if host_fed else None, targets=in_targets if host_fed else None)
+        coeffs = [p.data for p in self.coeff_params]
+        gcoeffs = [self.grad_of(p) for p in self.coeff_params]
+
+        def glue(phases):
+            ops.step_glue(geom, coeffs, gcoeffs, self.scratch, self.grad_grid, self.grid_cl, self.grad_grid, self.flat_p,
+                          self.flat_g, self.flat_m, self.flat_v, self.lr_dev, self.step_dev, self.betas[0],
+                          self.betas[1], self.eps, phases=phases)
+        if self.world > 1:
+            glue(1)
+            torch.distributed.all_reduce(self.flat_g, group=self.group)
+            glue(6)
+        else:
+            glue(7)
+
     def capture(self, host_fed=False):
         """Warm up eagerly (counts launches), then record the step into a CUDA graph; the optimiser state the
         warm-up touched is restored so that training starts from the initial state."""
@@ -239,6 +279,8 @@ class FastTrainer:
         trackers = [(d.tracker.EMA.clone(), d.tracker.EMAVar.clone()) for d in self.model.drop
                     if isinstance(d, SmallifyDropout)]
         w_dkl = self.w_dkl.clone() if self.var_cfg is not None else None
+        if self._glue and not self._glue_primed:
+            self._prime_glue()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -267,6 +309,8 @@ class FastTrainer:
                     ema, var = next(it)
                     d.tracker.EMA.copy_(ema)
                     d.tracker.EMAVar.copy_(var)
+        if self._glue:
+            self._prime_glue()   # the warm-up steps moved the coefficients: decode the restored ones
         torch.cuda.synchronize()
 
     def _run(self, host_fed):

@@ -153,3 +153,35 @@ def test_pipelined_host_fed_step_equals_serial_one():
     for x, y in zip(serial, piped):
         assert abs(x - y) <= 1e-6 * abs(x)
     assert float((ta.flat_p - tb.flat_p).abs().max()) <= 1e-6 * float(ta.flat_p.abs().max())
+
+
+@pytest.mark.skipif(__import__('os').environ.get('LFGC_TEST_GLUE', '0') != '1',
+                    reason='lfgc_step_glue is opt-in until measured on a B200 (LFGC_TEST_GLUE=1 runs this)')
+@pytest.mark.parametrize('wavelet,G', [('db2', 15), ('haar', 16), ('db2', 5)])
+def test_glue_step_equals_separate_kernels(wavelet, G, monkeypatch):
+    """LFGC_GLUE=1 (adjoint + Adam + next synthesis in one cooperative launch) against the separate kernels."""
+    from latent_feature_grid_compression_b200.model.model_utils import setup_model
+    from latent_feature_grid_compression_b200.training.fast_loop import FastTrainer
+    vol = _volume()
+
+    def make():
+        torch.manual_seed(2)
+        return setup_model(3, 32, 1, 4, 'fourier', 2, '', 0.1, 0.9, wavelet, 8, G, '').cuda().train()
+    a, b = make(), make()
+    b.load_state_dict(copy.deepcopy(a.state_dict()))
+    monkeypatch.setenv('LFGC_GLUE', '0')
+    ta = FastTrainer(a, vol, 3000, lr=0.008, seed=4)
+    monkeypatch.setenv('LFGC_GLUE', '1')
+    tb = FastTrainer(b, vol, 3000, lr=0.008, seed=4)
+    assert tb._glue and not ta._glue
+    for _ in range(7):
+        ta.step()
+        tb.step()
+    assert int(tb.step_dev[0]) == 7 and tb.launches_per_step == 3
+    assert abs(ta.last_loss() - tb.last_loss()) <= 1e-5 * abs(ta.last_loss())
+    assert float((ta.flat_p - tb.flat_p).abs().max()) <= 1e-5 * float(ta.flat_p.abs().max())
+    # the glue step leaves the grid of the UPDATED coefficients behind (the separate path decodes at the next step's start)
+    from latent_feature_grid_compression_b200 import ops
+    fresh = ops.decode_fwd(tb.geom, [p.data for p in tb.coeff_params], [None] * len(tb.coeff_params))
+    assert float((fresh - tb.grid_cl).abs().max()) <= 1e-6 * float(fresh.abs().max())
+    assert float(tb.grad_grid.abs().max()) == 0.0
