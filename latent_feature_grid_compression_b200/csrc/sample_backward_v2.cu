@@ -1,7 +1,8 @@
 // Fused training kernel, wide variant (the one the shipped configurations run): same mathematics as the generic
 // kernel in sample_backward.cu, re-organised for issue-slot and latency efficiency on sm_100a:
 //
-//  * 4 to 14 warps per CTA (one CTA per SM), 16 samples per warp: up to 3.5 resident warps per scheduler instead of 1,
+//  * 4 to 8 warps per CTA (one CTA per SM), 16 samples per warp: 2 resident warps per scheduler instead of 1 (wider
+//    CTAs are register-limited to 168 / 128 registers per thread and spill: measured slower),
 //    which is what hides the shared-memory / L2 latencies the generic kernel exposes (ncu: issue-active 32 %).
 //  * lane = 4 samples x 4 outputs; the multiply-accumulates are packed FFMA2 (fma.rn.f32x2, sm_100+): one issue
 //    slot per two FMAs, the activation broadcast folded into the instruction's scalar operand.
@@ -585,7 +586,7 @@ static int launch_nw(BwdArgs& A, float* grad_mlp, int accumulate, void* workspac
     return LFGC_OK;
 }
 
-static const int kWidths[] = {8, 7, 6, 5, 4, 12, 14, 10};  // ties go to the first
+static const int kWidths[] = {8, 7, 6, 5, 4};  // ties go to the first; 10-14 warps were measured and never win
 
 template <int FUSED, int NC0>
 static int launch(BwdArgs& A, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -601,9 +602,6 @@ static int launch(BwdArgs& A, float* grad_mlp, int accumulate, void* workspace, 
         if (!best || c < best_cost) { best = nw; best_cost = c; }
     }
     switch (best) {
-        case 14: return launch_nw<FUSED, NC0, 14>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
-        case 12: return launch_nw<FUSED, NC0, 12>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
-        case 10: return launch_nw<FUSED, NC0, 10>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
         case 8: return launch_nw<FUSED, NC0, 8>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
         case 7: return launch_nw<FUSED, NC0, 7>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);
         case 6: return launch_nw<FUSED, NC0, 6>(A, grad_mlp, accumulate, workspace, workspace_bytes, st);

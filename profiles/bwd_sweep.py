@@ -28,7 +28,7 @@ gm = torch.empty(geom.mlp_param_count, device=dev)
 loss = torch.zeros(1, device=dev)
 ref = None
 for n in [int(v) for v in os.environ.get('LFGC_SWEEP_N', '32768,262144').split(',')]:
-    for nw in [0, 4, 5, 6, 7, 8, 10, 12, 14]:
+    for nw in [0, 4, 5, 6, 7, 8]:
         if nw:
             os.environ['LFGC_BWD_WARPS'] = str(nw)
         else:
