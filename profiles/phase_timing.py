@@ -30,7 +30,7 @@ gm = torch.empty(geom.mlp_param_count, device=dev)
 loss = torch.zeros(1, device=dev)
 names = ['setup', 'input', 'forward', 'dz+bias', 'barrier', 'dW', 'dh/dfeat', 'scatter', 'tile barrier', 'flush']
 for n in (32768, 262144):
-    for nw in (8, 12):
+    for nw in (7, 8):
         os.environ['LFGC_BWD_WARPS'] = str(nw)
         for _ in range(3):
             ops.train_step(geom, volume, n, 1, 0, 1.0 / n, grid_cl, mlp, gg, gm, loss, ws)

@@ -378,38 +378,3 @@ def test_narrow_hidden_widths_against_oracle(C, G, H, Lyr, F, n):
     for name, p in model.named_parameters():
         ref = go[name]
         assert float(np.abs(p.grad.cpu().numpy() - ref).max()) <= GRAD_TOL * float(np.abs(ref).max()), name
-
-
-@pytest.mark.parametrize('tag', ['basic_db2_c16_g15', 'basic_haar_c4_g16', 'smallify_db2_c6_g15'])
-def test_ffma2_kernel_family_keeps_parity(tag, monkeypatch):
-    """The tcgen05 kernels are the default where the shape is covered; the FFMA2 kernels (wider shapes, the
-    log-likelihood step, LFGC_*_TC=0) must hold the same gates on the same fixtures."""
-    monkeypatch.setenv('LFGC_FORWARD_TC', '0')
-    monkeypatch.setenv('LFGC_BACKWARD_TC', '0')
-    test_forward_train_and_eval(tag)
-    test_backward_all_parameters(tag)
-
-
-def test_kernel_families_agree_on_ragged_and_tiny_batches(monkeypatch):
-    """n = 1, a partial tile and a multi-wave batch: tensor-core and FFMA2 kernels against each other."""
-    from latent_feature_grid_compression_b200 import ops
-    from latent_feature_grid_compression_b200.model.model_utils import setup_model
-    torch.manual_seed(12)
-    m = setup_model(3, 32, 1, 4, 'fourier', 2, '', 0.1, 0.9, 'db2', 16, 15, '').cuda()
-    geom = m.geometry()
-    grid = ops.decode_fwd(geom, [f.detach().contiguous() for f in m.feature_grid], [None] * len(m.feature_grid))
-    mlp = m.mlp_flat()
-    for n in (1, 129, 20000):
-        coords = torch.rand(n, 3, device='cuda') * 2.1 - 1.05
-        gout = torch.randn(n, device='cuda')
-        res = {}
-        for flag in ('1', '0'):
-            monkeypatch.setenv('LFGC_FORWARD_TC', flag)
-            monkeypatch.setenv('LFGC_BACKWARD_TC', flag)
-            y = ops.sample_forward(geom, coords, grid, mlp)
-            gg, gm = ops.sample_backward(geom, coords, gout, grid, mlp)
-            torch.cuda.synchronize()
-            res[flag] = (y.clone(), gg.clone(), gm.clone())
-        # each family is gated at 1e-5 against the oracle, so two families may differ by twice that
-        for a, b in zip(res['1'], res['0']):
-            assert float((a - b).abs().max()) <= 2e-5 * max(float(b.abs().max()), 1e-30)
