@@ -406,6 +406,11 @@ static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* wo
         // tensor-core kernel first (LFGC_BACKWARD_TC=0 forces the FFMA2 kernels); it covers the MSE / backward-only modes
         const char* e = getenv("LFGC_BACKWARD_TC");
         if (!(e && e[0] == '0') && !A.log_sigma && !(A.P.flags & kFlagPlainRelu)) {
+            const char* iw = getenv("LFGC_TC_ISSUER");   // opt-in: dedicated MMA-issue warp variant
+            if (iw && iw[0] == '1') {
+                const int rc9 = launch_backward_tc9(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
+                if (rc9 != 1) return rc9;
+            }
             const int rc = launch_backward_tc(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
             if (rc != 1) return rc;
         }

@@ -39,6 +39,11 @@ size_t backward_v2_workspace_floats(int pcount, int sms);
 int launch_backward_tc(BwdArgs& A, int fused, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
                        cudaStream_t st);
 
+// The same with a dedicated MMA-issue warp and the per-thread state trimmed to 168 registers (sample_backward_tc9.cu;
+// opt-in with LFGC_TC_ISSUER=1 until measured).
+int launch_backward_tc9(BwdArgs& A, int fused, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
+                        cudaStream_t st);
+
 // grad[i] (+)= sum_b partial[b][i] for i < pcount; loss_out[0] = sum_b partial[b][pcount] (fixed order: deterministic)
 void launch_reduce_partials(const float* partial, int nslices, int pstride, int pcount, float* grad, int accumulate,
                             float* loss_out, cudaStream_t st);

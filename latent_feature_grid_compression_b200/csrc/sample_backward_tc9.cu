@@ -1,0 +1,829 @@
+// Fused training kernel, tensor-core variant with a DEDICATED MMA-ISSUE WARP (opt-in, LFGC_TC_ISSUER=1; not yet
+// measured with the register diet below -- see DESIGN.md section 7).
+//
+// Same mathematics, TMEM map and operand layouts as sample_backward_tc.cu (read that header first).  Difference: the
+// tcgen05.mma instructions are issued by a ninth warp that owns no samples, so the compute warps never sit in the
+// issue loop while the shared-memory-bound weight-gradient MMAs drain (9 k of 32.6 k cycles per tile in the 8-warp
+// kernel, profiles/README.md).  Nine warps put three on one scheduler, which caps the kernel at 168 registers per
+// thread; the first attempt spilled and ran at 309 us instead of 248 us (n = 262144).  This version moves the two
+// largest per-thread arrays out of the register file:
+//     S'(z_l), l < L-1   -> shared memory  Gs[l][c][thread] (float4, conflict-free), written in the forward epilogue
+//     Wf-gradient sums   -> shared memory  Aw[c][thread]    (float4), read-modify-written once per tile
+// Handshake: compute threads arrive on an mbarrier (count = 256) when the operands of the next MMA group are in place;
+// the MMA warp waits on it, issues, and commits to the result barriers the compute threads wait on.
+#include "sample_backward.cuh"
+
+#include <stdlib.h>
+
+#ifdef LFGC_PHASE_TIMING
+__device__ unsigned long long g_btc9_cycles[16];
+#define BT_DECL long long _tl = clock64(); unsigned long long _tp[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0};
+#define BT_MARK(i) { long long _n = clock64(); _tp[i] += (unsigned long long)(_n - _tl); _tl = _n; }
+#define BT_FLUSH() { if (threadIdx.x == 0) for (int _i = 0; _i < 16; ++_i) atomicAdd(&g_btc9_cycles[_i], _tp[_i]); }
+#else
+#define BT_DECL
+#define BT_MARK(i)
+#define BT_FLUSH()
+#endif
+
+namespace lfgc {
+namespace btc9 {
+
+constexpr int HP = 32;
+constexpr int TILE = 128;
+constexpr int LMAX = 4;
+constexpr int kPanelW = HP * 16;     // bytes per K chunk of a forward weight operand (32 rows)
+constexpr int kBlkMN = TILE * 128;   // bytes of one MN-major [128 samples][32 columns] block
+constexpr int kOnesRow = 63;         // accumulator row that receives the bias gradient (column 31 of MN group 1)
+
+// TMEM column map
+constexpr int cAcc = 0, cA1 = 32, cDz = 224, cH0 = 288, cW = 352, kTmemCols = 512;
+__host__ __device__ constexpr int colA_hi(int l) { return l == 0 ? cA1 + 64 : cA1 + 64 * (l - 1); }
+__host__ __device__ constexpr int colA_lo(int l) { return l == 0 ? cA1 + 128 : cA1 + 64 * (l - 1) + 32; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE descriptor (cute::UMMA::SmemDescriptor bit layout, version 1)
+__device__ __forceinline__ uint64_t desc_k(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// MN-major, SWIZZLE_128B_BASE32B: LBO = bytes between 32-column groups, SBO = bytes between 4-sample atoms
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((kBlkMN >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((512 >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// kind::tf32, fp32 accumulate, M = 128
+__host__ __device__ constexpr uint32_t idesc(int N, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(id), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);  // round to nearest tf32
+    lo = x - hi;                                                         // exact in fp32
+}
+__device__ __forceinline__ void split4(const float4& a, float4& hi, float4& lo) {
+    split_tf32(a.x, hi.x, lo.x);
+    split_tf32(a.y, hi.y, lo.y);
+    split_tf32(a.z, hi.z, lo.z);
+    split_tf32(a.w, hi.w, lo.w);
+}
+
+// Bounded wait: a lost completion traps (reported as a launch failure) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 2000000000ll) __trap();   // ~1 s
+    }
+}
+
+// ---- TMEM <-> registers (32 lanes x 32 bit, N consecutive columns) ----------------------------------------------------
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_st<4>(uint32_t taddr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st<8>(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st<16>(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::
+            "r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// A operand from TMEM (lane = sample, 8 consecutive 32-bit columns per K = 8 step), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(id), "r"(accumulate)
+        : "memory");
+}
+// One lane of a converged warp (elect.sync).  Issuing tcgen05.mma under `if (threadIdx.x == 0)` makes the compiler wrap
+// every MMA in an ELECT / BRA.U.ANY serialisation loop (~60 cycles per instruction, measured); under a warp-uniform
+// branch + elect.sync it emits the bare UTCMMA sequence.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- shared-memory layout (bytes) ---------------------------------------------------------------------------------------
+struct Layout {
+    int ctrl, bias, wf, yx, Hm, Dm, Wf, Wb, Gs, Aw, total;
+    int Np0;       // rows of the layer-0 backward weight operand (feature columns, multiple of 16)
+    int wb0;       // bytes of the layer-0 backward weight operand (one of hi / lo)
+    int wfBytes, wbBytes;  // bytes of one of hi / lo
+};
+
+__host__ __device__ inline Layout make_layout(const SampleParams& P, int K0p, int tps) {
+    Layout o;
+    o.Np0 = (P.Cp + 15) & ~15;
+    o.wb0 = (HP / 4) * o.Np0 * 16;
+    o.wfBytes = (K0p + (P.L - 1) * HP) / 4 * kPanelW;
+    o.wbBytes = o.wb0 + (P.L - 1) * (HP / 4) * kPanelW;
+    int p = 0;
+    o.ctrl = p; p += 64;                      // mbarriers: [0,8) forward / dh, [8,16) dW, [16,24) operands ready; [24,28) TMEM base
+    o.bias = p; p += LMAX * HP * 4;
+    o.wf = p;   p += (HP + 4) * 4;
+    o.yx = p;   p += tps * TILE * 4;          // partial outputs of the threads sharing a sample
+    p = (p + 1023) & ~1023;
+    o.Hm = p;   p += 4 * kBlkMN;              // MN-major [h hi g0 | h hi g1 (+ones) | h lo g0 | h lo g1]
+    o.Dm = p;   p += 2 * kBlkMN;              // MN-major dz_l (hi | lo); parameter staging at start-up, flush scratch
+    o.Wf = p;   p += 2 * o.wfBytes;
+    o.Wb = p;   p += 2 * o.wbBytes;
+    p = (p + 15) & ~15;
+    o.Gs = p;   p += (LMAX - 1) * (HP / tps / 4) * (TILE * tps) * 16;   // S'(z_l), l < L-1: [l][c][thread] float4
+    o.Aw = p;   p += (HP / tps / 4) * (TILE * tps) * 16;                // Wf-gradient partial sums: [c][thread] float4
+    o.total = p;
+    return o;
+}
+
+// byte offset of column j (0..31) of sample s inside an MN-major block
+__device__ __forceinline__ int mn_off(int s, int j) { return s * 128 + ((((j >> 3) ^ s) & 3) << 5) + ((j & 7) << 2); }
+
+template <int FUSED, int TPS>
+__global__ void __launch_bounds__(TILE * TPS + 32, 1) backward_tc9_kernel(const __grid_constant__ BwdArgs A, const int K0p) {
+    LFGC_PDL_PROLOGUE();
+    constexpr int CW = HP / TPS;   // hidden columns per thread
+    constexpr int NC = TILE * TPS; // compute threads; one more warp only issues the MMAs
+    constexpr int NT = NC + 32;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    BT_DECL
+    const SampleParams& P = A.P;
+    const Layout Lo = make_layout(P, K0p, TPS);
+    float* bias = reinterpret_cast<float*>(smem + Lo.bias);
+    float* wfs = reinterpret_cast<float*>(smem + Lo.wf);
+    float* yx = reinterpret_cast<float*>(smem + Lo.yx);
+    unsigned char* Hm = smem + Lo.Hm;
+    unsigned char* DmHi = smem + Lo.Dm;
+    unsigned char* DmLo = DmHi + kBlkMN;
+    unsigned char* WfHi = smem + Lo.Wf;
+    unsigned char* WfLo = WfHi + Lo.wfBytes;
+    unsigned char* WbHi = smem + Lo.Wb;
+    unsigned char* WbLo = WbHi + Lo.wbBytes;
+    float4* Gs = reinterpret_cast<float4*>(smem + Lo.Gs);
+    float4* Aw = reinterpret_cast<float4*>(smem + Lo.Aw);
+    const uint32_t barA = smem_u32(smem + Lo.ctrl);        // forward layers and dh
+    const uint32_t barB = barA + 8;                        // weight-gradient MMAs
+    const uint32_t barR = barA + 16;                       // operands ready: NC arrivals per phase, waited by the MMA warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Lo.ctrl + 24);
+    const bool is_compute = threadIdx.x < NC;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp >> 2;                  // which share of the columns
+    const int s = ((warp & 3) << 5) | lane;   // sample within the tile = TMEM lane
+    const int col0 = q * CW;                  // first hidden column of this thread
+    const int H = P.H, in0 = P.in0, L = P.L;
+    const int nfix = 3 + 6 * P.F;
+    const int Cp = P.Cp;
+
+    // ---- one-time setup ------------------------------------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barA), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barB), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barR), "r"(NC));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    {
+        // zero what must read as zero / finite: the second column group of the MN-major activation block (only the ones
+        // column and the layer-0 columns >= 32 are ever written there) and the weight panels (pad rows / columns)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = threadIdx.x; e < kBlkMN / 16; e += NT) {
+            reinterpret_cast<float4*>(Hm + kBlkMN)[e] = z4;
+            reinterpret_cast<float4*>(Hm + 3 * kBlkMN)[e] = z4;
+        }
+        for (int e = threadIdx.x; e < (Lo.total - Lo.Wf) / 16; e += NT) reinterpret_cast<float4*>(smem + Lo.Wf)[e] = z4;
+        // the packed parameter block, staged through shared memory with independent loads (one L2 round trip)
+        float* stage = reinterpret_cast<float*>(DmHi);
+        if ((reinterpret_cast<uintptr_t>(A.mlp) & 15) == 0) {
+            const int n4 = A.pcount >> 2;
+            for (int e4 = threadIdx.x; e4 < n4; e4 += NT)
+                reinterpret_cast<float4*>(stage)[e4] = __ldg(reinterpret_cast<const float4*>(A.mlp) + e4);
+            if ((int)threadIdx.x < (A.pcount & 3)) stage[4 * n4 + threadIdx.x] = __ldg(A.mlp + 4 * n4 + threadIdx.x);
+        } else {
+            for (int e = threadIdx.x; e < A.pcount; e += NT) stage[e] = __ldg(A.mlp + e);
+        }
+    }
+    __syncthreads();
+    {
+        const float* stage = reinterpret_cast<const float*>(DmHi);
+        // ones column (column 31 of group 1 of the hi block): bias gradient row of every dW accumulator
+        for (int r = threadIdx.x; r < TILE; r += NT) *reinterpret_cast<float*>(Hm + kBlkMN + mn_off(r, 31)) = 1.0f;
+        for (int l = 0; l < L; ++l) {
+            const int K = l == 0 ? in0 : H;
+            const float* W = stage + mlp_w_off(l, in0, H);
+            const int fbase = (l == 0 ? 0 : (K0p + (l - 1) * HP) / 4) * kPanelW;
+            const int bbase = l == 0 ? 0 : Lo.wb0 + (l - 1) * (HP / 4) * kPanelW;
+            const int brows = l == 0 ? Lo.Np0 : HP;
+            for (int e = threadIdx.x; e < H * K; e += NT) {
+                const int j = e / K, r = e - j * K;
+                int k = r;
+                if (l == 0) k = r < nfix ? Cp + r : r - nfix;  // permuted layer-0 columns
+                float hi, lo;
+                split_tf32(W[e], hi, lo);
+                const int fo = fbase + (k >> 2) * kPanelW + j * 16 + (k & 3) * 4;          // forward: B[n = j][K = k]
+                *reinterpret_cast<float*>(WfHi + fo) = hi;
+                *reinterpret_cast<float*>(WfLo + fo) = lo;
+                if (l > 0 || k < Cp) {                                                     // backward: B[n = k][K = j]
+                    const int bo = bbase + (j >> 2) * brows * 16 + k * 16 + (j & 3) * 4;
+                    *reinterpret_cast<float*>(WbHi + bo) = hi;
+                    *reinterpret_cast<float*>(WbLo + bo) = lo;
+                }
+            }
+            const float* b = stage + mlp_b_off(l, in0, H);
+            for (int j = threadIdx.x; j < HP; j += NT) bias[l * HP + j] = j < H ? b[j] : 0.0f;
+        }
+        const float* wf = stage + mlp_wf_off(L, in0, H);
+        for (int j = threadIdx.x; j < HP; j += NT) wfs[j] = j < H ? wf[j] : 0.0f;
+        if (threadIdx.x == 0) wfs[HP] = wf[H];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's lane quarter
+    const float bf = wfs[HP];
+    const uint32_t aHm = smem_u32(Hm), aDmHi = smem_u32(DmHi), aDmLo = smem_u32(DmLo);
+    const uint32_t aWfHi = smem_u32(WfHi), aWfLo = smem_u32(WfLo), aWbHi = smem_u32(WbHi), aWbLo = smem_u32(WbLo);
+    uint32_t parA = 0, parB = 0;
+    bool pendingB = false;     // weight-gradient MMAs in flight: their operand buffers must not be overwritten yet
+    bool first_tile = true;
+
+    float accbf = 0.0f, loss_part = 0.0f;   // the Wf-gradient sums live in Aw (zeroed with the weight panels above)
+
+    uint64_t sample_base = A.sample_offset;
+    if (FUSED && A.step_dev) sample_base += (uint64_t)(*A.step_dev) * A.step_stride;
+
+    // this thread's 4 columns [j0, j0+4) of an MN-major block pair
+    auto put_mn = [&](unsigned char* hi_base, unsigned char* lo_base, int j0, const float4& hi, const float4& lo) {
+        const int off = mn_off(s, j0);
+        *reinterpret_cast<float4*>(hi_base + off) = hi;
+        *reinterpret_cast<float4*>(lo_base + off) = lo;
+    };
+    BT_MARK(0)  // setup
+
+    const int64_t ntiles = (A.n + TILE - 1) / TILE;
+    if (!is_compute) {
+        // ---- MMA warp: mirrors the control flow of the compute warps, one elected lane issues ------------------------------------
+        uint32_t parR = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int l = 0; l < L; ++l) {
+                mbar_wait(barR, parR);
+                parR ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const int nk = (l == 0 ? K0p : HP) / 8;
+                    const uint32_t boff = (uint32_t)((l == 0 ? 0 : (K0p + (l - 1) * HP) / 4) * kPanelW);
+                    constexpr uint32_t id = idesc(HP, 0, 0);
+                    const uint32_t ah = tmem + colA_hi(l), al = tmem + colA_lo(l);
+                    const uint64_t bh0 = desc_k(aWfHi + boff, kPanelW, 128), bl0 = desc_k(aWfLo + boff, kPanelW, 128);
+                    for (int ks = 0; ks < nk; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * 2 * kPanelW) >> 4);
+                        mma_tf32_ts(tmem + cAcc, ah + 8 * ks, bh0 + adv, id, ks > 0 ? 1u : 0u);
+                        mma_tf32_ts(tmem + cAcc, al + 8 * ks, bh0 + adv, id, 1u);
+                        mma_tf32_ts(tmem + cAcc, ah + 8 * ks, bl0 + adv, id, 1u);
+                    }
+                    mma_commit(barA);
+                }
+                __syncwarp();
+            }
+            for (int l = L - 1; l >= 0; --l) {
+                mbar_wait(barR, parR);
+                parR ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    // dh_l = dz_l W_l  (layer 0: only the feature columns)
+                    {
+                        const uint32_t id = l > 0 ? idesc(HP, 0, 0) : idesc(Lo.Np0, 0, 0);
+                        const uint32_t rows16 = (uint32_t)(l > 0 ? HP : Lo.Np0) * 16;
+                        const uint32_t boff = (uint32_t)(l > 0 ? Lo.wb0 + (l - 1) * (HP / 4) * kPanelW : 0);
+                        const uint64_t bh0 = desc_k(aWbHi + boff, rows16, 128), bl0 = desc_k(aWbLo + boff, rows16, 128);
+                        for (int ks = 0; ks < HP / 8; ++ks) {
+                            const uint64_t adv = (uint64_t)((ks * 2 * rows16) >> 4);
+                            mma_tf32_ts(tmem + cAcc, tmem + cDz + 8 * ks, bh0 + adv, id, ks > 0 ? 1u : 0u);
+                            mma_tf32_ts(tmem + cAcc, tmem + cDz + HP + 8 * ks, bh0 + adv, id, 1u);
+                            mma_tf32_ts(tmem + cAcc, tmem + cDz + 8 * ks, bl0 + adv, id, 1u);
+                        }
+                        mma_commit(barA);
+                    }
+                    // dW_l^T += [h_l | 1]^T dz_l, contraction over the 128 samples (8 per MMA); rows 0..63 of the accumulator
+                    // collect hi * dz, rows 64..127 lo * dz
+                    {
+                        constexpr uint32_t id = idesc(HP, 1, 1);
+                        const uint32_t d = tmem + cW + l * HP;
+                        const uint64_t a0 = desc_mn(aHm), bh0 = desc_mn(aDmHi), bl0 = desc_mn(aDmLo);
+                        for (int ks = 0; ks < TILE / 8; ++ks) {
+                            const uint64_t adv = (uint64_t)((ks * 1024) >> 4);
+                            mma_tf32(d, a0 + adv, bh0 + adv, id, (first_tile && ks == 0) ? 0u : 1u);
+                            mma_tf32(d, a0 + adv, bl0 + adv, id, 1u);
+                        }
+                        mma_commit(barB);
+                    }
+                }
+                __syncwarp();
+            }
+            first_tile = false;
+        }
+    } else
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- input stage: the TPS threads of a sample take the K chunks c = q, q + TPS, ... ----------------------------
+        const int64_t sg = tile * TILE + s;
+        const bool valid = sg < A.n;
+        float cx = 0.f, cy = 0.f, cz = 0.f, aux = 0.f;
+        if (valid) {
+            if (FUSED && !A.coords) {
+                unsigned long long v = A.explicit_idx ? (unsigned long long)A.explicit_idx[sg]
+                                                      : philox_voxel(A.seed, sample_base + (uint64_t)sg, A.n_voxels);
+                const unsigned long long r12 = (unsigned long long)A.R[1] * A.R[2];
+                const int i = (int)(v / r12);
+                const int j = (int)((v / A.R[2]) % A.R[1]);
+                const int k = (int)(v % A.R[2]);
+                cx = normalized_coord((float)i, A.max_idx[0], A.scales[0]);
+                cy = normalized_coord((float)j, A.max_idx[1], A.scales[1]);
+                cz = normalized_coord((float)k, A.max_idx[2], A.scales[2]);
+                aux = __ldg(A.volume + v);
+            } else {  // caller-supplied positions; aux = target value (fused) or d(loss)/d(out)
+                cx = __ldg(A.coords + 3 * sg);
+                cy = __ldg(A.coords + 3 * sg + 1);
+                cz = __ldg(A.coords + 3 * sg + 2);
+                aux = __ldg(A.grad_out + sg);
+            }
+        }
+        Corners Kc;
+        make_corners(P, cx, cy, cz, Kc);
+        // one K chunk (4 columns) of the layer-0 input: tf32 hi / lo operand columns and the fp32 copy
+        auto emit = [&](int c, const float (&v4)[4]) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(v4[i], hi[i], lo[i]);
+            tmem_st<4>(trow + colA_hi(0) + 4 * c, hi);
+            tmem_st<4>(trow + colA_lo(0) + 4 * c, lo);
+            tmem_st<4>(trow + cH0 + 4 * c, v4);
+        };
+        // feature chunks two at a time: 16 independent 128-bit gathers in flight per thread
+        for (int c = q; 4 * c < Cp; c += 2 * TPS) {
+            const int c2 = c + TPS;
+            const bool two = 4 * c2 < Cp;
+            float4 v[8], u[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) v[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c);
+            if (two) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) u[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c2);
+            }
+            float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                a[0] = fmaf(v[cc].x, Kc.w[cc], a[0]);
+                a[1] = fmaf(v[cc].y, Kc.w[cc], a[1]);
+                a[2] = fmaf(v[cc].z, Kc.w[cc], a[2]);
+                a[3] = fmaf(v[cc].w, Kc.w[cc], a[3]);
+            }
+            emit(c, a);
+            if (two) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    b[0] = fmaf(u[cc].x, Kc.w[cc], b[0]);
+                    b[1] = fmaf(u[cc].y, Kc.w[cc], b[1]);
+                    b[2] = fmaf(u[cc].z, Kc.w[cc], b[2]);
+                    b[3] = fmaf(u[cc].w, Kc.w[cc], b[3]);
+                }
+                emit(c2, b);
+            }
+        }
+        for (int c = (Cp >> 2) + q; c < K0p / 4; c += TPS) {
+            float v4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 4 * c + i - Cp;   // 0..2 xyz, then per frequency [sin x y z | cos x y z]
+                float val = 0.0f;
+                if (r < 3) {
+                    val = r == 0 ? cx : (r == 1 ? cy : cz);
+                } else if (r < nfix) {
+                    const int f = (r - 3) / 6, m = (r - 3) - 6 * f;
+                    const int ax = m >= 3 ? m - 3 : m;
+                    const float coord = ax == 0 ? cx : (ax == 1 ? cy : cz);
+                    float sn, cs;
+                    sincos_cw(__fmul_rn(coord, P.omega[f]), sn, cs);  // argument rounded to fp32 first
+                    val = m >= 3 ? cs : sn;
+                }
+                v4[i] = val;
+            }
+            emit(c, v4);
+        }
+        tmem_st_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(barR);
+        BT_MARK(1)  // input stage
+
+        // ---- forward ------------------------------------------------------------------------------------------------------------
+        float hs[CW], glast[CW];   // S'(z_l): l < L-1 goes to Gs (shared memory), the last layer's stays here briefly
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) {
+            if (l < L) {
+                BT_MARK(3)  // MMA issue
+                mbar_wait(barA, parA);
+                parA ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                BT_MARK(4)  // MMA wait
+
+                float z[CW];
+                tmem_ld<CW>(trow + cAcc + col0, z);
+                const float* bl_ = bias + l * HP + col0;
+#pragma unroll
+                for (int i = 0; i < CW; ++i) snake_and_grad_precise(z[i] + bl_[i], hs[i], glast[i]);
+                if (l + 1 < L && l < LMAX - 1) {
+#pragma unroll
+                    for (int c = 0; c < CW / 4; ++c)
+                        Gs[(l * (CW / 4) + c) * NC + threadIdx.x] =
+                            make_float4(glast[4 * c], glast[4 * c + 1], glast[4 * c + 2], glast[4 * c + 3]);
+                }
+                if (l + 1 < L) {
+                    float hi[CW], lo[CW];
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) split_tf32(hs[i], hi[i], lo[i]);
+                    tmem_st<CW>(trow + colA_hi(l + 1) + col0, hi);
+                    tmem_st<CW>(trow + colA_lo(l + 1) + col0, lo);
+                    tmem_st_wait();
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(barR);
+                    BT_MARK(5)  // forward epilogue
+                }
+            }
+        }
+
+        // ---- output, loss, dz_{L-1} --------------------------------------------------------------------------------------------
+        {
+            float yp = 0.0f;
+#pragma unroll
+            for (int i = 0; i < CW; ++i) yp = fmaf(hs[i], wfs[col0 + i], yp);
+            yx[q * TILE + s] = yp;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");   // compute threads only (the MMA warp is elsewhere)
+        float dy;
+        {
+            float y = bf;
+#pragma unroll
+            for (int t = 0; t < TPS; ++t) y += yx[t * TILE + s];
+            if (FUSED) {
+                const float e = y - aux;
+                dy = valid ? A.loss_scale2 * e : 0.0f;
+                if (q == 0 && valid) loss_part = fmaf(e, e, loss_part);
+            } else {
+                dy = valid ? aux : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CW / 4; ++c) {
+            float4 a = Aw[c * NC + threadIdx.x];
+            a.x = fmaf(dy, hs[4 * c], a.x);
+            a.y = fmaf(dy, hs[4 * c + 1], a.y);
+            a.z = fmaf(dy, hs[4 * c + 2], a.z);
+            a.w = fmaf(dy, hs[4 * c + 3], a.w);
+            Aw[c * NC + threadIdx.x] = a;
+        }
+        if (q == 0) accbf += dy;
+        float dz[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i) dz[i] = dy * wfs[col0 + i] * glast[i];
+        BT_MARK(6)  // output + loss
+
+        // ---- backward ----------------------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int l = LMAX - 1; l >= 0; --l) {
+            if (l < L) {
+                if (pendingB) {   // the previous weight-gradient MMAs still read the operand buffers written below
+                    mbar_wait(barB, parB);
+                    parB ^= 1u;
+                    pendingB = false;
+                }
+                BT_MARK(11)  // dW wait
+                // dz_l: TMEM operand of dh_l (hi | lo) and MN-major operand of dW_l
+                {
+                    float hi[CW], lo[CW];
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) split_tf32(dz[i], hi[i], lo[i]);
+                    tmem_st<CW>(trow + cDz + col0, hi);
+                    tmem_st<CW>(trow + cDz + HP + col0, lo);
+#pragma unroll
+                    for (int c = 0; c < CW / 4; ++c)
+                        put_mn(DmHi, DmLo, col0 + 4 * c, make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]),
+                               make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]));
+                }
+                // h_l -> MN-major operand (group 0; the layer-0 input also fills its columns >= 32 of group 1)
+                if (l > 0) {
+                    float hi[CW], lo[CW];
+                    tmem_ld<CW>(trow + colA_hi(l) + col0, hi);
+                    tmem_ld<CW>(trow + colA_lo(l) + col0, lo);
+#pragma unroll
+                    for (int c = 0; c < CW / 4; ++c)
+                        put_mn(Hm, Hm + 2 * kBlkMN, col0 + 4 * c, make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]),
+                               make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]));
+                } else {
+                    for (int c = q; c < K0p / 4; c += TPS) {
+                        float hv[4], hi[4], lo[4];
+                        tmem_ld<4>(trow + cH0 + 4 * c, hv);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_tf32(hv[i], hi[i], lo[i]);
+                        const int g = (4 * c) >> 5;   // 32-column group
+                        put_mn(Hm + g * kBlkMN, Hm + (2 + g) * kBlkMN, (4 * c) & 31, make_float4(hi[0], hi[1], hi[2], hi[3]),
+                               make_float4(lo[0], lo[1], lo[2], lo[3]));
+                    }
+                }
+                tmem_st_wait();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(barR);
+                BT_MARK(7)  // backward operand staging
+                pendingB = true;
+                BT_MARK(3)
+                mbar_wait(barA, parA);
+                parA ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                BT_MARK(4)
+                if (l > 0) {
+                    float dh[CW];
+                    tmem_ld<CW>(trow + cAcc + col0, dh);
+#pragma unroll
+                    for (int c = 0; c < CW / 4; ++c) {
+                        const float4 g4 = Gs[(((l > 0 ? l - 1 : 0)) * (CW / 4) + c) * NC + threadIdx.x];
+                        dz[4 * c] = dh[4 * c] * g4.x;
+                        dz[4 * c + 1] = dh[4 * c + 1] * g4.y;
+                        dz[4 * c + 2] = dh[4 * c + 2] * g4.z;
+                        dz[4 * c + 3] = dh[4 * c + 3] * g4.w;
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    BT_MARK(8)  // dz
+                } else {
+                    // scatter d(features) into the grid gradient
+                    for (int c = q; 4 * c < Cp; c += TPS) {
+                        float d[4];
+                        tmem_ld<4>(trow + cAcc + 4 * c, d);   // warp-collective: outside the per-sample predicate
+                        if (valid) {
+#pragma unroll
+                            for (int cc = 0; cc < 8; ++cc) {
+                                const float w = Kc.w[cc];
+                                if (w != 0.0f)
+                                    red_add_v4(A.grad_grid + Kc.off[cc] + 4 * c, make_float4(d[0] * w, d[1] * w, d[2] * w, d[3] * w));
+                            }
+                        }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    BT_MARK(9)  // scatter
+                }
+            }
+        }
+        first_tile = false;
+    }
+
+    // ---- flush: weight-gradient accumulators, final-layer gradient, loss ------------------------------------------------------
+    if (pendingB) {
+        mbar_wait(barB, parB);
+        parB ^= 1u;
+        pendingB = false;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* dst = A.partial + (size_t)blockIdx.x * A.pstride;
+    float* xch = reinterpret_cast<float*>(DmHi);   // [layer][row 0..63][32]: the lo * dz halves (accumulator rows 64..127)
+    if (is_compute && (warp & 3) >= 2) {
+        const int row = (((warp & 3) - 2) << 5) | lane;
+        for (int l = q; l < L; l += TPS) {
+            float r[32];
+            tmem_ld<32>(trow + cW + l * HP, r);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(xch + (l * 64 + row) * 32 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+    }
+    __syncthreads();
+    if (is_compute && (warp & 3) < 2) {   // accumulator rows 0..63 live in lane quarters 0 and 1
+        const int row = ((warp & 3) << 5) | lane;
+        for (int l = q; l < L; l += TPS) {
+            float r[32];
+            tmem_ld<32>(trow + cW + l * HP, r);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(xch + (l * 64 + row) * 32 + j);
+                r[j] += o.x; r[j + 1] += o.y; r[j + 2] += o.z; r[j + 3] += o.w;
+            }
+            const int Kin = l == 0 ? in0 : H;
+            const int woff = mlp_w_off(l, in0, H);
+            int orig = -1;   // column of W_l this accumulator row belongs to
+            if (l > 0) {
+                if (row < H) orig = row;
+            } else if (row < Cp) {
+                if (row < P.C) orig = nfix + row;
+            } else if (row < Cp + nfix) {
+                orig = row - Cp;
+            }
+            if (orig >= 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < H) dst[woff + j * Kin + orig] = r[j];
+            }
+            if (row == kOnesRow) {
+                const int boff = mlp_b_off(l, in0, H);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < H) dst[boff + j] = r[j];
+            }
+        }
+    }
+    {
+        float* red = reinterpret_cast<float*>(Hm);   // [128][36]: 32 Wf partials | bf | loss
+        if (is_compute) {
+#pragma unroll
+            for (int c = 0; c < CW / 4; ++c) {
+                const float4 a = Aw[c * NC + threadIdx.x];
+                red[s * 36 + col0 + 4 * c] = a.x;
+                red[s * 36 + col0 + 4 * c + 1] = a.y;
+                red[s * 36 + col0 + 4 * c + 2] = a.z;
+                red[s * 36 + col0 + 4 * c + 3] = a.w;
+            }
+        }
+        if (q == 0) {
+            red[s * 36 + 32] = accbf;
+            red[s * 36 + 33] = FUSED ? loss_part : 0.0f;
+        }
+        __syncthreads();
+        // column sums over the 128 samples: 7 row groups x 36 columns in parallel, then 7 partials per column
+        float* red2 = red + TILE * 36;
+        {
+            const int col = threadIdx.x % 36, rg = threadIdx.x / 36;
+            if (rg < 7 && col < 34) {
+                float t = 0.0f;
+                for (int r = rg; r < TILE; r += 7) t += red[r * 36 + col];
+                red2[rg * 36 + col] = t;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 34) {
+            float t = 0.0f;
+#pragma unroll
+            for (int g = 0; g < 7; ++g) t += red2[g * 36 + threadIdx.x];
+            const int wfo = mlp_wf_off(L, in0, H);
+            if (threadIdx.x < 32) {
+                if ((int)threadIdx.x < H) dst[wfo + threadIdx.x] = t;
+            } else if (threadIdx.x == 32) {
+                dst[wfo + H] = t;
+            } else {
+                dst[A.pcount] = t;
+            }
+        }
+    }
+    BT_MARK(10)  // flush
+    BT_FLUSH()
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
+}
+
+template <int FUSED, int TPS>
+static int launch_tps(BwdArgs& A, int K0p, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
+                      cudaStream_t st) {
+    const Layout Lo = make_layout(A.P, K0p, TPS);
+    if (Lo.total > max_smem_optin()) return 1;
+    if ((size_t)A.pcount * sizeof(float) > (size_t)2 * kBlkMN) return 1;   // parameter staging buffer
+    auto kern = backward_tc9_kernel<FUSED, TPS>;
+    LFGC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lo.total));
+    const int64_t ntiles = (A.n + TILE - 1) / TILE;
+    int64_t grid = sm_count();   // the kernel owns the SM's TMEM: one CTA per SM
+    if (grid > ntiles) grid = ntiles;
+    const size_t need = (size_t)grid * A.pstride * sizeof(float);
+    if (workspace_bytes < need) return fail(LFGC_E_WORKSPACE, "backward workspace too small: %zu < %zu", workspace_bytes, need);
+    A.partial = reinterpret_cast<float*>(workspace);
+    (void)launch_pdl(kern, dim3((unsigned)grid), dim3(TILE * TPS + 32), (size_t)(Lo.total), st, A, K0p);
+    LFGC_LAUNCH_OK();
+    launch_reduce_partials(A.partial, (int)grid, A.pstride, A.pcount, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
+
+}  // namespace btc9
+
+// Returns LFGC_OK after launching, 1 when the shape is not covered by the tensor-core kernel, or an error code.
+int launch_backward_tc9(BwdArgs& A, int fused, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
+                        cudaStream_t st) {
+    const SampleParams& P = A.P;
+    if (P.H > btc9::HP || P.L < 1 || P.L > btc9::LMAX) return 1;
+    const int K0 = P.Cp + 3 + 6 * P.F;
+    const int K0p = (K0 + 7) & ~7;
+    if (K0p > 56) return 1;   // two 32-column MN groups, the last column of the second one is the ones column
+    return fused ? btc9::launch_tps<1, 2>(A, K0p, grad_mlp, accumulate, workspace, workspace_bytes, st)
+                 : btc9::launch_tps<0, 2>(A, K0p, grad_mlp, accumulate, workspace, workspace_bytes, st);
+}
+
+}  // namespace lfgc

@@ -17,3 +17,8 @@ for tag in ('base', 'glue'):
     except Exception as e:
         print(tag, 'no result:', e)
 PY
+echo "== tcgen05 kernel with dedicated MMA warp (LFGC_TC_ISSUER=1): parity + time against the default"
+LFGC_TC_ISSUER=1 timeout 200 python profiles/tc_train_check.py 2>&1 | grep "TC=\|fused\|backward-only" | head -16
+LFGC_TC_ISSUER=1 timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_properties.py -q 2>&1 | tail -3
+LFGC_TC_ISSUER=1 timeout 240 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2> /dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('issuer-warp: us/step %.2f kernel_us %.2f' % (d['extra']['us_per_optimiser_step'], d['roofline']['kernel_us']))"
