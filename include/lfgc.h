@@ -55,8 +55,7 @@ enum {
 
 /* flags for lfgc_forward / lfgc_reconstruct / lfgc_train_step */
 enum {
-    LFGC_F_CLAMP = 1,        /* clamp output to [-1, 1] (eval mode, Feature_Grid_Model.py:78) */
-    LFGC_F_FAST_SIN = 2      /* range-reduced MUFU sin/cos instead of the precise path (not used for fp32 parity) */
+    LFGC_F_CLAMP = 1         /* clamp output to [-1, 1] (eval mode, Feature_Grid_Model.py:78) */
 };
 
 /* Static shape of one model instance: what model_utils.setup_model fixes (model/model_utils.py:23-59). */
