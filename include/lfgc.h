@@ -246,8 +246,9 @@ int lfgc_deviation_stats(const float* pred, const float* gt, int64_t n, double* 
  * [0] = number of steps taken so far (incremented by the kernel, so the call is graph-replayable; this is the
  * counter lfgc_train_step reads), [1] = scratch ticket counter that must be zero-initialised;
  * lr is a DEVICE float (the host decay strategies write it).  grad_scale multiplies the gradient first
- * (1/world for data parallel means).  l2[n] (nullable) adds 2*l2_weight*p (the Sum coeff^2 regulariser of
- * SmallifyLoss / VariationalDropoutLoss) and l1 similarly adds l1_weight*sign(p) where the flags say so. */
+ * (1/world for data parallel means).  The bias corrections 1 - beta^step are evaluated in fp32 as
+ * -expm1(step * log(beta)).  The sample-independent regulariser gradients are separate calls (lfgc_add_l1_grad,
+ * lfgc_add_l2_grad, lfgc_variational_dkl_grad) issued before this one. */
 int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
               float beta1, float beta2, float eps, float grad_scale, void* stream);
 
