@@ -99,6 +99,20 @@ class FastTrainer:
                     self._slices.append((off, n))
                     off += n
         self.flat_g = torch.zeros_like(self.flat_p)
+        self._symm = None
+        import os
+        if self.world > 1 and os.environ.get('LFGC_ALLREDUCE', 'nccl') == 'symm':
+            # opt-in: one-shot all-reduce over NVLink peer memory (torch symmetric memory: every rank reads the peers'
+            # gradient buffers directly, barrier before and after inside the op) instead of the NCCL ring / tree, whose
+            # latency dominates this 0.5 MB message.  The gradient buffer must then live in symmetric memory.
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self.group if self.group is not None else dist.group.WORLD
+            g = symm_mem.empty(total, dtype=torch.float32, device=self.device)
+            g.zero_()
+            symm_mem.rendezvous(g, grp)
+            self.flat_g = g
+            self._symm = dict(name=grp.group_name, out=torch.zeros_like(self.flat_p))
         self.flat_m = torch.zeros_like(self.flat_p)
         self.flat_v = torch.zeros_like(self.flat_p)
         # keep the model's own MLP pack coherent with the shared buffer
@@ -168,6 +182,14 @@ class FastTrainer:
     def grad_of(self, p):
         return self._grad_view[id(p)]
 
+    def _allreduce_grads(self):
+        """Sum the flat gradient over the ranks; returns the tensor that holds the result."""
+        if self._symm is None:
+            torch.distributed.all_reduce(self.flat_g, group=self.group)
+            return self.flat_g
+        torch.ops.symm_mem.one_shot_all_reduce_out(self.flat_g, 'sum', self._symm['name'], self._symm['out'])
+        return self._symm['out']
+
     def _step_body(self, host_fed=False):
         model, geom = self.model, self.geom
         in_coords, in_targets = self._in_coords, self._in_targets
@@ -217,8 +239,7 @@ class FastTrainer:
             self.grad_of(spec.grad_params[0]).copy_(g0)
             if len(spec.grad_params) == 2:
                 self.grad_of(spec.grad_params[1]).copy_(g1)
-        if self.world > 1:
-            torch.distributed.all_reduce(self.flat_g, group=self.group)
+        g_red = self._allreduce_grads() if self.world > 1 else self.flat_g
         if self.var_cfg is not None:
             # sample-independent terms of VariationalDropoutLoss, added once after the reduction: KL of the live masks
             # (weight ramped on the device) and weight_weights * sum coeff^2, both times batch_scale
@@ -226,19 +247,19 @@ class FastTrainer:
             if self._var_sizes:
                 a = self.mask_off
                 b = a + 2 * sum(self._var_sizes)
-                ops.variational_dkl_grad(self.flat_p[a:b], self.flat_g[a:b], self._var_sizes, self.w_dkl, self.step_dev,
+                ops.variational_dkl_grad(self.flat_p[a:b], g_red[a:b], self._var_sizes, self.w_dkl, self.step_dev,
                                          1.0 + float(cfg['weight_dkl_multiplier']), float(cfg.get('weight_dkl_max', 30.0)),
                                          self.var_scale)
             ww = float(cfg['weight_weights']) * self.var_scale
             if ww > 0.0 and self.n_coeff_elems:
-                ops.add_l2_grad(self.flat_g[:self.n_coeff_elems], self.flat_p[:self.n_coeff_elems], ww)
+                ops.add_l2_grad(g_red[:self.n_coeff_elems], self.flat_p[:self.n_coeff_elems], ww)
         # sample-independent regularisers (SmallifyLoss): added once, after the reduction
         if self.weight_l2 > 0.0 and self.n_coeff_elems:
-            ops.add_l2_grad(self.flat_g[:self.n_coeff_elems], self.flat_p[:self.n_coeff_elems], self.weight_l2)
+            ops.add_l2_grad(g_red[:self.n_coeff_elems], self.flat_p[:self.n_coeff_elems], self.weight_l2)
         if self.weight_l1 > 0.0 and self.n_mask_elems:
             a, b = self.mask_off, self.mask_off + self.n_mask_elems
-            ops.add_l1_grad(self.flat_g[a:b], self.flat_p[a:b], self.weight_l1)
-        ops.adam(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_dev, self.step_dev, self.betas[0],
+            ops.add_l1_grad(g_red[a:b], self.flat_p[a:b], self.weight_l1)
+        ops.adam(self.flat_p, g_red, self.flat_m, self.flat_v, self.lr_dev, self.step_dev, self.betas[0],
                  self.betas[1], self.eps)
 
     def _prime_glue(self):
@@ -261,14 +282,13 @@ class FastTrainer:
         coeffs = [p.data for p in self.coeff_params]
         gcoeffs = [self.grad_of(p) for p in self.coeff_params]
 
-        def glue(phases):
+        def glue(phases, g=None):
             ops.step_glue(geom, coeffs, gcoeffs, self.scratch, self.grad_grid, self.grid_cl, self.grad_grid, self.flat_p,
-                          self.flat_g, self.flat_m, self.flat_v, self.lr_dev, self.step_dev, self.betas[0],
-                          self.betas[1], self.eps, phases=phases)
+                          self.flat_g if g is None else g, self.flat_m, self.flat_v, self.lr_dev, self.step_dev,
+                          self.betas[0], self.betas[1], self.eps, phases=phases)
         if self.world > 1:
             glue(1)
-            torch.distributed.all_reduce(self.flat_g, group=self.group)
-            glue(6)
+            glue(6, self._allreduce_grads())
         else:
             glue(7)
 
