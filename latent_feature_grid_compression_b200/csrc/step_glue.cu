@@ -17,6 +17,7 @@
 #include "lfgc_common.cuh"
 
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -231,7 +232,9 @@ static int launch(const Args& A, cudaStream_t st) {
     int occ = 0;
     LFGC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     if (occ < 1) return fail(LFGC_E_UNSUPPORTED, "step_glue: kernel does not fit on an SM");
-    if (occ > 4) occ = 4;
+    int cap = 2;   // CTAs per SM: more CTAs shorten the phases, fewer shorten the grid barriers (tuning: LFGC_GLUE_OCC)
+    if (const char* e = getenv("LFGC_GLUE_OCC")) { const int v = atoi(e); if (v >= 1 && v <= 8) cap = v; }
+    if (occ > cap) occ = cap;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(sm_count() * occ));
     cfg.blockDim = dim3(256);
