@@ -47,7 +47,7 @@ struct Args {
 
 // one output element of synthesis level l (wavelet.cu idwt_level_kernel<NT>, no multipliers)
 template <int NT>
-__device__ __forceinline__ void synth_elem(const Args& A, int l, long long idx) {
+__host__ __device__ __forceinline__ void synth_elem(const Args& A, int l, long long idx) {
     constexpr int NP = NT / 2;
     const bool last = l == A.n_coeff - 1;
     const int Cs = last ? A.Cp : A.C;
@@ -111,7 +111,7 @@ __device__ __forceinline__ void synth_elem(const Args& A, int l, long long idx) 
 // one (sub-band, position, channel) element of the adjoint of level l (wavelet.cu idwt_level_bwd_kernel<NT>, no
 // multipliers, overwrite semantics)
 template <int NT>
-__device__ __forceinline__ void adjoint_elem(const Args& A, int l, long long idx) {
+__host__ __device__ __forceinline__ void adjoint_elem(const Args& A, int l, long long idx) {
     const int* t = A.t[l];
     const int* d = A.d[l];
     const long long dvol = (long long)d[0] * d[1] * d[2];
@@ -160,6 +160,18 @@ __device__ __forceinline__ void adjoint_elem(const Args& A, int l, long long idx
     }
 }
 
+// torch.optim.Adam for one element (optim.cu adam_kernel); step_size = lr / (1 - b1^step), bc2_sqrt = sqrt(1 - b2^step)
+__host__ __device__ __forceinline__ void adam_elem(const Args& A, long long i, float step_size, float bc2_sqrt) {
+    const float gi = A.g[i] * A.gscale;
+    float mi = A.m[i], vi = A.v[i];
+    mi = mi + (gi - mi) * (1.0f - A.b1);
+    vi = vi * A.b2 + (1.0f - A.b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + A.eps;
+    A.p[i] = A.p[i] - step_size * (mi / denom);
+    A.m[i] = mi;
+    A.v[i] = vi;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(256) step_glue_kernel(const __grid_constant__ Args A) {
     cg::grid_group grid = cg::this_grid();
@@ -192,16 +204,7 @@ __global__ void __launch_bounds__(256) step_glue_kernel(const __grid_constant__ 
         const float bc2 = -expm1f((float)step * logf(A.b2));
         const float step_size = *A.lr / bc1;
         const float bc2_sqrt = sqrtf(bc2);
-        for (long long i = gtid; i < A.n; i += gsize) {
-            const float gi = A.g[i] * A.gscale;
-            float mi = A.m[i], vi = A.v[i];
-            mi = mi + (gi - mi) * (1.0f - A.b1);
-            vi = vi * A.b2 + (1.0f - A.b2) * gi * gi;
-            const float denom = sqrtf(vi) / bc2_sqrt + A.eps;
-            A.p[i] = A.p[i] - step_size * (mi / denom);
-            A.m[i] = mi;
-            A.v[i] = vi;
-        }
+        for (long long i = gtid; i < A.n; i += gsize) adam_elem(A, i, step_size, bc2_sqrt);
         grid.sync();
         if (gtid == 0) *A.step = step;
     }
@@ -255,20 +258,19 @@ static int launch(const Args& A, cudaStream_t st) {
 
 using namespace lfgc;
 
-extern "C" int lfgc_step_glue(const lfgc_wavelet_desc* w, int Cp, float* const* coeff, float* const* grad_coeff,
-                              float* scratch, const float* grad_grid_cl, float* grid_cl, float* also_zero, float* p,
-                              const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
-                              float beta1, float beta2, float eps, float grad_scale, int phases, void* stream) {
+static int glue_fill_args(glue::Args& A, const lfgc_wavelet_desc* w, int Cp, float* const* coeff, float* const* grad_coeff,
+                          float* scratch, const float* grad_grid_cl, float* grid_cl, float* also_zero, float* p,
+                          const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+                          float beta1, float beta2, float eps, float grad_scale, int phases) {
+
     if (!w || !coeff || !grad_coeff) return fail(LFGC_E_INVALID, "step_glue: null descriptor / pointer table");
     if (w->n_coeff < 1 || w->n_coeff > LFGC_MAX_LEVELS || w->C < 1) return fail(LFGC_E_INVALID, "step_glue: bad descriptor");
     if (w->n_coeff > 1 && w->n_taps != 2 && w->n_taps != 4)
         return fail(LFGC_E_UNSUPPORTED, "step_glue: filter length %d (the fused step covers 2 and 4 taps)", w->n_taps);
     if (Cp < w->C || (Cp & 3)) return fail(LFGC_E_INVALID, "Cp=%d must be a multiple of 4 and >= C=%d", Cp, w->C);
-    if ((phases & 7) == 0) return LFGC_OK;
     if ((phases & 1) && !grad_grid_cl) return fail(LFGC_E_INVALID, "step_glue: grad_grid_cl is null");
     if ((phases & 2) && (!p || !g || !m || !v || !lr || !step_count || n < 0)) return fail(LFGC_E_INVALID, "step_glue: bad Adam arguments");
     if ((phases & 4) && !grid_cl) return fail(LFGC_E_INVALID, "step_glue: grid_cl is null");
-    glue::Args A;
     A.n_coeff = w->n_coeff;
     A.C = w->C;
     A.Cp = Cp;
@@ -311,6 +313,78 @@ extern "C" int lfgc_step_glue(const lfgc_wavelet_desc* w, int Cp, float* const* 
     A.eps = eps;
     A.gscale = grad_scale;
     A.phases = phases & 7;
-    cudaStream_t st = (cudaStream_t)stream;
-    return w->n_taps == 2 ? glue::launch<2>(A, st) : glue::launch<4>(A, st);
+    return LFGC_OK;
 }
+
+extern "C" int lfgc_step_glue(const lfgc_wavelet_desc* w, int Cp, float* const* coeff, float* const* grad_coeff,
+                              float* scratch, const float* grad_grid_cl, float* grid_cl, float* also_zero, float* p,
+                              const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+                              float beta1, float beta2, float eps, float grad_scale, int phases, void* stream) {
+    if ((phases & 7) == 0) return LFGC_OK;
+    glue::Args A;
+    const int rc = glue_fill_args(A, w, Cp, coeff, grad_coeff, scratch, grad_grid_cl, grid_cl, also_zero, p, g, m, v, n, lr,
+                                  step_count, beta1, beta2, eps, grad_scale, phases);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return w->n_taps == 2 || w->n_coeff == 1 ? glue::launch<2>(A, st) : glue::launch<4>(A, st);
+}
+
+#ifdef LFGC_GLUE_HOST_TEST
+// Test hook (only in builds made by tests/test_glue_host.py, never in liblfgc.so): the SAME per-element functions and the
+// same phase order run sequentially on HOST memory, so the index arithmetic of the glue kernel can be checked against
+// the numpy oracle without a GPU.  All pointers are host pointers here.
+template <int NT>
+static void glue_run_host(const glue::Args& A) {
+    using namespace glue;
+    if (A.phases & 1) {
+        if (A.n_coeff == 1) {
+            const long long nvox = (long long)A.d[0][0] * A.d[0][1] * A.d[0][2];
+            for (long long i = 0; i < nvox * A.C; ++i) A.gcoeff[0][(i % A.C) * nvox + i / A.C] = A.grad_grid[(i / A.C) * A.Cp + i % A.C];
+        } else {
+            for (int l = A.n_coeff - 1; l >= 1; --l) {
+                const long long total = 8ll * A.d[l][0] * A.d[l][1] * A.d[l][2] * A.C;
+                for (long long i = 0; i < total; ++i) adjoint_elem<NT>(A, l, i);
+            }
+        }
+    }
+    if (A.phases & 2) {
+        const int step = *A.step + 1;
+        const float bc1 = -expm1f((float)step * logf(A.b1));
+        const float bc2 = -expm1f((float)step * logf(A.b2));
+        const float step_size = *A.lr / bc1;
+        const float bc2_sqrt = sqrtf(bc2);
+        for (long long i = 0; i < A.n; ++i) adam_elem(A, i, step_size, bc2_sqrt);
+        *A.step = step;
+    }
+    if (A.phases & 4) {
+        if (A.n_coeff == 1) {
+            const long long nvox = (long long)A.d[0][0] * A.d[0][1] * A.d[0][2];
+            for (long long i = 0; i < nvox * A.Cp; ++i) {
+                const int c = (int)(i % A.Cp);
+                if (A.also_zero) A.also_zero[i] = 0.0f;
+                A.grid_cl[i] = c < A.C ? A.coeff[0][(long long)c * nvox + i / A.Cp] : 0.0f;
+            }
+        } else {
+            for (int l = 1; l < A.n_coeff; ++l) {
+                const bool last = l == A.n_coeff - 1;
+                const long long total = (long long)A.t[l][0] * A.t[l][1] * A.t[l][2] * (last ? A.Cp : A.C);
+                for (long long i = 0; i < total; ++i) synth_elem<NT>(A, l, i);
+            }
+        }
+    }
+}
+
+extern "C" int lfgc_step_glue_host(const lfgc_wavelet_desc* w, int Cp, float* const* coeff, float* const* grad_coeff,
+                                   float* scratch, const float* grad_grid_cl, float* grid_cl, float* also_zero, float* p,
+                                   const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+                                   float beta1, float beta2, float eps, float grad_scale, int phases) {
+    if ((phases & 7) == 0) return LFGC_OK;
+    glue::Args A;
+    const int rc = glue_fill_args(A, w, Cp, coeff, grad_coeff, scratch, grad_grid_cl, grid_cl, also_zero, p, g, m, v, n, lr,
+                                  step_count, beta1, beta2, eps, grad_scale, phases);
+    if (rc) return rc;
+    if (w->n_taps == 2 || w->n_coeff == 1) glue_run_host<2>(A);
+    else glue_run_host<4>(A);
+    return LFGC_OK;
+}
+#endif
