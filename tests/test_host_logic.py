@@ -151,3 +151,53 @@ def test_dropin_aliases_expose_the_reference_module_names():
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, 'dropin') + os.pathsep + ROOT)
     out = subprocess.run([sys.executable, '-c', code], cwd='/tmp', env=env, capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == 'ok', out.stderr
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/lfgc.h against the ctypes signature the package binds it with: same arity, and the
+    same class (pointer / 32-bit int / 64-bit int / size_t / float / double) for every argument and the result.  A
+    float-vs-double or int-vs-int64 slip would otherwise only show up as garbage on the GPU."""
+    import ctypes as C
+    import re
+    from latent_feature_grid_compression_b200 import _lib
+    text = open(os.path.join(ROOT, 'include', 'lfgc.h')).read()
+    text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
+    protos = re.findall(r'\n\s*((?:const\s+)?[A-Za-z_][\w\s\*]*?)\b(lfgc_\w+)\s*\(([^;{]*?)\)\s*;', text)
+    assert len(protos) >= 30
+
+    def c_class(decl):
+        decl = decl.strip()
+        if decl == 'void':
+            return None
+        if '*' in decl or '[' in decl:
+            return 'ptr'
+        base = re.sub(r'\b(const|unsigned)\b', '', decl).split()
+        t = base[0] if base else ''
+        return {'int': 'i32', 'int32_t': 'i32', 'int64_t': 'i64', 'uint64_t': 'i64', 'long': 'i64', 'size_t': 'size',
+                'float': 'f32', 'double': 'f64'}.get(t, 'other:' + t)
+
+    def ct_class(t):
+        if t is None:
+            return None
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, 'contents') or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return 'ptr'
+        return {C.c_int: 'i32', C.c_int32: 'i32', C.c_uint32: 'i32', C.c_int64: 'i64', C.c_uint64: 'i64',
+                C.c_longlong: 'i64', C.c_size_t: 'size', C.c_float: 'f32', C.c_double: 'f64'}.get(t, 'other:%r' % t)
+
+    seen = set()
+    for ret, name, args in protos:
+        assert name in _lib._SIGNATURES, name + ' is declared in lfgc.h but not bound'
+        res, argtypes = _lib._SIGNATURES[name]
+        seen.add(name)
+        ret = ret.strip()
+        want_ret = 'ptr' if '*' in ret else c_class('long' if ret.startswith('long long') else ret)
+        # size_t and 64-bit ints are the same register class on LP64; keep them distinct for arguments only
+        got_ret = ct_class(res)
+        assert (want_ret, got_ret) in ((want_ret, want_ret), ('size', 'i64'), ('i64', 'size')), (name, ret, res)
+        decls = [a for a in (s.strip() for s in args.split(',')) if a]
+        want = [c_class(a) for a in decls if c_class(a) is not None]
+        got = [ct_class(t) for t in argtypes]
+        assert len(want) == len(got), (name, len(want), len(got))
+        for i, (w, g) in enumerate(zip(want, got)):
+            assert w == g or {w, g} == {'size', 'i64'}, '%s: argument %d is %s in the header, %s in ctypes' % (name, i, w, g)
+    assert seen == set(_lib._SIGNATURES), set(_lib._SIGNATURES) - seen
