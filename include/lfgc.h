@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LFGC_ABI_VERSION 1
+#define LFGC_ABI_VERSION 2 /* 2: lfgc_adam / lfgc_step_glue take their hyper-parameters as doubles */
 #define LFGC_MAX_LEVELS 12 /* coefficient tensors per model (1 low-pass + up to 11 detail levels) */
 #define LFGC_MAX_TAPS 16   /* longest supported 1-D reconstruction filter */
 #define LFGC_MAX_LAYERS 8  /* hidden layers of the decoder MLP */
@@ -246,11 +246,12 @@ int lfgc_deviation_stats(const float* pred, const float* gt, int64_t n, double* 
  * [0] = number of steps taken so far (incremented by the kernel, so the call is graph-replayable; this is the
  * counter lfgc_train_step reads), [1] = scratch ticket counter that must be zero-initialised;
  * lr is a DEVICE float (the host decay strategies write it).  grad_scale multiplies the gradient first
- * (1/world for data parallel means).  The bias corrections 1 - beta^step are evaluated in fp32 as
- * -expm1(step * log(beta)).  The sample-independent regulariser gradients are separate calls (lfgc_add_l1_grad,
+ * (1/world for data parallel means).  The hyper-parameters are doubles, as in torch: 1 - beta and log(beta) are formed
+ * in fp64 on the host and then rounded (1 - fl32(0.999) would be 4.7e-5 off); the bias corrections 1 - beta^step are
+ * evaluated on the device in fp32 as -expm1(step * fl32(log(beta))).  The sample-independent regulariser gradients are separate calls (lfgc_add_l1_grad,
  * lfgc_add_l2_grad, lfgc_variational_dkl_grad) issued before this one. */
 int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
-              float beta1, float beta2, float eps, float grad_scale, void* stream);
+              double beta1, double beta2, double eps, double grad_scale, void* stream);
 
 /* p-gradient of the sample-independent regularisers added in place: g += w_l2 * 2 * p (n_l2 leading elements) */
 int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream);
@@ -267,8 +268,8 @@ int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* st
  * and 4 (haar, db2).  Needs a device that supports cooperative launches (every B200 does). */
 int lfgc_step_glue(const lfgc_wavelet_desc* w, int Cp, float* const* coeff, float* const* grad_coeff, float* scratch,
                    const float* grad_grid_cl, float* grid_cl, float* also_zero, float* p, const float* g, float* m,
-                   float* v, int64_t n, const float* lr, int32_t* step_count, float beta1, float beta2, float eps,
-                   float grad_scale, int phases, void* stream);
+                   float* v, int64_t n, const float* lr, int32_t* step_count, double beta1, double beta2, double eps,
+                   double grad_scale, int phases, void* stream);
 
 /* Gradient of the KL regulariser of VariationalDropoutLoss (model/Variational_Dropout_Layer.py:54-69,115-122) added
  * in place to the mask-parameter gradients, and the per-step ramp of its weight (:57-58).  mask_params / mask_grads

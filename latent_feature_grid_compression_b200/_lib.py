@@ -17,6 +17,7 @@ MAX_LAYERS = 8
 
 MASK_IDENTITY, MASK_DIRECT, MASK_VARIATIONAL, MASK_STE_SIGMOID, MASK_BERNOULLI = range(5)
 F_CLAMP = 1
+ABI_VERSION = 2   # include/lfgc.h LFGC_ABI_VERSION this binding was written against
 
 _ERRORS = {-1: 'LFGC_E_INVALID', -2: 'LFGC_E_UNSUPPORTED', -3: 'LFGC_E_CUDA', -4: 'LFGC_E_WORKSPACE'}
 
@@ -71,11 +72,11 @@ _SIGNATURES = {
     'lfgc_reconstruct': (C.c_int, [C.POINTER(ModelDesc), _f, _f, C.POINTER(C.c_int32), _f, _f, _f, C.c_int32,
                                    C.c_int32, _f, C.c_int, _f]),
     'lfgc_deviation_stats': (C.c_int, [_f, _f, _i64, _f, _f]),
-    'lfgc_adam': (C.c_int, [_f, _f, _f, _f, _i64, _f, _f, C.c_float, C.c_float, C.c_float, C.c_float, _f]),
+    'lfgc_adam': (C.c_int, [_f, _f, _f, _f, _i64, _f, _f, C.c_double, C.c_double, C.c_double, C.c_double, _f]),
     'lfgc_add_l2_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_add_l1_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_step_glue': (C.c_int, [C.POINTER(WaveletDesc), C.c_int, C.POINTER(_f), C.POINTER(_f), _f, _f, _f, _f, _f, _f, _f, _f, _i64, _f, _f,
-                                 C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _f]),
+                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _f]),
     'lfgc_variational_dkl_grad': (C.c_int, [_f, _f, C.c_int, C.POINTER(C.c_int64), _f, _f, C.c_double, C.c_double,
                                             C.c_float, _f]),
 }
@@ -98,7 +99,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.lfgc_abi_version() != 1:
+    if lib.lfgc_abi_version() != ABI_VERSION:
         raise LfgcError('liblfgc.so ABI version mismatch; rebuild')
     _lib = lib
     return lib

@@ -2,6 +2,7 @@
 #include "lfgc_common.cuh"
 
 #include <atomic>
+#include <math.h>
 #include <stdlib.h>
 
 namespace lfgc {
@@ -21,6 +22,19 @@ bool pdl_enabled() {
         return e && e[0] == '1';              // against 79.9 us without (the graph already hides the launch latency)
     }();
     return on;
+}
+
+AdamCoef make_adam_coef(double beta1, double beta2, double eps, double grad_scale) {
+    AdamCoef c;
+    c.b1 = (float)beta1;
+    c.b2 = (float)beta2;
+    c.omb1 = (float)(1.0 - beta1);
+    c.omb2 = (float)(1.0 - beta2);
+    c.logb1 = (float)log(beta1);
+    c.logb2 = (float)log(beta2);
+    c.eps = (float)eps;
+    c.gscale = (float)grad_scale;
+    return c;
 }
 
 static int g_sm_count[64];

@@ -68,6 +68,16 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// torch.optim.Adam coefficients as torch forms them: the betas are Python doubles there, so 1 - beta and the bias
+// corrections come from the fp64 values and are only then rounded to fp32 (1 - fl32(0.999) would be 4.7e-5 off).
+struct AdamCoef {
+    float b1, b2;          // fl32(beta)
+    float omb1, omb2;      // fl32(1 - beta)
+    float logb1, logb2;    // fl32(log(beta)): bias correction 1 - beta^step = -expm1(step * log(beta))
+    float eps, gscale;
+};
+AdamCoef make_adam_coef(double beta1, double beta2, double eps, double grad_scale);   // api.cu
+
 int sm_count();            // cached per device
 int max_smem_optin();      // cached per device (bytes)
 
@@ -89,6 +99,29 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
 }
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// One element of torch.optim.Adam (training/training.py:199,232; torch/optim/adam.py _single_tensor_adam):
+//   exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2);
+//   denom = exp_avg_sq.sqrt() / sqrt(bias_correction2) + eps; param.addcdiv_(exp_avg, denom, value=-lr / bias_correction1)
+__host__ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamCoef& c,
+                                                     float step_size, float bc2_sqrt) {
+    const float gi = g * c.gscale;
+    float mi = m, vi = v;
+    mi = mi + (gi - mi) * c.omb1;
+    vi = vi * c.b2 + c.omb2 * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + c.eps;
+    p = p - step_size * (mi / denom);
+    m = mi;
+    v = vi;
+}
+// step_size = lr / (1 - beta1^step), bc2_sqrt = sqrt(1 - beta2^step)
+__host__ __device__ __forceinline__ void adam_step_scalars(const AdamCoef& c, int step, float lr, float& step_size,
+                                                           float& bc2_sqrt) {
+    const float bc1 = -expm1f((float)step * c.logb1);
+    const float bc2 = -expm1f((float)step * c.logb2);
+    step_size = lr / bc1;
+    bc2_sqrt = sqrtf(bc2);
+}
 
 // Branch-free fp32 sin/cos: Cody-Waite reduction by pi/2 (three-term split, exact products through FMA) followed
 // by the classic minimax polynomials on [-pi/4, pi/4].  Max error ~1 ulp for |x| < 1e4 (beyond that the 3-term

@@ -9,29 +9,26 @@ namespace lfgc {
 // one launch and stays correct under CUDA-graph replay.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, const float* __restrict__ lr_ptr,
-                            int32_t* __restrict__ step_ptr, float b1, float b2, float eps, float gscale) {
+                            int32_t* __restrict__ step_ptr, const AdamCoef c) {
     LFGC_PDL_PROLOGUE();
     __shared__ float s_step_size, s_bc2_sqrt;
     __shared__ int s_step;
     if (threadIdx.x == 0) {
         const int step = *reinterpret_cast<volatile int32_t*>(step_ptr) + 1;
         s_step = step;
-        // bias corrections 1 - beta^step as -expm1(step * log(beta)): fp32 keeps ~1e-7 relative accuracy without the
-        // cancellation of 1 - pow() and without the slow fp64 pipe (one thread per block sits on this latency)
-        const float bc1 = -expm1f((float)step * logf(b1));
-        const float bc2 = -expm1f((float)step * logf(b2));
-        s_step_size = *lr_ptr / bc1;
-        s_bc2_sqrt = sqrtf(bc2);
+        // bias corrections in fp32 from fl32(log(beta)) (see AdamCoef): ~1e-7 relative, without the cancellation of
+        // 1 - pow() and without the slow fp64 pipe (one thread per block sits on this latency)
+        float step_size, bc2_sqrt;
+        adam_step_scalars(c, step, *lr_ptr, step_size, bc2_sqrt);
+        s_step_size = step_size;
+        s_bc2_sqrt = bc2_sqrt;
     }
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        const float gi = g[i] * gscale;
-        float mi = m[i], vi = v[i];
-        mi = mi + (gi - mi) * (1.0f - b1);              // exp_avg.lerp_(grad, 1 - beta1)
-        vi = vi * b2 + (1.0f - b2) * gi * gi;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-        const float denom = sqrtf(vi) / s_bc2_sqrt + eps;
-        p[i] = p[i] - s_step_size * (mi / denom);       // param.addcdiv_(exp_avg, denom, value=-step_size)
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_update(pi, g[i], mi, vi, c, s_step_size, s_bc2_sqrt);
+        p[i] = pi;
         m[i] = mi;
         v[i] = vi;
     }
@@ -126,11 +123,12 @@ extern "C" int lfgc_variational_dkl_grad(const float* mask_params, float* mask_g
 
 
 extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
-                         float beta1, float beta2, float eps, float grad_scale, void* stream) {
+                         double beta1, double beta2, double eps, double grad_scale, void* stream) {
     if (!p || !g || !m || !v || !lr || !step_count || n < 0) return fail(LFGC_E_INVALID, "adam: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t blocks = n == 0 ? 1 : (n + 255) / 256;
-    (void)launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), st, p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale);
+    (void)launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), st, p, g, m, v, n, lr, step_count,
+                     make_adam_coef(beta1, beta2, eps, grad_scale));
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }

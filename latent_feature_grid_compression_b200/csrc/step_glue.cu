@@ -41,7 +41,7 @@ struct Args {
     long long n;
     const float* lr;
     int* step;
-    float b1, b2, eps, gscale;
+    AdamCoef c;
     int phases;                       // 1 = adjoint, 2 = Adam, 4 = synthesis
 };
 
@@ -160,14 +160,11 @@ __host__ __device__ __forceinline__ void adjoint_elem(const Args& A, int l, long
     }
 }
 
-// torch.optim.Adam for one element (optim.cu adam_kernel); step_size = lr / (1 - b1^step), bc2_sqrt = sqrt(1 - b2^step)
+// torch.optim.Adam for one element: the function optim.cu's adam_kernel uses (lfgc_common.cuh adam_update)
 __host__ __device__ __forceinline__ void adam_elem(const Args& A, long long i, float step_size, float bc2_sqrt) {
-    const float gi = A.g[i] * A.gscale;
-    float mi = A.m[i], vi = A.v[i];
-    mi = mi + (gi - mi) * (1.0f - A.b1);
-    vi = vi * A.b2 + (1.0f - A.b2) * gi * gi;
-    const float denom = sqrtf(vi) / bc2_sqrt + A.eps;
-    A.p[i] = A.p[i] - step_size * (mi / denom);
+    float pi = A.p[i], mi = A.m[i], vi = A.v[i];
+    adam_update(pi, A.g[i], mi, vi, A.c, step_size, bc2_sqrt);
+    A.p[i] = pi;
     A.m[i] = mi;
     A.v[i] = vi;
 }
@@ -200,10 +197,8 @@ __global__ void __launch_bounds__(256) step_glue_kernel(const __grid_constant__ 
     if (A.phases & 2) {
         // torch.optim.Adam; every thread reads the step count before anybody publishes the new one (after the barrier)
         const int step = *reinterpret_cast<volatile int*>(A.step) + 1;
-        const float bc1 = -expm1f((float)step * logf(A.b1));
-        const float bc2 = -expm1f((float)step * logf(A.b2));
-        const float step_size = *A.lr / bc1;
-        const float bc2_sqrt = sqrtf(bc2);
+        float step_size, bc2_sqrt;
+        adam_step_scalars(A.c, step, *A.lr, step_size, bc2_sqrt);
         for (long long i = gtid; i < A.n; i += gsize) adam_elem(A, i, step_size, bc2_sqrt);
         grid.sync();
         if (gtid == 0) *A.step = step;
@@ -261,7 +256,7 @@ using namespace lfgc;
 static int glue_fill_args(glue::Args& A, const lfgc_wavelet_desc* w, int Cp, float* const* coeff, float* const* grad_coeff,
                           float* scratch, const float* grad_grid_cl, float* grid_cl, float* also_zero, float* p,
                           const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
-                          float beta1, float beta2, float eps, float grad_scale, int phases) {
+                          double beta1, double beta2, double eps, double grad_scale, int phases) {
 
     if (!w || !coeff || !grad_coeff) return fail(LFGC_E_INVALID, "step_glue: null descriptor / pointer table");
     if (w->n_coeff < 1 || w->n_coeff > LFGC_MAX_LEVELS || w->C < 1) return fail(LFGC_E_INVALID, "step_glue: bad descriptor");
@@ -308,10 +303,7 @@ static int glue_fill_args(glue::Args& A, const lfgc_wavelet_desc* w, int Cp, flo
     A.n = n;
     A.lr = lr;
     A.step = step_count;
-    A.b1 = beta1;
-    A.b2 = beta2;
-    A.eps = eps;
-    A.gscale = grad_scale;
+    A.c = make_adam_coef(beta1, beta2, eps, grad_scale);
     A.phases = phases & 7;
     return LFGC_OK;
 }
@@ -319,7 +311,7 @@ static int glue_fill_args(glue::Args& A, const lfgc_wavelet_desc* w, int Cp, flo
 extern "C" int lfgc_step_glue(const lfgc_wavelet_desc* w, int Cp, float* const* coeff, float* const* grad_coeff,
                               float* scratch, const float* grad_grid_cl, float* grid_cl, float* also_zero, float* p,
                               const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
-                              float beta1, float beta2, float eps, float grad_scale, int phases, void* stream) {
+                              double beta1, double beta2, double eps, double grad_scale, int phases, void* stream) {
     if ((phases & 7) == 0) return LFGC_OK;
     glue::Args A;
     const int rc = glue_fill_args(A, w, Cp, coeff, grad_coeff, scratch, grad_grid_cl, grid_cl, also_zero, p, g, m, v, n, lr,
@@ -349,10 +341,8 @@ static void glue_run_host(const glue::Args& A) {
     }
     if (A.phases & 2) {
         const int step = *A.step + 1;
-        const float bc1 = -expm1f((float)step * logf(A.b1));
-        const float bc2 = -expm1f((float)step * logf(A.b2));
-        const float step_size = *A.lr / bc1;
-        const float bc2_sqrt = sqrtf(bc2);
+        float step_size, bc2_sqrt;
+        adam_step_scalars(A.c, step, *A.lr, step_size, bc2_sqrt);
         for (long long i = 0; i < A.n; ++i) adam_elem(A, i, step_size, bc2_sqrt);
         *A.step = step;
     }
@@ -377,7 +367,7 @@ static void glue_run_host(const glue::Args& A) {
 extern "C" int lfgc_step_glue_host(const lfgc_wavelet_desc* w, int Cp, float* const* coeff, float* const* grad_coeff,
                                    float* scratch, const float* grad_grid_cl, float* grid_cl, float* also_zero, float* p,
                                    const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
-                                   float beta1, float beta2, float eps, float grad_scale, int phases) {
+                                   double beta1, double beta2, double eps, double grad_scale, int phases) {
     if ((phases & 7) == 0) return LFGC_OK;
     glue::Args A;
     const int rc = glue_fill_args(A, w, Cp, coeff, grad_coeff, scratch, grad_grid_cl, grid_cl, also_zero, p, g, m, v, n, lr,
