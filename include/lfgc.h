@@ -34,6 +34,7 @@ extern "C" {
 #define LFGC_MAX_LEVELS 12 /* coefficient tensors per model (1 low-pass + up to 11 detail levels) */
 #define LFGC_MAX_TAPS 16   /* longest supported 1-D reconstruction filter */
 #define LFGC_MAX_LAYERS 8  /* hidden layers of the decoder MLP */
+#define LFGC_MAX_PEERS 16  /* ranks whose gradient buffers lfgc_adam_p2p can sum */
 
 enum {
     LFGC_OK = 0,
@@ -252,6 +253,14 @@ int lfgc_deviation_stats(const float* pred, const float* gt, int64_t n, double* 
  * lfgc_add_l2_grad, lfgc_variational_dkl_grad) issued before this one. */
 int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
               double beta1, double beta2, double eps, double grad_scale, void* stream);
+
+/* lfgc_adam fused with a one-shot all-reduce over peer memory (the path's one collective): the gradient is
+ * the sum over the `world` buffers peer_g[r] (HOST array of DEVICE pointers, this rank's own buffer included, e.g. the
+ * buffer_ptrs of a torch symmetric-memory allocation), accumulated in rank order so that all ranks stay bit-identical.
+ * The caller brackets the launch with cross-rank barriers: every rank's gradients are complete before, nobody
+ * overwrites its buffer until all ranks have read it after. */
+int lfgc_adam_p2p(float* p, const float* const* peer_g, int world, float* m, float* v, int64_t n, const float* lr,
+                  int32_t* step_count, double beta1, double beta2, double eps, double grad_scale, void* stream);
 
 /* p-gradient of the sample-independent regularisers added in place: g += w_l2 * 2 * p (n_l2 leading elements) */
 int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream);

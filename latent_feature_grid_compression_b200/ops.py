@@ -376,6 +376,16 @@ def adam(p, g, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_sc
                           _p(_req(lr_dev, 'lr')), _p(step_dev), beta1, beta2, eps, grad_scale, _stream()), 'lfgc_adam')
 
 
+def adam_p2p(p, peer_grad_ptrs, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """Adam whose gradient is the rank-ordered sum of the ranks' buffers read over NVLink (lfgc_adam_p2p).
+    ``peer_grad_ptrs``: device addresses of every rank's gradient buffer (symmetric memory), this rank's included."""
+    lib = L.load()
+    _req(step_dev, 'step', torch.int32)
+    L.check(lib.lfgc_adam_p2p(_p(_req(p, 'p')), L.ptr_array([int(a) for a in peer_grad_ptrs]), len(peer_grad_ptrs),
+                              _p(_req(m, 'm')), _p(_req(v, 'v')), p.numel(), _p(_req(lr_dev, 'lr')), _p(step_dev),
+                              beta1, beta2, eps, grad_scale, _stream()), 'lfgc_adam_p2p')
+
+
 def step_glue(geom: Geometry, coeffs, grad_coeffs, scratch, grad_grid_cl, grid_cl, also_zero, p, g, m, v, lr_dev,
               step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, phases=7):
     """Synthesis adjoint (1) + Adam (2) + synthesis of the updated coefficients (4) in one cooperative launch

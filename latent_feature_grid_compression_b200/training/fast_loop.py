@@ -101,18 +101,22 @@ class FastTrainer:
         self.flat_g = torch.zeros_like(self.flat_p)
         self._symm = None
         import os
-        if self.world > 1 and os.environ.get('LFGC_ALLREDUCE', 'nccl') == 'symm':
-            # opt-in: one-shot all-reduce over NVLink peer memory (torch symmetric memory: every rank reads the peers'
-            # gradient buffers directly, barrier before and after inside the op) instead of the NCCL ring / tree, whose
-            # latency dominates this 0.5 MB message.  The gradient buffer must then live in symmetric memory.
+        mode = os.environ.get('LFGC_ALLREDUCE', 'nccl')
+        if self.world > 1 and mode in ('symm', 'p2p'):
+            # opt-in: the gradient buffer lives in torch symmetric memory (every rank can read the peers' buffers over
+            # NVLink).  'symm': torch's one-shot all-reduce op instead of the NCCL ring / tree, whose latency dominates
+            # this 0.5 MB message.  'p2p': no separate collective at all -- lfgc_adam_p2p sums the peers' buffers inside
+            # the Adam kernel, bracketed by symmetric-memory barriers (mask-free / regulariser-free models).
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
             grp = self.group if self.group is not None else dist.group.WORLD
             g = symm_mem.empty(total, dtype=torch.float32, device=self.device)
             g.zero_()
-            symm_mem.rendezvous(g, grp)
+            hdl = symm_mem.rendezvous(g, grp)
             self.flat_g = g
-            self._symm = dict(name=grp.group_name, out=torch.zeros_like(self.flat_p))
+            fused = (mode == 'p2p' and self.var_cfg is None and self.weight_l1 == 0.0 and self.weight_l2 == 0.0)
+            self._symm = dict(name=grp.group_name, out=torch.zeros_like(self.flat_p), hdl=hdl,
+                              peers=[int(a) for a in hdl.buffer_ptrs] if fused else None)
         self.flat_m = torch.zeros_like(self.flat_p)
         self.flat_v = torch.zeros_like(self.flat_p)
         # keep the model's own MLP pack coherent with the shared buffer
@@ -190,6 +194,15 @@ class FastTrainer:
         torch.ops.symm_mem.one_shot_all_reduce_out(self.flat_g, 'sum', self._symm['name'], self._symm['out'])
         return self._symm['out']
 
+    def _adam_p2p(self):
+        """Adam with the all-reduce folded in (lfgc_adam_p2p): barrier (all ranks' gradients are complete), peer reads +
+        update, barrier (nobody overwrites its gradient buffer before everyone has read it)."""
+        hdl = self._symm['hdl']
+        hdl.barrier(channel=0)
+        ops.adam_p2p(self.flat_p, self._symm['peers'], self.flat_m, self.flat_v, self.lr_dev, self.step_dev,
+                     self.betas[0], self.betas[1], self.eps)
+        hdl.barrier(channel=1)
+
     def _step_body(self, host_fed=False):
         model, geom = self.model, self.geom
         in_coords, in_targets = self._in_coords, self._in_targets
@@ -239,6 +252,8 @@ class FastTrainer:
             self.grad_of(spec.grad_params[0]).copy_(g0)
             if len(spec.grad_params) == 2:
                 self.grad_of(spec.grad_params[1]).copy_(g1)
+        if self.world > 1 and self._symm is not None and self._symm['peers'] is not None:
+            return self._adam_p2p()
         g_red = self._allreduce_grads() if self.world > 1 else self.flat_g
         if self.var_cfg is not None:
             # sample-independent terms of VariationalDropoutLoss, added once after the reduction: KL of the live masks

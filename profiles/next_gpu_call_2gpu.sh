@@ -19,3 +19,4 @@ PY
 run nccl "LFGC_ALLREDUCE=nccl"          # also checks that the run EXITS now (round 1: it did not)
 run symm "LFGC_ALLREDUCE=symm"          # one-shot all-reduce over symmetric memory
 run symm_glue "LFGC_ALLREDUCE=symm LFGC_GLUE=1"
+run p2p "LFGC_ALLREDUCE=p2p"            # all-reduce folded into the Adam kernel (lfgc_adam_p2p) between symm-mem barriers
