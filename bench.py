@@ -398,7 +398,8 @@ def run_native(args):
                                 step='one volume pass = %d optimiser steps (sampler + GT + synthesis + fwd + MSE + bwd '
                                      '+ adjoint%s + Adam), CUDA-graph replay' % (steps_per_pass, ' + NCCL all-reduce' if world > 1 else ''),
                                 l2='flushed between timed steps (256 MiB write outside the event pairs)',
-                                parallelism='dp%d' % world),
+                                parallelism='dp%d' % world,
+                                switches={k: v for k, v in sorted(os.environ.items()) if k.startswith('LFGC_')}),
                     e2e=e2e, gpu_launches=int(trainer.launches_per_step * steps_per_pass * args.steps),
                     clocks=dict(sm_mhz=clk['sm_mhz'], sm_max_mhz=clk['sm_max_mhz'], reasons=clk['reasons'],
                                 samples=clk['samples']),
