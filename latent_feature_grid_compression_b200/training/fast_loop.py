@@ -422,22 +422,82 @@ class FastTrainer:
         """Mean squared error of the last step's local batch (device -> host read)."""
         return float(self.loss_sum.item()) / self.batch
 
+    def complete_loss(self) -> float:
+        """``complete_loss`` of training/training.py:130-135 for the last step: MSE over the GLOBAL batch plus the
+        SmallifyLoss terms (Smallify_Dropout.py:22-40).  The MSE is the step's own (pre-update parameters); the
+        regulariser sums are read after the update (one Adam step later than the reference; they carry weights of
+        1e-8 in the shipped configs and only feed the plateau test of SmallifyDecayStrategy).  Rank-identical."""
+        if self.var_cfg is not None:
+            raise L.LfgcError('complete_loss() is defined for the MSE (+ SmallifyLoss) objective only')
+        with torch.no_grad():
+            t = self.loss_sum.double() / float(self.batch * self.world)
+            if self.world > 1:
+                t = t.clone()
+                torch.distributed.all_reduce(t, group=self.group)
+            if self.weight_l1 > 0.0 and self.n_mask_elems:
+                t = t + self.weight_l1 * self.flat_p[self.mask_off:self.mask_off + self.n_mask_elems].abs().sum().double()
+            if self.weight_l2 > 0.0 and self.n_coeff_elems:
+                t = t + self.weight_l2 * (self.flat_p[:self.n_coeff_elems].double() ** 2).sum()
+            return float(t.item())
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # whole training run: the reference's ``training(args)`` flow on the fast loop
 # ---------------------------------------------------------------------------------------------------------------------
 
-class NeurcompDecay:
-    """x ``lr_decay`` whenever a pass boundary is crossed and (pass + 1) % pass_decay == 0
-    (reference training/learning_rate_decay.py:24-34)."""
+class LRSchedule:
+    """The reference's ``LearningRateDecayStrategy`` pair (training/learning_rate_decay.py:12-57), selected like
+    ``create_instance`` (:14-18): ``smallify_decay == 0`` -> NeurcompDecayStrategy (x ``lr_decay`` whenever a pass
+    boundary is crossed and (pass + 1) % pass_decay == 0), else SmallifyDecayStrategy (loss plateau: after
+    ``smallify_decay`` pass boundaries without a new best loss multiply the rate by ``lr_decay``; once the rate is at or
+    below 1e-7 the strategy asks for an early stop).
 
-    def __init__(self, trainer: FastTrainer, lr: float, pass_decay: int, lr_decay: float):
-        self.trainer, self.lr, self.pass_decay, self.lr_decay = trainer, lr, pass_decay, lr_decay
+    ONE object spans both training phases, as in the reference (training/training.py:200,222-237): it stays bound to
+    the PHASE-1 optimiser, so in phase 2 it keeps counting (and the plateau flavour can still stop the run) but its
+    rate changes no longer reach the optimiser that is stepping.  ``bind(trainer)`` / ``bind(None)`` model that."""
 
-    def update(self, prior_passes: int, cur_passes: float):
-        if prior_passes != int(cur_passes) and (int(cur_passes) + 1) % self.pass_decay == 0:
-            self.lr *= self.lr_decay
+    def __init__(self, args, lr: float):
+        self.lr = float(lr)                          # learning rate of the phase-1 optimiser
+        self.lr_decay = float(args['lr_decay'])
+        self.smallify = int(args.get('smallify_decay', 0) or 0)
+        self.epoch_delay = self.smallify if self.smallify else int(args['pass_decay'])
+        self.lr_stop = 1e-07
+        self.last_loss = None
+        self.no_gain_epoch = 0
+        self.trainer = None
+        self.decays = 0
+
+    def bind(self, trainer):
+        self.trainer = trainer
+
+    def _decay(self):
+        self.lr *= self.lr_decay
+        self.decays += 1
+        if self.trainer is not None:
             self.trainer.set_lr(self.lr)
+
+    def update(self, prior_passes: int, cur_passes: float, loss_fn=None) -> bool:
+        """Call after every optimiser step; ``loss_fn()`` returns the step's complete loss (only evaluated at a pass
+        boundary of the plateau strategy: one device->host read per volume pass).  True = stop training."""
+        if prior_passes == int(cur_passes):
+            return False
+        if not self.smallify:
+            if (int(cur_passes) + 1) % self.epoch_delay == 0:
+                self._decay()
+            return False
+        loss = float(loss_fn())
+        if self.last_loss is None or loss < self.last_loss:
+            self.last_loss = loss
+            self.no_gain_epoch = 0
+        else:
+            self.no_gain_epoch += 1
+        if self.no_gain_epoch == self.epoch_delay:
+            if self.lr > self.lr_stop:
+                self._decay()
+            else:
+                return True
+            self.no_gain_epoch = 0
+        return False
 
 
 def _regulariser_weights(args):
@@ -447,10 +507,35 @@ def _regulariser_weights(args):
     return 0.0, 0.0
 
 
-def solve_phase(model, volume, n_voxels, args, max_pass, lr, decay: bool, seed=0, rank=0, world=1, group=None,
-                regularise=True, verbose=False):
-    """The reference's pass accounting (training.py:87,112-114,178): stop once int(volume_passes) >= max_pass."""
+def epoch_schedule(n_voxels: int, batch_size: int, sample_size: int, max_pass: float):
+    """The reference's pass accounting as a generator of (step index, prior_passes, volume_passes, last) tuples
+    (training/training.py:76-114,178): the ``while int(volume_passes) + 1 < max_pass`` test is evaluated only at
+    DataLoader-epoch boundaries (one epoch = ceil(n_voxels / batch_size) batches = ``sample_size`` volume passes);
+    inside an epoch the loop leaves only through ``int(volume_passes) >= max_pass``.  The caller may stop early
+    (plateau strategy) by closing the generator."""
+    per_step = float(batch_size * sample_size)
+    steps_per_epoch = -(-int(n_voxels) // int(batch_size))
+    seen, passes, step = 0.0, 0.0, 0
+    while int(passes) + 1 < max_pass:
+        for _ in range(steps_per_epoch):
+            prior = int(seen / n_voxels)
+            seen += per_step
+            passes = seen / n_voxels
+            step += 1
+            done = int(passes) >= max_pass
+            yield step, prior, passes, done
+            if done:
+                break
+
+
+def solve_phase(model, volume, n_voxels, args, max_pass, lr, sched: Optional[LRSchedule] = None, bind: bool = True,
+                seed=0, rank=0, world=1, group=None, regularise=True, verbose=False):
+    """``solve_model`` (training/training.py:71-181) on the graph-captured step.  The GLOBAL batch is the reference's
+    ``batch_size * sample_size``; with ``world`` ranks each takes ``1/world`` of it (strong scaling, same optimisation
+    problem).  Returns (trainer, stopped_early)."""
     batch = int(args['batch_size']) * int(args['sample_size'])
+    if batch % world != 0:
+        raise L.LfgcError('batch_size * sample_size = %d is not divisible by the world size %d' % (batch, world))
     w1, w2 = _regulariser_weights(args) if regularise else (0.0, 0.0)
     variational = None
     drop = args.get('drop_type') or ''
@@ -465,28 +550,28 @@ def solve_phase(model, volume, n_voxels, args, max_pass, lr, decay: bool, seed=0
             variational['variance_model'] = Variance_Model().to(volume.device).train()
         else:
             variational['log_sigma'] = float(args['variational_sigma'])
-    trainer = FastTrainer(model, volume, batch // world if world > 1 else batch, lr=lr, seed=seed, rank=rank,
+        if sched is not None and sched.smallify:
+            raise L.LfgcError('smallify_decay != 0 (loss-plateau schedule) is not implemented for the variational loss '
+                              'in the fast loop; use the module path (training/training.py) for that combination')
+    trainer = FastTrainer(model, volume, batch // world, lr=lr, seed=seed, rank=rank,
                           world_size=world, process_group=group, weight_l1=w1, weight_l2=w2, variational=variational)
-    sched = NeurcompDecay(trainer, lr, int(args['pass_decay']), float(args['lr_decay'])) if decay else None
-    seen = 0.0
-    passes = 0.0
-    per_step = trainer.batch * world
-    while int(passes) + 1 < max_pass:
-        prior = int(seen / n_voxels)
+    if sched is not None:
+        sched.bind(trainer if bind else None)
+    stopped = False
+    for step, prior, passes, last in epoch_schedule(n_voxels, int(args['batch_size']), int(args['sample_size']),
+                                                    max_pass):
         trainer.step()
-        seen += per_step
-        passes = seen / n_voxels
-        if sched is not None:
-            sched.update(prior, passes)
+        if sched is not None and sched.update(prior, passes, trainer.complete_loss):
+            stopped = True
+            break
         if verbose and trainer.steps_done % 500 == 0:
             print('pass %.3f / %.1f  mse %.6f' % (passes, max_pass, trainer.last_loss()))
-        if int(passes) >= max_pass:
-            break
     torch.cuda.synchronize()
-    return trainer
+    return trainer, stopped
 
 
-def train_volume(args: dict, volume: Optional[torch.Tensor] = None, seed: int = 0, verbose: bool = False):
+def train_volume(args: dict, volume: Optional[torch.Tensor] = None, seed: int = 0, verbose: bool = False, rank: int = 0,
+                 world: int = 1, group=None):
     """Two-phase training + evaluation with the reference's schedule (training/training.py:184-243): 2/3 of the
     passes with masks and regularisers, bake the masks, 1/3 fine-tuning at lr/10, strip the mask layers, reconstruct
     the volume and report PSNR / compression ratio."""
@@ -504,12 +589,15 @@ def train_volume(args: dict, volume: Optional[torch.Tensor] = None, seed: int = 
                         args['wavelet_filter'], args['grid_features'], args['grid_size'], args.get('checkpoint_path', ''))
     model.to(device)
     model.train()
-    t1 = solve_phase(model, volume_dev, dataset.n_voxels, args, args['max_pass'] * (2.0 / 3.0), args['lr'], True,
-                     seed=seed, verbose=verbose)
+    sched = LRSchedule(args, args['lr'])
+    t1, _ = solve_phase(model, volume_dev, dataset.n_voxels, args, args['max_pass'] * (2.0 / 3.0), args['lr'], sched,
+                        bind=True, seed=seed, rank=rank, world=world, group=group, verbose=verbose)
     zeros = model.save_dropvalues_on_grid(device)
-    # phase 2: plain MSE, lr / 10, no decay (the reference's strategy object stays bound to the first optimizer)
-    t2 = solve_phase(model, volume_dev, dataset.n_voxels, args, args['max_pass'] * (1.0 / 3.0), args['lr'] / 10.0, False,
-                     seed=seed + 1, regularise=False, verbose=verbose)
+    # phase 2: plain MSE, lr / 10; the strategy object stays bound to the first optimiser (reference
+    # training/training.py:234-237), so its decays do not reach this phase -- but its early stop does
+    t2, _ = solve_phase(model, volume_dev, dataset.n_voxels, args, args['max_pass'] * (1.0 / 3.0), args['lr'] / 10.0,
+                        sched, bind=False, seed=seed + 1, rank=rank, world=world, group=group, regularise=False,
+                        verbose=verbose)
     model.remove_drop_layers(device)
     psnr, l1, mse, rmse = tiled_net_out(dataset, model, True, gt_vol=volume_dev, evaluate=True, write_vols=False)
     n_params = sum(p.numel() for n, p in model.named_parameters() if 'drop' not in n)
