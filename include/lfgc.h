@@ -30,11 +30,11 @@
 extern "C" {
 #endif
 
-#define LFGC_ABI_VERSION 2 /* 2: lfgc_adam / lfgc_step_glue take their hyper-parameters as doubles */
+#define LFGC_ABI_VERSION 3 /* 3: lfgc_grid_step / lfgc_train_step_partials replace lfgc_step_glue */
 #define LFGC_MAX_LEVELS 12 /* coefficient tensors per model (1 low-pass + up to 11 detail levels) */
 #define LFGC_MAX_TAPS 16   /* longest supported 1-D reconstruction filter */
 #define LFGC_MAX_LAYERS 8  /* hidden layers of the decoder MLP */
-#define LFGC_MAX_PEERS 16  /* ranks whose gradient buffers lfgc_adam_p2p can sum */
+#define LFGC_MAX_PEERS 16  /* ranks whose gradient buffers lfgc_grid_step can sum */
 
 enum {
     LFGC_OK = 0,
@@ -254,31 +254,60 @@ int lfgc_deviation_stats(const float* pred, const float* gt, int64_t n, double* 
 int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
               double beta1, double beta2, double eps, double grad_scale, void* stream);
 
-/* lfgc_adam fused with a one-shot all-reduce over peer memory (the path's one collective): the gradient is
- * the sum over the `world` buffers peer_g[r] (HOST array of DEVICE pointers, this rank's own buffer included, e.g. the
- * buffer_ptrs of a torch symmetric-memory allocation), accumulated in rank order so that all ranks stay bit-identical.
- * The caller brackets the launch with cross-rank barriers: every rank's gradients are complete before, nobody
- * overwrites its buffer until all ranks have read it after. */
-int lfgc_adam_p2p(float* p, const float* const* peer_g, int world, float* m, float* v, int64_t n, const float* lr,
-                  int32_t* step_count, double beta1, double beta2, double eps, double grad_scale, void* stream);
-
 /* p-gradient of the sample-independent regularisers added in place: g += w_l2 * 2 * p (n_l2 leading elements) */
 int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 
-/* Everything of one optimiser step that is not per-sample, for mask-free models, in ONE cooperative launch
- * (grid-wide barriers between the phases instead of kernel boundaries).  phases is a bit mask:
- *   1  synthesis adjoint (lfgc_decode_bwd without multipliers): grad_grid_cl -> grad_coeff[l] (overwritten)
- *   2  Adam over the flat buffers (lfgc_adam; step_count[0] is incremented, step_count[1] is not used)
- *   4  synthesis of the (updated) coefficients (lfgc_decode_fwd without multipliers) -> grid_cl, also_zero cleared
- * i.e. 1|2|4 replaces lfgc_decode_bwd + lfgc_adam + lfgc_decode_fwd of the NEXT step (training/training.py:137,
- * torch.optim.Adam.step, model/Feature_Grid_Model.py:102-108); data-parallel callers run 1, all-reduce, then 2|4.
- * coeff / grad_coeff are HOST arrays of n_coeff DEVICE pointers; scratch as for lfgc_decode_fwd.  Filter lengths 2
- * and 4 (haar, db2).  Needs a device that supports cooperative launches (every B200 does). */
-int lfgc_step_glue(const lfgc_wavelet_desc* w, int Cp, float* const* coeff, float* const* grad_coeff, float* scratch,
-                   const float* grad_grid_cl, float* grid_cl, float* also_zero, float* p, const float* g, float* m,
-                   float* v, int64_t n, const float* lr, int32_t* step_count, double beta1, double beta2, double eps,
-                   double grad_scale, int phases, void* stream);
+/* lfgc_train_step that LEAVES the MLP-gradient partial sums in the workspace instead of reducing them: *nslices_out (host
+ * int, written at call time) rows of (lfgc_mlp_param_count + 1) floats, the last float of a row being that slice's
+ * share of the loss sum.  lfgc_grid_step reduces them (same fixed order -> deterministic) together with the rest of the
+ * optimiser step, which saves a dependent launch.  n must be positive. */
+int lfgc_train_step_partials(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n, uint64_t seed,
+                             uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
+                             const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
+                             float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl,
+                             void* workspace, size_t workspace_bytes, int32_t* nslices_out, void* stream);
+
+/* Everything of one optimiser step that is not per-sample, for mask-free models, in ONE launch: [sum over the
+ * data-parallel ranks' gradient buffers, read from peer memory] -> reduction of the MLP-gradient partial sums (+ loss) ->
+ * synthesis adjoint (autograd of Feature_Grid_Model.decode_volume, model/Feature_Grid_Model.py:102-108) -> [+ 2 weight_l2
+ * coeff, SmallifyLoss' weight term, model/Smallify_Dropout.py:29,37] -> Adam over coefficients and MLP (torch.optim.Adam,
+ * training/training.py:199,232) -> synthesis of the UPDATED coefficients into the channels-last grid the next step gathers
+ * from, gradient accumulator cleared.  Replaces lfgc_decode_bwd + lfgc_adam + the next step's lfgc_decode_fwd (+ the
+ * partial reduction of lfgc_train_step).  One CTA per channel, the channel's wavelet pyramid in shared memory, levels
+ * evaluated separably; no grid-wide barrier.  step_count as for lfgc_adam ([0] steps taken, [1] ticket scratch = 0).
+ * All pointers inside the struct are DEVICE pointers; the struct itself is read on the host at call time. */
+typedef struct lfgc_grid_step_args {
+    int32_t n_srcs;                               /* gradient sources summed in index order: 1, or the world size */
+    const float* grad_grid[LFGC_MAX_PEERS];       /* channels-last grid gradients (G0,G1,G2,Cp), one per source */
+    const float* mlp_partials[LFGC_MAX_PEERS];    /* per source: nslices rows of pstride floats (MLP gradient, loss at [pcount]) */
+    int32_t nslices;                              /* rows per source (lfgc_train_step_partials' nslices_out; 1 after a reduction) */
+    int32_t pstride, pcount;                      /* row stride (>= pcount + 1) and MLP parameter count (0: no MLP block) */
+    float* zero_grid;                             /* gradient accumulator to clear (normally grad_grid[0]); NULL: none */
+    float* grid_cl;                               /* out: decoded grid of the updated coefficients, channels-last */
+    float* p;                                     /* flat parameter buffer ... */
+    float* g;                                     /* ... gradients (written: coefficient and MLP sections) ... */
+    float* m;                                     /* ... Adam first ... */
+    float* v;                                     /* ... and second moments */
+    int64_t coeff_off[LFGC_MAX_LEVELS];           /* offset (floats) of coefficient tensor l inside the flat buffers */
+    int64_t mlp_off;                              /* offset of the packed MLP block */
+    float* loss_out;                              /* sum of the loss slots of all sources / slices; NULL: none */
+    const float* lr;                              /* device scalar */
+    int32_t* step_count;
+    double beta1, beta2, eps, grad_scale, weight_l2;
+    /* Data-parallel barrier inside the kernel (sync_epoch != NULL; n_srcs = world size, the sources are the ranks'
+     * buffers in PEER memory): before any source is read, this rank stores its epoch (*sync_epoch + 1) into slot [rank]
+     * of every rank's flag array and waits until all n_srcs slots of its own array carry that epoch; the kernel then
+     * increments *sync_epoch.  Flags and epoch start at 0; every rank must issue the same sequence of launches.  The
+     * caller double-buffers the sources by epoch parity (a rank may only overwrite a buffer its peers read one epoch
+     * later), which is why one barrier per step is enough. */
+    int32_t rank;
+    int32_t* sync_flags[LFGC_MAX_PEERS];          /* flag array (int32[n_srcs]) of every rank, as mapped on THIS device */
+    int32_t* sync_epoch;                          /* this rank's launch counter (device int32) */
+} lfgc_grid_step_args;
+int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a, void* stream);
+/* dynamic shared memory lfgc_grid_step needs for this pyramid; 0 = not supported (does not fit: use the separate kernels) */
+size_t lfgc_grid_step_smem_bytes(const lfgc_wavelet_desc* w);
 
 /* Gradient of the KL regulariser of VariationalDropoutLoss (model/Variational_Dropout_Layer.py:54-69,115-122) added
  * in place to the mask-parameter gradients, and the per-step ramp of its weight (:57-58).  mask_params / mask_grads

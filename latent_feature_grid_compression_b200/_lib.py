@@ -14,10 +14,11 @@ LIB_PATH = os.environ.get('LFGC_LIB', _DEFAULT_LIB_PATH)  # debug builds only; t
 MAX_LEVELS = 12
 MAX_TAPS = 16
 MAX_LAYERS = 8
+MAX_PEERS = 16
 
 MASK_IDENTITY, MASK_DIRECT, MASK_VARIATIONAL, MASK_STE_SIGMOID, MASK_BERNOULLI = range(5)
 F_CLAMP = 1
-ABI_VERSION = 2   # include/lfgc.h LFGC_ABI_VERSION this binding was written against
+ABI_VERSION = 3   # include/lfgc.h LFGC_ABI_VERSION this binding was written against
 
 _ERRORS = {-1: 'LFGC_E_INVALID', -2: 'LFGC_E_UNSUPPORTED', -3: 'LFGC_E_CUDA', -4: 'LFGC_E_WORKSPACE'}
 
@@ -39,6 +40,18 @@ class WaveletDesc(C.Structure):
 
 _f = C.c_void_p      # device pointers travel as integers
 _i64 = C.c_int64
+
+
+class GridStepArgs(C.Structure):
+    """lfgc_grid_step_args (include/lfgc.h)."""
+    _fields_ = [('n_srcs', C.c_int32), ('grad_grid', _f * MAX_PEERS), ('mlp_partials', _f * MAX_PEERS),
+                ('nslices', C.c_int32), ('pstride', C.c_int32), ('pcount', C.c_int32), ('zero_grid', _f),
+                ('grid_cl', _f), ('p', _f), ('g', _f), ('m', _f), ('v', _f), ('coeff_off', _i64 * MAX_LEVELS),
+                ('mlp_off', _i64), ('loss_out', _f), ('lr', _f), ('step_count', _f), ('beta1', C.c_double),
+                ('beta2', C.c_double), ('eps', C.c_double), ('grad_scale', C.c_double), ('weight_l2', C.c_double),
+                ('rank', C.c_int32), ('sync_flags', _f * MAX_PEERS), ('sync_epoch', _f)]
+
+
 _SIGNATURES = {
     'lfgc_abi_version': (C.c_int, []),
     'lfgc_last_error': (C.c_char_p, []),
@@ -73,12 +86,13 @@ _SIGNATURES = {
                                    C.c_int32, _f, C.c_int, _f]),
     'lfgc_deviation_stats': (C.c_int, [_f, _f, _i64, _f, _f]),
     'lfgc_adam': (C.c_int, [_f, _f, _f, _f, _i64, _f, _f, C.c_double, C.c_double, C.c_double, C.c_double, _f]),
-    'lfgc_adam_p2p': (C.c_int, [_f, C.POINTER(_f), C.c_int, _f, _f, _i64, _f, _f, C.c_double, C.c_double, C.c_double,
-                                C.c_double, _f]),
     'lfgc_add_l2_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_add_l1_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
-    'lfgc_step_glue': (C.c_int, [C.POINTER(WaveletDesc), C.c_int, C.POINTER(_f), C.POINTER(_f), _f, _f, _f, _f, _f, _f, _f, _f, _i64, _f, _f,
-                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _f]),
+    'lfgc_train_step_partials': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f,
+                                           C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, C.c_size_t,
+                                           C.POINTER(C.c_int32), _f]),
+    'lfgc_grid_step': (C.c_int, [C.POINTER(WaveletDesc), C.c_int, C.POINTER(GridStepArgs), _f]),
+    'lfgc_grid_step_smem_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
     'lfgc_variational_dkl_grad': (C.c_int, [_f, _f, C.c_int, C.POINTER(C.c_int64), _f, _f, C.c_double, C.c_double,
                                             C.c_float, _f]),
 }

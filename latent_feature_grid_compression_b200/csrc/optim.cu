@@ -44,52 +44,6 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
-// Adam fused with a one-shot all-reduce over peer memory: the gradient of element i is the sum, in rank order (so every
-// rank forms bit-identical parameters), of the W ranks' gradient buffers, read straight over NVLink from symmetric
-// memory (torch.distributed._symmetric_memory provides the mapping and the barriers before / after this launch).
-// For the 0.5 MB gradient of the shipped configurations this replaces an NCCL all-reduce whose cost is all latency.
-struct PeerGrads {
-    const float* g[LFGC_MAX_PEERS];
-    int world;
-};
-
-__global__ void adam_p2p_kernel(float* __restrict__ p, const PeerGrads P, float* __restrict__ m, float* __restrict__ v,
-                                int64_t n, const float* __restrict__ lr_ptr, int32_t* __restrict__ step_ptr,
-                                const AdamCoef c) {
-    LFGC_PDL_PROLOGUE();
-    __shared__ float s_step_size, s_bc2_sqrt;
-    __shared__ int s_step;
-    if (threadIdx.x == 0) {
-        const int step = *reinterpret_cast<volatile int32_t*>(step_ptr) + 1;
-        s_step = step;
-        float step_size, bc2_sqrt;
-        adam_step_scalars(c, step, *lr_ptr, step_size, bc2_sqrt);
-        s_step_size = step_size;
-        s_bc2_sqrt = bc2_sqrt;
-    }
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        float gsum = 0.0f;
-        for (int r = 0; r < P.world; ++r) gsum += __ldcv(P.g[r] + i);   // peer data changes every step: never from L1
-        float pi = p[i], mi = m[i], vi = v[i];
-        adam_update(pi, gsum, mi, vi, c, s_step_size, s_bc2_sqrt);
-        p[i] = pi;
-        m[i] = mi;
-        v[i] = vi;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const int ticket = atomicAdd(step_ptr + 1, 1);
-        if (ticket == (int)gridDim.x - 1) {
-            step_ptr[1] = 0;
-            __threadfence();
-            step_ptr[0] = s_step;
-        }
-    }
-}
-
 __global__ void add_l2_grad_kernel(float* __restrict__ g, const float* __restrict__ p, int64_t n, float w2) {
     LFGC_PDL_PROLOGUE();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,24 +129,6 @@ extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n
     const int64_t blocks = n == 0 ? 1 : (n + 255) / 256;
     (void)launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), st, p, g, m, v, n, lr, step_count,
                      make_adam_coef(beta1, beta2, eps, grad_scale));
-    LFGC_LAUNCH_OK();
-    return LFGC_OK;
-}
-
-extern "C" int lfgc_adam_p2p(float* p, const float* const* peer_g, int world, float* m, float* v, int64_t n,
-                             const float* lr, int32_t* step_count, double beta1, double beta2, double eps,
-                             double grad_scale, void* stream) {
-    if (!p || !peer_g || !m || !v || !lr || !step_count || n < 0) return fail(LFGC_E_INVALID, "adam_p2p: bad arguments");
-    if (world < 1 || world > LFGC_MAX_PEERS) return fail(LFGC_E_UNSUPPORTED, "adam_p2p: world size %d (1..%d)", world, LFGC_MAX_PEERS);
-    PeerGrads P;
-    P.world = world;
-    for (int r = 0; r < LFGC_MAX_PEERS; ++r) {
-        P.g[r] = r < world ? peer_g[r] : nullptr;
-        if (r < world && !P.g[r]) return fail(LFGC_E_INVALID, "adam_p2p: gradient pointer of rank %d is null", r);
-    }
-    const int64_t blocks = n == 0 ? 1 : (n + 255) / 256;
-    (void)launch_pdl(adam_p2p_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, p, P, m, v, n, lr,
-                     step_count, make_adam_coef(beta1, beta2, eps, grad_scale));
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }

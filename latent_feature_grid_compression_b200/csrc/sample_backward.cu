@@ -406,11 +406,6 @@ static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* wo
         // tensor-core kernel first (LFGC_BACKWARD_TC=0 forces the FFMA2 kernels); it covers the MSE / backward-only modes
         const char* e = getenv("LFGC_BACKWARD_TC");
         if (!(e && e[0] == '0') && !A.log_sigma && !(A.P.flags & kFlagPlainRelu)) {
-            const char* iw = getenv("LFGC_TC_ISSUER");   // opt-in: dedicated MMA-issue warp variant
-            if (iw && iw[0] == '1') {
-                const int rc9 = launch_backward_tc9(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
-                if (rc9 != 1) return rc9;
-            }
             const int rc = launch_backward_tc(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
             if (rc != 1) return rc;
         }
@@ -436,8 +431,8 @@ static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* wo
     A.partial = reinterpret_cast<float*>(workspace);
     (void)launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)(smem), st, A);
     LFGC_LAUNCH_OK();
-    launch_reduce_partials(A.partial, (int)grid, A.pstride, A.pcount, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
-    LFGC_LAUNCH_OK();
+    finish_partials(A, (int)grid, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
+    if (!A.defer_reduce) LFGC_LAUNCH_OK();
     return LFGC_OK;
 }
 
@@ -469,6 +464,8 @@ extern "C" int lfgc_backward(const lfgc_model_desc* m, const float* coords, int6
                              float* grad_coords, int accumulate_mlp, void* workspace, size_t workspace_bytes,
                              void* stream) {
     BwdArgs A;
+    A.defer_reduce = 0;
+    A.nslices = 0;
     int rc = fill_sample_params(m, 0, A.P);
     if (rc) return rc;
     rc = common_checks(m, n, grid_cl, mlp, grad_grid_cl, grad_mlp, workspace);
@@ -505,10 +502,16 @@ static int train_step_impl(const lfgc_model_desc* m, const float* volume, const 
                            const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
                            float loss_scale, const float* log_sigma, float* dlog_sigma, const float* grid_cl,
                            const float* mlp, float* grad_grid_cl, float* grad_mlp, float* loss_sum, int accumulate_mlp,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+                           void* workspace, size_t workspace_bytes, void* stream, int32_t* nslices_out = nullptr) {
     BwdArgs A;
+    A.defer_reduce = nslices_out ? 1 : 0;
+    A.nslices = 0;
     int rc = fill_sample_params(m, 0, A.P);
     if (rc) return rc;
+    if (nslices_out) {
+        *nslices_out = 0;
+        grad_mlp = reinterpret_cast<float*>(workspace);   // unused in deferred mode; keeps the common checks uniform
+    }
     rc = common_checks(m, n, grid_cl, mlp, grad_grid_cl, grad_mlp, workspace);
     if (rc) return rc;
     if ((explicit_coords == nullptr) != (explicit_gt == nullptr))
@@ -547,7 +550,9 @@ static int train_step_impl(const lfgc_model_desc* m, const float* volume, const 
     A.grid = grid_cl;
     A.mlp = mlp;
     A.grad_grid = grad_grid_cl;
-    return launch_backward<32, 1>(A, grad_mlp, accumulate_mlp, workspace, workspace_bytes, (cudaStream_t)stream);
+    rc = launch_backward<32, 1>(A, grad_mlp, accumulate_mlp, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (rc == LFGC_OK && nslices_out) *nslices_out = A.nslices;
+    return rc;
 }
 
 extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
@@ -559,6 +564,19 @@ extern "C" int lfgc_train_step(const lfgc_model_desc* m, const float* volume, co
     return train_step_impl(m, volume, R, n, seed, sample_offset, step_dev, step_stride, explicit_idx, explicit_coords,
                            explicit_gt, loss_scale, nullptr, nullptr, grid_cl, mlp, grad_grid_cl, grad_mlp, loss_sum,
                            accumulate_mlp, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lfgc_train_step_partials(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
+                                        uint64_t seed, uint64_t sample_offset, const int32_t* step_dev,
+                                        uint64_t step_stride, const int64_t* explicit_idx, const float* explicit_coords,
+                                        const float* explicit_gt, float loss_scale, const float* grid_cl, const float* mlp,
+                                        float* grad_grid_cl, void* workspace, size_t workspace_bytes,
+                                        int32_t* nslices_out, void* stream) {
+    if (!nslices_out) return fail(LFGC_E_INVALID, "train_step_partials: nslices_out is null");
+    if (n == 0) return fail(LFGC_E_INVALID, "train_step_partials: n must be positive (nothing would be written)");
+    return train_step_impl(m, volume, R, n, seed, sample_offset, step_dev, step_stride, explicit_idx, explicit_coords,
+                           explicit_gt, loss_scale, nullptr, nullptr, grid_cl, mlp, grad_grid_cl, nullptr, nullptr, 0,
+                           workspace, workspace_bytes, stream, nslices_out);
 }
 
 extern "C" int lfgc_train_step_weighted(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
@@ -586,6 +604,8 @@ extern "C" int lfgc_plain_mlp_backward(int H, int L, const float* x, int64_t n, 
                                        float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
                                        void* stream) {
     BwdArgs A;
+    A.defer_reduce = 0;
+    A.nslices = 0;
     int rc = fill_plain_params(H, L, A.P);
     if (rc) return rc;
     if (n < 0 || !mlp || !grad_mlp || !workspace) return fail(LFGC_E_INVALID, "plain_mlp_backward: null pointer or n<0");

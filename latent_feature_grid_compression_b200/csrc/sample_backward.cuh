@@ -27,6 +27,8 @@ struct BwdArgs {
     float* partial;             // [gridDim.x][pcount]
     int pcount;                 // packed MLP parameter count
     int pstride;                // floats per workspace slice: pcount + 1 (the last entry carries the loss partial)
+    int defer_reduce;           // 1: leave the partial sums in the workspace (lfgc_train_step_partials); the reduction
+    int nslices;                //    is folded into lfgc_grid_step, which is told how many slices there are (out)
 };
 
 // Tries the wide kernel (v2: 8-12 warps per CTA, S'(z) in registers, packed FFMA2).  Returns LFGC_OK after
@@ -39,13 +41,13 @@ size_t backward_v2_workspace_floats(int pcount, int sms);
 int launch_backward_tc(BwdArgs& A, int fused, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
                        cudaStream_t st);
 
-// The same with a dedicated MMA-issue warp and the per-thread state trimmed to 168 registers (sample_backward_tc9.cu;
-// opt-in with LFGC_TC_ISSUER=1 until measured).
-int launch_backward_tc9(BwdArgs& A, int fused, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
-                        cudaStream_t st);
-
 // grad[i] (+)= sum_b partial[b][i] for i < pcount; loss_out[0] = sum_b partial[b][pcount] (fixed order: deterministic)
 void launch_reduce_partials(const float* partial, int nslices, int pstride, int pcount, float* grad, int accumulate,
                             float* loss_out, cudaStream_t st);
+// what every launcher calls after its kernel: reduce now, or (A.defer_reduce) only record the slice count
+inline void finish_partials(BwdArgs& A, int nslices, float* grad, int accumulate, float* loss_out, cudaStream_t st) {
+    A.nslices = nslices;
+    if (!A.defer_reduce) launch_reduce_partials(A.partial, nslices, A.pstride, A.pcount, grad, accumulate, loss_out, st);
+}
 
 }  // namespace lfgc

@@ -788,8 +788,8 @@ static int launch_tps(BwdArgs& A, int K0p, float* grad_mlp, int accumulate, void
     A.partial = reinterpret_cast<float*>(workspace);
     (void)launch_pdl(kern, dim3((unsigned)grid), dim3(TILE * TPS), (size_t)(Lo.total), st, A, K0p);
     LFGC_LAUNCH_OK();
-    launch_reduce_partials(A.partial, (int)grid, A.pstride, A.pcount, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
-    LFGC_LAUNCH_OK();
+    finish_partials(A, (int)grid, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
+    if (!A.defer_reduce) LFGC_LAUNCH_OK();
     return LFGC_OK;
 }
 

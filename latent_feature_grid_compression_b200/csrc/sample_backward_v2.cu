@@ -580,9 +580,8 @@ static int launch_nw(BwdArgs& A, float* grad_mlp, int accumulate, void* workspac
     A.partial = reinterpret_cast<float*>(workspace);
     (void)launch_pdl(kern, dim3((unsigned)grid), dim3(32 * NW), (size_t)(smem), st, A);
     LFGC_LAUNCH_OK();
-    launch_reduce_partials(A.partial, (int)grid * KGmax, A.pstride, A.pcount, grad_mlp, accumulate,
-                           FUSED ? A.loss_sum : nullptr, st);
-    LFGC_LAUNCH_OK();
+    finish_partials(A, (int)grid * KGmax, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
+    if (!A.defer_reduce) LFGC_LAUNCH_OK();
     return LFGC_OK;
 }
 

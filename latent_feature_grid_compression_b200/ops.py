@@ -376,27 +376,69 @@ def adam(p, g, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_sc
                           _p(_req(lr_dev, 'lr')), _p(step_dev), beta1, beta2, eps, grad_scale, _stream()), 'lfgc_adam')
 
 
-def adam_p2p(p, peer_grad_ptrs, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
-    """Adam whose gradient is the rank-ordered sum of the ranks' buffers read over NVLink (lfgc_adam_p2p).
-    ``peer_grad_ptrs``: device addresses of every rank's gradient buffer (symmetric memory), this rank's included."""
+def train_step_partials(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl,
+                        mlp_flat, grad_grid_cl, workspace, step_dev=None, step_stride: int = 0, coords=None,
+                        targets=None, explicit_idx=None) -> int:
+    """``train_step`` that leaves the MLP-gradient partial sums (and the loss partials) in ``workspace`` for
+    ``grid_step`` to reduce; returns the number of partial rows (lfgc_train_step_partials)."""
     lib = L.load()
-    _req(step_dev, 'step', torch.int32)
-    L.check(lib.lfgc_adam_p2p(_p(_req(p, 'p')), L.ptr_array([int(a) for a in peer_grad_ptrs]), len(peer_grad_ptrs),
-                              _p(_req(m, 'm')), _p(_req(v, 'v')), p.numel(), _p(_req(lr_dev, 'lr')), _p(step_dev),
-                              beta1, beta2, eps, grad_scale, _stream()), 'lfgc_adam_p2p')
+    if volume is not None:
+        _req(volume, 'volume')
+    if coords is not None:
+        _req(coords, 'coords')
+        _req(targets, 'targets')
+    if explicit_idx is not None:
+        _req(explicit_idx, 'explicit_idx', torch.int64)
+    shape3 = L.int3(volume.shape) if volume is not None else None
+    ns = ct.c_int32(0)
+    L.check(lib.lfgc_train_step_partials(ct.byref(geom.model_desc), _p(volume), shape3, int(n), int(seed),
+                                         int(sample_offset), _p(step_dev), int(step_stride), _p(explicit_idx),
+                                         _p(coords), _p(targets), float(loss_scale), _p(_req(grid_cl, 'grid_cl')),
+                                         _p(_req(mlp_flat, 'mlp')), _p(_req(grad_grid_cl, 'grad_grid_cl')),
+                                         _p(_req(workspace, 'workspace')), workspace.numel() * 4, ct.byref(ns),
+                                         _stream()), 'lfgc_train_step_partials')
+    return int(ns.value)
 
 
-def step_glue(geom: Geometry, coeffs, grad_coeffs, scratch, grad_grid_cl, grid_cl, also_zero, p, g, m, v, lr_dev,
-              step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, phases=7):
-    """Synthesis adjoint (1) + Adam (2) + synthesis of the updated coefficients (4) in one cooperative launch
-    (lfgc_step_glue, mask-free models)."""
+def grid_step_supported(geom: Geometry) -> bool:
+    """True when the per-channel wavelet pyramid of this model fits in shared memory (lfgc_grid_step_smem_bytes)."""
+    return int(L.load().lfgc_grid_step_smem_bytes(ct.byref(geom.wavelet_desc))) > 0
+
+
+def grid_step(geom: Geometry, grad_grids, mlp_partials, nslices: int, pstride: int, pcount: int, grid_cl, p, g, m, v,
+              coeff_offs, mlp_off: int, lr_dev, step_dev, zero_grid=None, loss_out=None, beta1=0.9, beta2=0.999,
+              eps=1e-8, grad_scale=1.0, weight_l2=0.0, sync=None):
+    """Everything of one optimiser step that is not per-sample, one launch (lfgc_grid_step): partial reduction +
+    synthesis adjoint + Adam + synthesis of the updated coefficients.  ``grad_grids`` / ``mlp_partials``: lists (one
+    entry per gradient source: this rank, or every data-parallel rank in rank order) of tensors or raw device
+    addresses.  ``sync = dict(rank=, flags=[address of every rank's flag array], epoch=<int32 device tensor>)`` turns
+    on the in-kernel peer barrier (sources in peer memory)."""
     lib = L.load()
     _req(step_dev, 'step', torch.int32)
-    L.check(lib.lfgc_step_glue(ct.byref(geom.wavelet_desc), geom.Cp, L.ptr_array([_p(c) for c in coeffs]),
-                               L.ptr_array([_p(c) for c in grad_coeffs]), _p(scratch), _p(grad_grid_cl), _p(grid_cl),
-                               _p(also_zero), _p(_req(p, 'p')), _p(_req(g, 'g')), _p(_req(m, 'm')), _p(_req(v, 'v')),
-                               p.numel(), _p(_req(lr_dev, 'lr')), _p(step_dev), beta1, beta2, eps, grad_scale,
-                               int(phases), _stream()), 'lfgc_step_glue')
+    a = L.GridStepArgs()
+    a.n_srcs = len(grad_grids)
+    addr = lambda t: int(t) if isinstance(t, int) else _p(t)
+    for r, (gg, mp) in enumerate(zip(grad_grids, mlp_partials)):
+        a.grad_grid[r] = addr(gg)
+        a.mlp_partials[r] = addr(mp) if mp is not None else None
+    a.nslices, a.pstride, a.pcount = int(nslices), int(pstride), int(pcount)
+    a.zero_grid = _p(zero_grid)
+    a.grid_cl = _p(_req(grid_cl, 'grid_cl'))
+    a.p, a.g, a.m, a.v = _p(_req(p, 'p')), _p(_req(g, 'g')), _p(_req(m, 'm')), _p(_req(v, 'v'))
+    for l, o in enumerate(coeff_offs):
+        a.coeff_off[l] = int(o)
+    a.mlp_off = int(mlp_off)
+    a.loss_out = _p(loss_out)
+    a.lr = _p(_req(lr_dev, 'lr'))
+    a.step_count = _p(step_dev)
+    a.beta1, a.beta2, a.eps, a.grad_scale, a.weight_l2 = float(beta1), float(beta2), float(eps), float(grad_scale), \
+        float(weight_l2)
+    if sync is not None:
+        a.rank = int(sync['rank'])
+        for r, f in enumerate(sync['flags']):
+            a.sync_flags[r] = int(f)
+        a.sync_epoch = _p(_req(sync['epoch'], 'epoch', torch.int32))
+    L.check(lib.lfgc_grid_step(ct.byref(geom.wavelet_desc), geom.Cp, ct.byref(a), _stream()), 'lfgc_grid_step')
 
 
 def add_l2_grad(g, p, weight: float):

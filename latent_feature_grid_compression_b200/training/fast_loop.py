@@ -99,24 +99,6 @@ class FastTrainer:
                     self._slices.append((off, n))
                     off += n
         self.flat_g = torch.zeros_like(self.flat_p)
-        self._symm = None
-        import os
-        mode = os.environ.get('LFGC_ALLREDUCE', 'nccl')
-        if self.world > 1 and mode in ('symm', 'p2p'):
-            # opt-in: the gradient buffer lives in torch symmetric memory (every rank can read the peers' buffers over
-            # NVLink).  'symm': torch's one-shot all-reduce op instead of the NCCL ring / tree, whose latency dominates
-            # this 0.5 MB message.  'p2p': no separate collective at all -- lfgc_adam_p2p sums the peers' buffers inside
-            # the Adam kernel, bracketed by symmetric-memory barriers (mask-free / regulariser-free models).
-            import torch.distributed as dist
-            import torch.distributed._symmetric_memory as symm_mem
-            grp = self.group if self.group is not None else dist.group.WORLD
-            g = symm_mem.empty(total, dtype=torch.float32, device=self.device)
-            g.zero_()
-            hdl = symm_mem.rendezvous(g, grp)
-            self.flat_g = g
-            fused = (mode == 'p2p' and self.var_cfg is None and self.weight_l1 == 0.0 and self.weight_l2 == 0.0)
-            self._symm = dict(name=grp.group_name, out=torch.zeros_like(self.flat_p), hdl=hdl,
-                              peers=[int(a) for a in hdl.buffer_ptrs] if fused else None)
         self.flat_m = torch.zeros_like(self.flat_p)
         self.flat_v = torch.zeros_like(self.flat_p)
         # keep the model's own MLP pack coherent with the shared buffer
@@ -140,7 +122,38 @@ class FastTrainer:
         self.step_dev = torch.zeros(2, device=self.device, dtype=torch.int32)  # [steps taken, Adam ticket scratch]
         self.loss_sum = torch.zeros(1, device=self.device, dtype=torch.float32)
         self.grid_cl = torch.empty((*self.geom.G, self.geom.Cp), device=self.device, dtype=torch.float32)
-        self.grad_grid = torch.zeros_like(self.grid_cl)
+        # [grid gradient, channels-last | MLP gradient | loss]: one buffer, so that the grid-step path of a data-parallel
+        # run all-reduces ONE message (the adjoint is linear: reducing the grid gradient replaces reducing the coefficient
+        # gradients, 0.23 MB instead of 0.45 MB at C16/G15)
+        n_grid = self.grid_cl.numel()
+        self._n_red = (n_grid + self.n_mlp_elems + 1 + 3) // 4 * 4
+        self._p2p = None
+        import os
+        mode = os.environ.get('LFGC_ALLREDUCE', 'p2p')
+        gstep_ok = (os.environ.get('LFGC_GRID_STEP', '1') != '0' and self.var_cfg is None and not self.mask_params
+                    and all(s is None for s in model.mask_specs()) and self.weight_l1 == 0.0
+                    and ops.grid_step_supported(self.geom))
+        if self.world > 1 and mode == 'p2p' and gstep_ok and self.world <= L.MAX_PEERS:
+            # No collective at all: the two parity copies of the buffer live in torch symmetric memory, lfgc_grid_step
+            # reads every rank's copy over NVLink behind its own in-kernel barrier (flags at the end of the allocation).
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self.group if self.group is not None else dist.group.WORLD
+            buf = symm_mem.empty(2 * self._n_red + 64, dtype=torch.float32, device=self.device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, grp)
+            bases = [int(a) for a in hdl.buffer_ptrs]
+            self._red2 = [buf[:self._n_red], buf[self._n_red:2 * self._n_red]]
+            self._p2p = dict(buf=buf, hdl=hdl, rank=int(hdl.rank),
+                             peers=[[b + 4 * self._n_red * par for b in bases] for par in (0, 1)],
+                             flags=[b + 4 * 2 * self._n_red for b in bases],
+                             epoch=torch.zeros(1, device=self.device, dtype=torch.int32))
+            torch.cuda.synchronize()
+            dist.barrier(group=grp)          # every rank's flags are zero before anybody's first launch
+        else:
+            self._red2 = [torch.zeros(self._n_red, device=self.device, dtype=torch.float32)]
+        self._par = 0                        # parity of the next step (only the p2p path has two buffers)
+        self._set_red(0)
         self.scratch = torch.empty(max(self.geom.decode_scratch_bytes // 4, 4), device=self.device)
         self.workspace = torch.empty(self.geom.backward_workspace_bytes // 4, device=self.device)
         self.steps_done = 0
@@ -151,13 +164,15 @@ class FastTrainer:
         self._in_coords = torch.zeros((self.batch, 3), device=self.device, dtype=torch.float32)
         self._in_targets = torch.zeros(self.batch, device=self.device, dtype=torch.float32)
         self._pipe = None   # lazily built state of step_host_pipelined
-        # opt-in (LFGC_GLUE=1): adjoint + Adam + next step's synthesis in one cooperative launch (lfgc_step_glue); only
-        # for mask-free models without regularisers, haar / db2
-        import os
-        self._glue = (os.environ.get('LFGC_GLUE', '0') == '1' and self.var_cfg is None and not self.mask_params
-                      and all(s is None for s in model.mask_specs()) and self.weight_l1 == 0.0 and self.weight_l2 == 0.0
-                      and (len(self.coeff_params) == 1 or model.filter.filter_length in (2, 4)))
-        self._glue_primed = False
+        # mask-free models whose per-channel wavelet pyramid fits in shared memory: the whole non-per-sample part of the
+        # step (partial reduction + adjoint + Adam + next synthesis) is ONE launch, lfgc_grid_step (LFGC_GRID_STEP=0: off)
+        self._gstep = gstep_ok
+        self._gstep_primed = False
+        self._coeff_offs = []
+        off = 0
+        for p in self.coeff_params:
+            self._coeff_offs.append(off)
+            off += p.numel()
         if self.var_cfg is not None:
             cfg = self.var_cfg
             self.var_scale = float(cfg['n_voxels']) / float(self.batch * self.world)   # batch_scale of the reference
@@ -183,33 +198,28 @@ class FastTrainer:
             self._var_sizes = sizes
 
     # ------------------------------------------------------------------------------------------------------------
+    def _set_red(self, par):
+        """Views of the [grid gradient | MLP gradient | loss] staging buffer the step with parity ``par`` uses."""
+        n_grid = self.grid_cl.numel()
+        self.red = self._red2[par % len(self._red2)]
+        self.grad_grid = self.red[:n_grid].view_as(self.grid_cl)
+        self.red_mlp = self.red[n_grid:n_grid + self.n_mlp_elems + 1]
+
     def grad_of(self, p):
         return self._grad_view[id(p)]
 
     def _allreduce_grads(self):
-        """Sum the flat gradient over the ranks; returns the tensor that holds the result."""
-        if self._symm is None:
-            torch.distributed.all_reduce(self.flat_g, group=self.group)
-            return self.flat_g
-        torch.ops.symm_mem.one_shot_all_reduce_out(self.flat_g, 'sum', self._symm['name'], self._symm['out'])
-        return self._symm['out']
-
-    def _adam_p2p(self):
-        """Adam with the all-reduce folded in (lfgc_adam_p2p): barrier (all ranks' gradients are complete), peer reads +
-        update, barrier (nobody overwrites its gradient buffer before everyone has read it)."""
-        hdl = self._symm['hdl']
-        hdl.barrier(channel=0)
-        ops.adam_p2p(self.flat_p, self._symm['peers'], self.flat_m, self.flat_v, self.lr_dev, self.step_dev,
-                     self.betas[0], self.betas[1], self.eps)
-        hdl.barrier(channel=1)
+        """Sum the flat gradient over the ranks (NCCL); returns the tensor that holds the result."""
+        torch.distributed.all_reduce(self.flat_g, group=self.group)
+        return self.flat_g
 
     def _step_body(self, host_fed=False):
         model, geom = self.model, self.geom
         in_coords, in_targets = self._in_coords, self._in_targets
         if isinstance(host_fed, tuple):   # ('pipe', b): the pipelined host-fed step reads staging buffer pair b
             in_coords, in_targets = self._pipe['coords'][host_fed[1]], self._pipe['targets'][host_fed[1]]
-        if self._glue:
-            return self._step_body_glue(host_fed, in_coords, in_targets)
+        if self._gstep:
+            return self._step_body_gstep(host_fed, in_coords, in_targets)
         specs = model.mask_specs()
         mults, auxs = _multipliers(specs)
         coeffs = [p.data for p in self.coeff_params]
@@ -252,8 +262,6 @@ class FastTrainer:
             self.grad_of(spec.grad_params[0]).copy_(g0)
             if len(spec.grad_params) == 2:
                 self.grad_of(spec.grad_params[1]).copy_(g1)
-        if self.world > 1 and self._symm is not None and self._symm['peers'] is not None:
-            return self._adam_p2p()
         g_red = self._allreduce_grads() if self.world > 1 else self.flat_g
         if self.var_cfg is not None:
             # sample-independent terms of VariationalDropoutLoss, added once after the reduction: KL of the live masks
@@ -277,35 +285,50 @@ class FastTrainer:
         ops.adam(self.flat_p, g_red, self.flat_m, self.flat_v, self.lr_dev, self.step_dev, self.betas[0],
                  self.betas[1], self.eps)
 
-    def _prime_glue(self):
-        """The glue step expects the grid of the CURRENT coefficients (and a cleared gradient accumulator) on entry:
-        every step leaves them behind for the next one, this provides them for the first."""
+    def _prime_gstep(self):
+        """The grid-step path expects the grid of the CURRENT coefficients (and a cleared gradient accumulator) on
+        entry: every step leaves them behind for the next one, this provides them for the first."""
         coeffs = [p.data for p in self.coeff_params]
-        ops.decode_fwd(self.geom, coeffs, [None] * len(coeffs), scratch=self.scratch, out=self.grid_cl,
-                       also_zero=self.grad_grid)
-        self._glue_primed = True
+        ops.decode_fwd(self.geom, coeffs, [None] * len(coeffs), scratch=self.scratch, out=self.grid_cl)
+        for r in self._red2:
+            r.zero_()
+        self._gstep_primed = True
 
-    def _step_body_glue(self, host_fed, in_coords, in_targets):
+    def _step_body_gstep(self, host_fed, in_coords, in_targets):
+        """Two launches per optimiser step: the fused per-sample kernel (partial sums left in the workspace) and
+        lfgc_grid_step.  Data parallel (NCCL): the partial reduction stays a launch of its own, [grid gradient | MLP
+        gradient] is all-reduced as one message, then lfgc_grid_step."""
         geom = self.geom
         n_global = self.batch * self.world
-        ops.train_step(geom, self.volume, self.batch, self.seed,
-                       parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
-                       parallel.loss_scale(self.batch, self.world), self.grid_cl,
-                       self.mlp_flat, self.grad_grid, self.flat_g[self.mlp_off:], self.loss_sum, self.workspace,
-                       step_dev=self.step_dev, step_stride=n_global,
-                       coords=in_coords if host_fed else None, targets=in_targets if host_fed else None)
-        coeffs = [p.data for p in self.coeff_params]
-        gcoeffs = [self.grad_of(p) for p in self.coeff_params]
-
-        def glue(phases, g=None):
-            ops.step_glue(geom, coeffs, gcoeffs, self.scratch, self.grad_grid, self.grid_cl, self.grad_grid, self.flat_p,
-                          self.flat_g if g is None else g, self.flat_m, self.flat_v, self.lr_dev, self.step_dev,
-                          self.betas[0], self.betas[1], self.eps, phases=phases)
-        if self.world > 1:
-            glue(1)
-            glue(6, self._allreduce_grads())
-        else:
-            glue(7)
+        pcount = self.n_mlp_elems
+        kw = dict(step_dev=self.step_dev, step_stride=n_global, coords=in_coords if host_fed else None,
+                  targets=in_targets if host_fed else None)
+        offset = parallel.sample_stream_offset(0, self.rank, self.batch, self.world)
+        scale = parallel.loss_scale(self.batch, self.world)
+        common = dict(grid_cl=self.grid_cl, p=self.flat_p, g=self.flat_g, m=self.flat_m, v=self.flat_v,
+                      coeff_offs=self._coeff_offs, mlp_off=self.mlp_off, lr_dev=self.lr_dev, step_dev=self.step_dev,
+                      zero_grid=self.grad_grid, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                      weight_l2=self.weight_l2)
+        if self.world == 1:
+            ns = ops.train_step_partials(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl,
+                                         self.mlp_flat, self.grad_grid, self.workspace, **kw)
+            ops.grid_step(geom, [self.grad_grid], [self.workspace], ns, pcount + 1, pcount, loss_out=self.loss_sum,
+                          **common)
+            return
+        ops.train_step(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl, self.mlp_flat,
+                       self.grad_grid, self.red_mlp[:pcount], self.loss_sum, self.workspace, **kw)
+        if self._p2p is None:
+            torch.distributed.all_reduce(self.red, group=self.group)
+            ops.grid_step(geom, [self.grad_grid], [self.red_mlp], 1, pcount + 1, pcount, **common)
+            return
+        # peer reads inside lfgc_grid_step: this step's buffers of all ranks are the sources; the accumulator cleared is
+        # the OTHER parity's (its last readers finished before they announced this epoch)
+        P = self._p2p
+        par = self._par
+        n_grid = self.grid_cl.numel()
+        common['zero_grid'] = self._red2[par ^ 1][:n_grid]
+        ops.grid_step(geom, P['peers'][par], [a + 4 * n_grid for a in P['peers'][par]], 1, pcount + 1, pcount,
+                      sync=dict(rank=P['rank'], flags=P['flags'], epoch=P['epoch']), **common)
 
     def capture(self, host_fed=False):
         """Warm up eagerly (counts launches), then record the step into a CUDA graph; the optimiser state the
@@ -314,23 +337,31 @@ class FastTrainer:
         trackers = [(d.tracker.EMA.clone(), d.tracker.EMAVar.clone()) for d in self.model.drop
                     if isinstance(d, SmallifyDropout)]
         w_dkl = self.w_dkl.clone() if self.var_cfg is not None else None
-        if self._glue and not self._glue_primed:
-            self._prime_glue()
+        if self._gstep and not self._gstep_primed:
+            self._prime_gstep()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(2):
+            for _ in range(2):      # an even number of steps: the buffer parity is back where it started
                 before = ops.launch_count()
+                self._set_red(self._par)
                 self._step_body(host_fed)
+                self._advance_par()
                 self.launches_per_step = ops.launch_count() - before
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        graph = None
-        if self._use_graph:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._step_body(host_fed)
-        self._graphs[host_fed] = graph
+        keep = self._par
+        for par in ((0, 1) if self._p2p is not None else (0,)):
+            graph = None
+            if self._use_graph:
+                self._par = par
+                self._set_red(par)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._step_body(host_fed)
+            self._graphs[(host_fed, par)] = graph
+        self._par = keep
+        self._set_red(keep)
         with torch.no_grad():
             self.flat_p.copy_(state[0])
             self.flat_m.copy_(state[1])
@@ -344,18 +375,26 @@ class FastTrainer:
                     ema, var = next(it)
                     d.tracker.EMA.copy_(ema)
                     d.tracker.EMAVar.copy_(var)
-        if self._glue:
-            self._prime_glue()   # the warm-up steps moved the coefficients: decode the restored ones
+        if self._gstep:
+            self._prime_gstep()   # the warm-up steps moved the coefficients: decode the restored ones
         torch.cuda.synchronize()
+        if self._p2p is not None:
+            torch.distributed.barrier(group=self.group)   # nobody starts real steps while a peer still warms up
+
+    def _advance_par(self):
+        if self._p2p is not None:
+            self._par ^= 1
 
     def _run(self, host_fed):
-        if host_fed not in self._graphs:
+        if (host_fed, 0) not in self._graphs:
             self.capture(host_fed)
-        g = self._graphs[host_fed]
+        self._set_red(self._par)
+        g = self._graphs[(host_fed, self._par)]
         if g is not None:
             g.replay()
         else:
             self._step_body(host_fed)
+        self._advance_par()
         self.steps_done += 1
 
     def step(self):
