@@ -70,128 +70,177 @@ struct Bufs {
     float* X;    // x-pass intermediate: [4 (a,b)][d0][d1][t2]
     float* Y;    // y-pass intermediate: [2 (a)][d0][t1][t2]
     float* Cg;   // detail bands of every level: gradient after the adjoint, updated value after Adam
+    const float* lo;   // reconstruction taps (shared-memory copies in the kernel: the tap index differs between the
+    const float* hi;   // lanes of a warp, which would serialise constant-bank reads)
 };
+
+// Every pass is organised by COLUMNS: a work unit is one 1-D line of the pass (fixed position in the two untouched
+// dimensions) times a range [o0, o1) of output positions along the filtered dimension.  The index decomposition happens
+// once per unit, the inner loops are division-free and the filter-tap selection is uniform over a warp.  (A first version
+// decomposed a flat index per OUTPUT ELEMENT: six integer divisions per element made the kernel 44 us, slower than the
+// six launches it replaces.)
 
 // ---- synthesis level l, separable: x pass -> y pass -> z pass ----------------------------------------------------------
 // band k = 4a + 2b + c, (a, b, c) = filter along (dim0, dim1, dim2), 0 = low / 1 = high; k = 0 is the running low-pass
 // (Torch_Wavelet_Transform.py:39-57,91-104).  out[o] = sum_i in[i] * f[o + off - 2 i].
-__host__ __device__ __forceinline__ void synth_x(const Args& A, const Bufs& S, int l, int idx) {
+// x pass: column = (ab, iz, iy), 4 d0 d1 of them; outputs ox in [o0, o1) of t2
+__host__ __device__ __forceinline__ void synth_x(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
     const int d0 = A.d[l][0], d1 = A.d[l][1], d2 = A.d[l][2], t2 = A.t[l][2];
     const int dvol = d0 * d1 * d2;
-    const int ox = idx % t2;
-    int r = idx / t2;
-    const int iy = r % d1;
-    r /= d1;
-    const int iz = r % d0;
-    const int ab = r / d0;
-    const int o = ox + A.off[l][2];
-    const float* b0 = ab == 0 ? S.L : S.Cg + A.cg_off[l] + (2 * ab - 1) * dvol;   // band (a, b, 0)
-    const float* b1 = S.Cg + A.cg_off[l] + (2 * ab) * dvol;                        // band (a, b, 1)
-    const int row = (iz * d1 + iy) * d2;
-    float acc = 0.0f;
-    for (int a = 0; 2 * a < A.ntaps; ++a) {
-        const int i = (o >> 1) - a;
-        const int tt = (o & 1) + 2 * a;
-        if (i >= 0 && i < d2) {
-            acc = fmaf(b0[row + i], A.lo[tt], acc);
-            acc = fmaf(b1[row + i], A.hi[tt], acc);
+    const int ab = col / (d0 * d1);
+    const int zy = col - ab * d0 * d1;   // iz * d1 + iy
+    const float* b0 = (ab == 0 ? S.L : S.Cg + A.cg_off[l] + (2 * ab - 1) * dvol) + zy * d2;   // band (a, b, 0)
+    const float* b1 = S.Cg + A.cg_off[l] + (2 * ab) * dvol + zy * d2;                         // band (a, b, 1)
+    float* out = S.X + col * t2;
+    for (int ox = o0; ox < o1; ++ox) {
+        const int o = ox + A.off[l][2];
+        float acc = 0.0f;
+        for (int a = 0; 2 * a < A.ntaps; ++a) {
+            const int i = (o >> 1) - a;
+            const int tt = (o & 1) + 2 * a;
+            if (i >= 0 && i < d2) {
+                acc = fmaf(b0[i], S.lo[tt], acc);
+                acc = fmaf(b1[i], S.hi[tt], acc);
+            }
         }
+        out[ox] = acc;
     }
-    S.X[idx] = acc;
 }
-__host__ __device__ __forceinline__ void synth_y(const Args& A, const Bufs& S, int l, int idx) {
+// y pass: column = (a, iz, ox), 2 d0 t2 of them; outputs oy in [o0, o1) of t1
+__host__ __device__ __forceinline__ void synth_y(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
     const int d0 = A.d[l][0], d1 = A.d[l][1], t1 = A.t[l][1], t2 = A.t[l][2];
-    const int ox = idx % t2;
-    int r = idx / t2;
-    const int oy = r % t1;
-    r /= t1;
-    const int iz = r % d0;
-    const int a_ = r / d0;
-    const int o = oy + A.off[l][1];
+    const int az = col / t2;             // a * d0 + iz
+    const int ox = col - az * t2;
+    const int a_ = az / d0;
+    const int iz = az - a_ * d0;
     const int plane = d0 * d1 * t2;
     const float* x0 = S.X + (2 * a_) * plane + iz * d1 * t2 + ox;       // (a, b = 0)
     const float* x1 = x0 + plane;                                        // (a, b = 1)
-    float acc = 0.0f;
-    for (int a = 0; 2 * a < A.ntaps; ++a) {
-        const int i = (o >> 1) - a;
-        const int tt = (o & 1) + 2 * a;
-        if (i >= 0 && i < d1) {
-            acc = fmaf(x0[i * t2], A.lo[tt], acc);
-            acc = fmaf(x1[i * t2], A.hi[tt], acc);
+    float* out = S.Y + az * t1 * t2 + ox;
+    for (int oy = o0; oy < o1; ++oy) {
+        const int o = oy + A.off[l][1];
+        float acc = 0.0f;
+        for (int a = 0; 2 * a < A.ntaps; ++a) {
+            const int i = (o >> 1) - a;
+            const int tt = (o & 1) + 2 * a;
+            if (i >= 0 && i < d1) {
+                acc = fmaf(x0[i * t2], S.lo[tt], acc);
+                acc = fmaf(x1[i * t2], S.hi[tt], acc);
+            }
         }
+        out[oy * t2] = acc;
     }
-    S.Y[idx] = acc;
 }
-__host__ __device__ __forceinline__ void synth_z(const Args& A, const Bufs& S, int l, int idx) {
+// z pass: column = (oy, ox), t1 t2 of them; outputs oz in [o0, o1) of t0
+__host__ __device__ __forceinline__ void synth_z(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
     const int d0 = A.d[l][0], t1 = A.t[l][1], t2 = A.t[l][2];
-    const int rest = idx % (t1 * t2);
-    const int oz = idx / (t1 * t2);
-    const int o = oz + A.off[l][0];
-    const int plane = d0 * t1 * t2;
-    const float* y0 = S.Y + rest;
-    const float* y1 = y0 + plane;
-    float acc = 0.0f;
-    for (int a = 0; 2 * a < A.ntaps; ++a) {
-        const int i = (o >> 1) - a;
-        const int tt = (o & 1) + 2 * a;
-        if (i >= 0 && i < d0) {
-            acc = fmaf(y0[i * t1 * t2], A.lo[tt], acc);
-            acc = fmaf(y1[i * t1 * t2], A.hi[tt], acc);
+    const int pl = t1 * t2;
+    const float* y0 = S.Y + col;
+    const float* y1 = y0 + d0 * pl;
+    for (int oz = o0; oz < o1; ++oz) {
+        const int o = oz + A.off[l][0];
+        float acc = 0.0f;
+        for (int a = 0; 2 * a < A.ntaps; ++a) {
+            const int i = (o >> 1) - a;
+            const int tt = (o & 1) + 2 * a;
+            if (i >= 0 && i < d0) {
+                acc = fmaf(y0[i * pl], S.lo[tt], acc);
+                acc = fmaf(y1[i * pl], S.hi[tt], acc);
+            }
         }
+        S.L[oz * pl + col] = acc;
     }
-    S.L[idx] = acc;
 }
 
 // ---- adjoint of synthesis level l, separable: z^T pass -> y^T pass -> x^T pass ------------------------------------------
 // g_in[i] = sum_tt g_out[2 i + tt - off] * f[tt]
-__host__ __device__ __forceinline__ void adj_z(const Args& A, const Bufs& S, int l, int idx) {
+// z^T pass: column = (oy, ox), t1 t2 of them; outputs (a, iz) = o in [o0, o1) of 2 d0
+__host__ __device__ __forceinline__ void adj_z(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
     const int d0 = A.d[l][0], t0 = A.t[l][0], t1 = A.t[l][1], t2 = A.t[l][2];
-    const int rest = idx % (t1 * t2);
-    int r = idx / (t1 * t2);
-    const int iz = r % d0;
-    const int a_ = r / d0;
-    const float* f = a_ ? A.hi : A.lo;
-    float acc = 0.0f;
-    for (int tt = 0; tt < A.ntaps; ++tt) {
-        const int q = 2 * iz + tt - A.off[l][0];
-        if (q >= 0 && q < t0) acc = fmaf(S.L[q * t1 * t2 + rest], f[tt], acc);
+    const int pl = t1 * t2;
+    for (int o = o0; o < o1; ++o) {
+        const int a_ = o >= d0;
+        const int iz = o - a_ * d0;
+        const float* f = a_ ? S.hi : S.lo;
+        float acc = 0.0f;
+        for (int tt = 0; tt < A.ntaps; ++tt) {
+            const int q = 2 * iz + tt - A.off[l][0];
+            if (q >= 0 && q < t0) acc = fmaf(S.L[q * pl + col], f[tt], acc);
+        }
+        S.Y[o * pl + col] = acc;
     }
-    S.Y[idx] = acc;
 }
-__host__ __device__ __forceinline__ void adj_y(const Args& A, const Bufs& S, int l, int idx) {
+// y^T pass: column = (a, iz, ox), 2 d0 t2 of them; outputs (b, iy) = o in [o0, o1) of 2 d1
+__host__ __device__ __forceinline__ void adj_y(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
     const int d0 = A.d[l][0], d1 = A.d[l][1], t1 = A.t[l][1], t2 = A.t[l][2];
-    const int ox = idx % t2;
-    int r = idx / t2;
-    const int iy = r % d1;
-    r /= d1;
-    const int iz = r % d0;
-    const int ab = r / d0;
-    const float* f = (ab & 1) ? A.hi : A.lo;
-    const float* y = S.Y + ((ab >> 1) * d0 + iz) * t1 * t2 + ox;
-    float acc = 0.0f;
-    for (int tt = 0; tt < A.ntaps; ++tt) {
-        const int q = 2 * iy + tt - A.off[l][1];
-        if (q >= 0 && q < t1) acc = fmaf(y[q * t2], f[tt], acc);
+    const int az = col / t2;             // a * d0 + iz
+    const int ox = col - az * t2;
+    const int a_ = az / d0;
+    const int iz = az - a_ * d0;
+    const float* y = S.Y + az * t1 * t2 + ox;
+    for (int o = o0; o < o1; ++o) {
+        const int b_ = o >= d1;
+        const int iy = o - b_ * d1;
+        const float* f = b_ ? S.hi : S.lo;
+        float acc = 0.0f;
+        for (int tt = 0; tt < A.ntaps; ++tt) {
+            const int q = 2 * iy + tt - A.off[l][1];
+            if (q >= 0 && q < t1) acc = fmaf(y[q * t2], f[tt], acc);
+        }
+        S.X[(((2 * a_ + b_) * d0 + iz) * d1 + iy) * t2 + ox] = acc;
     }
-    S.X[idx] = acc;
 }
-__host__ __device__ __forceinline__ void adj_x(const Args& A, const Bufs& S, int l, int idx) {
+// x^T pass: column = (ab, iz, iy), 4 d0 d1 of them; outputs (c, ix) = o in [o0, o1) of 2 d2
+__host__ __device__ __forceinline__ void adj_x(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
     const int d0 = A.d[l][0], d1 = A.d[l][1], d2 = A.d[l][2], t2 = A.t[l][2];
     const int dvol = d0 * d1 * d2;
-    const int k = idx / dvol;
-    const int pos = idx - k * dvol;
-    const int ix = pos % d2;
-    const int zy = pos / d2;   // iz * d1 + iy
-    const float* f = (k & 1) ? A.hi : A.lo;
-    const float* x = S.X + ((k >> 1) * d0 * d1 + zy) * t2;
-    float acc = 0.0f;
-    for (int tt = 0; tt < A.ntaps; ++tt) {
-        const int q = 2 * ix + tt - A.off[l][2];
-        if (q >= 0 && q < t2) acc = fmaf(x[q], f[tt], acc);
+    const int ab = col / (d0 * d1);
+    const int zy = col - ab * d0 * d1;
+    const float* x = S.X + col * t2;
+    for (int o = o0; o < o1; ++o) {
+        const int c_ = o >= d2;
+        const int ix = o - c_ * d2;
+        const float* f = c_ ? S.hi : S.lo;
+        float acc = 0.0f;
+        for (int tt = 0; tt < A.ntaps; ++tt) {
+            const int q = 2 * ix + tt - A.off[l][2];
+            if (q >= 0 && q < t2) acc = fmaf(x[q], f[tt], acc);
+        }
+        const int k = 2 * ab + c_;
+        const int pos = zy * d2 + ix;
+        if (k == 0) S.L[pos] = acc;                                   // gradient of the low-pass input of this level
+        else S.Cg[A.cg_off[l] + (k - 1) * dvol + pos] = acc;          // gradient of detail band k
     }
-    if (k == 0) S.L[pos] = acc;                                   // gradient of the low-pass input of this level
-    else S.Cg[A.cg_off[l] + (k - 1) * dvol + pos] = acc;          // gradient of detail band k
 }
+
+// Work distribution of one pass over `nthreads` workers: ncols columns x n_out outputs; when there are fewer columns
+// than workers the output range is cut into groups so that (almost) every worker has something to do.
+struct PassPlan {
+    int ncols, n_out, groups, per;
+};
+__host__ __device__ __forceinline__ PassPlan plan_pass(int ncols, int n_out, int nthreads) {
+    PassPlan p;
+    p.ncols = ncols;
+    p.n_out = n_out;
+    int g = ncols > 0 ? nthreads / ncols : 1;
+    if (g < 1) g = 1;
+    if (g > n_out) g = n_out;
+    p.groups = g;
+    p.per = (n_out + g - 1) / g;
+    return p;
+}
+#define LFGC_PASS(fn, ncols_, nout_)                                                           \
+    {                                                                                          \
+        const PassPlan pp = plan_pass((ncols_), (nout_), kThreads);                            \
+        for (int u = tid; u < pp.ncols * pp.groups; u += kThreads) {                           \
+            const int grp = u / pp.ncols;                                                      \
+            const int col = u - grp * pp.ncols;                                                \
+            const int b0_ = grp * pp.per;                                                      \
+            const int b1_ = b0_ + pp.per < pp.n_out ? b0_ + pp.per : pp.n_out;                 \
+            fn(A, S, l, col, b0_, b1_);                                                        \
+        }                                                                                      \
+        __syncthreads();                                                                       \
+    }
 
 // Adam on element e of coefficient tensor l of channel c; the gradient sits in shared memory and is replaced there by
 // the updated coefficient (what the synthesis below reads)
@@ -244,8 +293,13 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_step_size, s_bc2_sqrt;
     __shared__ int s_step;
+    __shared__ float s_lo[LFGC_MAX_TAPS], s_hi[LFGC_MAX_TAPS];
     const int tid = threadIdx.x;
     if (A.sync_epoch) peer_barrier(A, tid);
+    if (tid < LFGC_MAX_TAPS) {
+        s_lo[tid] = A.lo[tid];
+        s_hi[tid] = A.hi[tid];
+    }
     if (tid == 0) {
         const int step = *reinterpret_cast<volatile int*>(A.step) + 1;
         float step_size, bc2_sqrt;
@@ -261,6 +315,8 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
         S.X = S.L + A.sL;
         S.Y = S.X + A.sX;
         S.Cg = S.Y + A.sY;
+        S.lo = s_lo;
+        S.hi = s_hi;
         const int last = A.n_coeff - 1;
         // ---- this channel's slice of the grid gradient (summed over the ranks in rank order), accumulator cleared ----------
         const int* G = last >= 1 ? A.t[last] : A.d[0];
@@ -280,29 +336,49 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
         // ---- adjoint, finest -> coarsest --------------------------------------------------------------------------------------
         for (int l = last; l >= 1; --l) {
             const int d0 = A.d[l][0], d1 = A.d[l][1], d2 = A.d[l][2], t1 = A.t[l][1], t2 = A.t[l][2];
-            for (int i = tid; i < 2 * d0 * t1 * t2; i += kThreads) adj_z(A, S, l, i);
-            __syncthreads();
-            for (int i = tid; i < 4 * d0 * d1 * t2; i += kThreads) adj_y(A, S, l, i);
-            __syncthreads();
-            for (int i = tid; i < 8 * d0 * d1 * d2; i += kThreads) adj_x(A, S, l, i);
-            __syncthreads();
+            LFGC_PASS(adj_z, t1 * t2, 2 * d0)
+            LFGC_PASS(adj_y, 2 * d0 * t2, 2 * d1)
+            LFGC_PASS(adj_x, 4 * d0 * d1, 2 * d2)
         }
         // ---- Adam on this channel's coefficients ---------------------------------------------------------------------------------
         const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
         for (int l = 0; l <= last; ++l) {
             const int n_l = coeff_elems(A, l);
-            for (int e = tid; e < n_l; e += kThreads) adam_coeff(A, S, l, c, e, n_l, step_size, bc2_sqrt);
+            float* slots = l == 0 ? S.L : S.Cg + A.cg_off[l];
+            const long long base = A.coeff_off[l] + (long long)c * n_l;
+            for (int e0 = 0; e0 < n_l; e0 += 4 * kThreads) {       // four elements per thread: 12 loads in flight
+                float pi[4], mi[4], vi[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int e = e0 + k * kThreads + tid;
+                    if (e < n_l) {
+                        pi[k] = A.p[base + e];
+                        mi[k] = A.m[base + e];
+                        vi[k] = A.v[base + e];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int e = e0 + k * kThreads + tid;
+                    if (e < n_l) {
+                        const float gi = fmaf(A.w2x2, pi[k], slots[e]);
+                        adam_update(pi[k], gi, mi[k], vi[k], A.c, step_size, bc2_sqrt);
+                        A.p[base + e] = pi[k];
+                        A.m[base + e] = mi[k];
+                        A.v[base + e] = vi[k];
+                        A.g[base + e] = gi;
+                        slots[e] = pi[k];
+                    }
+                }
+            }
         }
         __syncthreads();
         // ---- synthesis of the updated coefficients, coarsest -> finest ------------------------------------------------------------
         for (int l = 1; l <= last; ++l) {
             const int d0 = A.d[l][0], d1 = A.d[l][1], t0 = A.t[l][0], t1 = A.t[l][1], t2 = A.t[l][2];
-            for (int i = tid; i < 4 * d0 * d1 * t2; i += kThreads) synth_x(A, S, l, i);
-            __syncthreads();
-            for (int i = tid; i < 2 * d0 * t1 * t2; i += kThreads) synth_y(A, S, l, i);
-            __syncthreads();
-            for (int i = tid; i < t0 * t1 * t2; i += kThreads) synth_z(A, S, l, i);
-            __syncthreads();
+            LFGC_PASS(synth_x, 4 * d0 * d1, t2)
+            LFGC_PASS(synth_y, 2 * d0 * t2, t1)
+            LFGC_PASS(synth_z, t1 * t2, t0)
         }
         for (int i = tid; i < nvox; i += kThreads) A.grid_cl[(long long)i * A.Cp + c] = S.L[i];
         if (c == A.C - 1) {
@@ -310,25 +386,30 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
                 A.grid_cl[(long long)(i / (A.Cp - A.C)) * A.Cp + A.C + i % (A.Cp - A.C)] = 0.0f;
         }
     } else {
-        // ---- MLP block: fixed-order reduction of the partial sums (deterministic), then Adam ---------------------------------------
-        __syncthreads();
-        const int j = (c - A.C) * kThreads + tid;
+        // ---- MLP block: fixed-order reduction of the partial sums (deterministic), then Adam.  64 parameters x 16 slice
+        // groups per CTA: every thread has all its loads in flight at once, the 16 partial sums meet in shared memory -----
+        constexpr int PX = 64, SY = kThreads / PX;
+        const int px = tid % PX, sy = tid / PX;
+        const int j = (c - A.C) * PX + px;
+        float acc = 0.0f;
         if (j <= A.pcount) {
-            const int ns = A.nslices;
-            float t = 0.0f;
             for (int r = 0; r < A.n_srcs; ++r) {
                 const float* src = A.mlp_partials[r] + j;
-                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;   // four independent chains, fixed association
-                int b = 0;
-                for (; b + 4 <= ns; b += 4) {
-                    a0 += __ldcv(src + (size_t)(b + 0) * A.pstride);
-                    a1 += __ldcv(src + (size_t)(b + 1) * A.pstride);
-                    a2 += __ldcv(src + (size_t)(b + 2) * A.pstride);
-                    a3 += __ldcv(src + (size_t)(b + 3) * A.pstride);
+                for (int b = sy; b < A.nslices; b += 4 * SY) {
+                    float t0 = __ldcv(src + (size_t)b * A.pstride), t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+                    if (b + SY < A.nslices) t1 = __ldcv(src + (size_t)(b + SY) * A.pstride);
+                    if (b + 2 * SY < A.nslices) t2 = __ldcv(src + (size_t)(b + 2 * SY) * A.pstride);
+                    if (b + 3 * SY < A.nslices) t3 = __ldcv(src + (size_t)(b + 3 * SY) * A.pstride);
+                    acc += (t0 + t1) + (t2 + t3);
                 }
-                for (; b < ns; ++b) a0 += __ldcv(src + (size_t)b * A.pstride);
-                t += (a0 + a1) + (a2 + a3);
             }
+        }
+        smem[sy * PX + px] = acc;
+        __syncthreads();
+        if (sy == 0 && j <= A.pcount) {
+            float t = 0.0f;
+#pragma unroll
+            for (int g = 0; g < SY; ++g) t += smem[g * PX + px];
             if (j < A.pcount) {
                 const long long i = A.mlp_off + j;
                 float pi = A.p[i], mi = A.m[i], vi = A.v[i];
@@ -412,7 +493,8 @@ static int gstep_check_desc(const lfgc_wavelet_desc* w) {
 extern "C" size_t lfgc_grid_step_smem_bytes(const lfgc_wavelet_desc* w) {
     if (gstep_check_desc(w)) return 0;
     gstep::Args A;
-    const size_t bytes = gstep_layout(A, w) * sizeof(float);
+    size_t bytes = gstep_layout(A, w) * sizeof(float);
+    if (bytes < 4096) bytes = 4096;   // the MLP CTAs stage 64 x 16 partial sums in the same allocation
     int cap = max_smem_optin();
     if (cap <= 0) cap = 232448;   // no device visible (build container): B200 opt-in limit
     return bytes <= (size_t)cap - 64 ? bytes : 0;
@@ -454,7 +536,7 @@ static int gstep_fill(gstep::Args& A, const lfgc_wavelet_desc* w, int Cp, const 
     A.step = a->step_count;
     A.c = make_adam_coef(a->beta1, a->beta2, a->eps, a->grad_scale);
     A.w2x2 = (float)(2.0 * a->weight_l2);
-    A.n_mlp_ctas = a->pcount > 0 ? (a->pcount + 1 + gstep::kThreads - 1) / gstep::kThreads : 0;
+    A.n_mlp_ctas = a->pcount > 0 ? (a->pcount + 1 + 63) / 64 : 0;   // 64 parameters per CTA (see the kernel)
     A.rank = a->rank;
     A.sync_epoch = a->sync_epoch;
     for (int r = 0; r < LFGC_MAX_PEERS; ++r) {
@@ -482,6 +564,16 @@ extern "C" int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_gri
 // Test hook (only in builds made by tests/test_grid_step_host.py, never in liblfgc.so): the SAME per-element functions in
 // the same phase order, run sequentially on HOST memory, so the separable index arithmetic can be checked against the
 // numpy oracle without a GPU.  All pointers are host pointers here.
+#define HOST_PASS(fn, ncols_, nout_)                                                           \
+    {                                                                                          \
+        const PassPlan pp = plan_pass((ncols_), (nout_), kThreads);                            \
+        for (int u = 0; u < pp.ncols * pp.groups; ++u) {                                       \
+            const int grp = u / pp.ncols, col = u - grp * pp.ncols;                            \
+            const int b0_ = grp * pp.per;                                                      \
+            const int b1_ = b0_ + pp.per < pp.n_out ? b0_ + pp.per : pp.n_out;                 \
+            fn(A, S, l, col, b0_, b1_);                                                        \
+        }                                                                                      \
+    }
 extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a) {
     using namespace gstep;
     Args A;
@@ -494,6 +586,8 @@ extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfg
     S.X = S.L + A.sL;
     S.Y = S.X + A.sX;
     S.Cg = S.Y + A.sY;
+    S.lo = A.lo;
+    S.hi = A.hi;
     const int step = A.step[0] + 1;
     float step_size, bc2_sqrt;
     adam_step_scalars(A.c, step, *A.lr, step_size, bc2_sqrt);
@@ -508,9 +602,10 @@ extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfg
         }
         for (int l = last; l >= 1; --l) {
             const int d0 = A.d[l][0], d1 = A.d[l][1], d2 = A.d[l][2], t1 = A.t[l][1], t2 = A.t[l][2];
-            for (int i = 0; i < 2 * d0 * t1 * t2; ++i) adj_z(A, S, l, i);
-            for (int i = 0; i < 4 * d0 * d1 * t2; ++i) adj_y(A, S, l, i);
-            for (int i = 0; i < 8 * d0 * d1 * d2; ++i) adj_x(A, S, l, i);
+            // same column / group decomposition as the kernel (plan_pass with the kernel's thread count)
+            HOST_PASS(adj_z, t1 * t2, 2 * d0)
+            HOST_PASS(adj_y, 2 * d0 * t2, 2 * d1)
+            HOST_PASS(adj_x, 4 * d0 * d1, 2 * d2)
         }
         for (int l = 0; l <= last; ++l) {
             const int n_l = coeff_elems(A, l);
@@ -518,9 +613,9 @@ extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfg
         }
         for (int l = 1; l <= last; ++l) {
             const int d0 = A.d[l][0], d1 = A.d[l][1], t0 = A.t[l][0], t1 = A.t[l][1], t2 = A.t[l][2];
-            for (int i = 0; i < 4 * d0 * d1 * t2; ++i) synth_x(A, S, l, i);
-            for (int i = 0; i < 2 * d0 * t1 * t2; ++i) synth_y(A, S, l, i);
-            for (int i = 0; i < t0 * t1 * t2; ++i) synth_z(A, S, l, i);
+            HOST_PASS(synth_x, 4 * d0 * d1, t2)
+            HOST_PASS(synth_y, 2 * d0 * t2, t1)
+            HOST_PASS(synth_z, t1 * t2, t0)
         }
         for (int i = 0; i < nvox; ++i) A.grid_cl[(long long)i * A.Cp + c] = S.L[i];
     }

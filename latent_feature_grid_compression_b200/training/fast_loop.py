@@ -567,11 +567,11 @@ def epoch_schedule(n_voxels: int, batch_size: int, sample_size: int, max_pass: f
                 break
 
 
-def solve_phase(model, volume, n_voxels, args, max_pass, lr, sched: Optional[LRSchedule] = None, bind: bool = True,
-                seed=0, rank=0, world=1, group=None, regularise=True, verbose=False):
-    """``solve_model`` (training/training.py:71-181) on the graph-captured step.  The GLOBAL batch is the reference's
-    ``batch_size * sample_size``; with ``world`` ranks each takes ``1/world`` of it (strong scaling, same optimisation
-    problem).  Returns (trainer, stopped_early)."""
+def make_trainer(model, volume, n_voxels, args, lr, seed=0, rank=0, world=1, group=None, regularise=True,
+                 variational_sched_check=None):
+    """FastTrainer for one phase of the reference's ``training(args)`` (training/training.py:184-237): the objective the
+    ``args`` dict selects (MSE, MSE + SmallifyLoss, or VariationalDropoutLoss with the static / dynamic variance), the
+    GLOBAL batch ``batch_size * sample_size`` split over ``world`` ranks (strong scaling: the same optimisation problem)."""
     batch = int(args['batch_size']) * int(args['sample_size'])
     if batch % world != 0:
         raise L.LfgcError('batch_size * sample_size = %d is not divisible by the world size %d' % (batch, world))
@@ -589,11 +589,18 @@ def solve_phase(model, volume, n_voxels, args, max_pass, lr, sched: Optional[LRS
             variational['variance_model'] = Variance_Model().to(volume.device).train()
         else:
             variational['log_sigma'] = float(args['variational_sigma'])
-        if sched is not None and sched.smallify:
+        if variational_sched_check is not None and variational_sched_check.smallify:
             raise L.LfgcError('smallify_decay != 0 (loss-plateau schedule) is not implemented for the variational loss '
                               'in the fast loop; use the module path (training/training.py) for that combination')
-    trainer = FastTrainer(model, volume, batch // world, lr=lr, seed=seed, rank=rank,
-                          world_size=world, process_group=group, weight_l1=w1, weight_l2=w2, variational=variational)
+    return FastTrainer(model, volume, batch // world, lr=lr, seed=seed, rank=rank, world_size=world,
+                       process_group=group, weight_l1=w1, weight_l2=w2, variational=variational)
+
+
+def solve_phase(model, volume, n_voxels, args, max_pass, lr, sched: Optional[LRSchedule] = None, bind: bool = True,
+                seed=0, rank=0, world=1, group=None, regularise=True, verbose=False):
+    """``solve_model`` (training/training.py:71-181) on the graph-captured step.  Returns (trainer, stopped_early)."""
+    trainer = make_trainer(model, volume, n_voxels, args, lr, seed=seed, rank=rank, world=world, group=group,
+                           regularise=regularise, variational_sched_check=sched)
     if sched is not None:
         sched.bind(trainer if bind else None)
     stopped = False
