@@ -33,12 +33,45 @@ namespace lfgc {
 namespace gstep {
 
 constexpr int kThreads = 1024;
+constexpr int kMaxCoeff = 8;   // coefficient tensors this kernel handles (pyramids that fit in shared memory have few)
+
+// n / d for the small non-negative n, d of this kernel (n * d < 2^32) without an integer division: one IMAD.HI
+struct FastDiv {
+    unsigned mul;   // floor(2^32 / d) + 1; 0 stands for d == 1
+};
+__host__ __device__ __forceinline__ FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.mul = d <= 1 ? 0u : (unsigned)(0x100000000ull / d) + 1u;
+    return f;
+}
+__host__ __device__ __forceinline__ int fdiv(int n, FastDiv f) {
+#ifdef __CUDA_ARCH__
+    return f.mul ? (int)__umulhi((unsigned)n, f.mul) : n;
+#else
+    return f.mul ? (int)(((unsigned long long)(unsigned)n * f.mul) >> 32) : n;
+#endif
+}
+
+// Work distribution of one pass over the CTA's threads: ncols columns (1-D lines of the pass) x n positions along the
+// filtered dimension; with fewer columns than threads the positions are cut into `groups` ranges of `per`.
+struct PassPlan {
+    int ncols, n, groups, per;
+    FastDiv by_ncols;
+};
+
+struct LevelPlan {
+    int d[3], t[3], off[3];
+    int cg_off;                 // offset (floats) of this level's detail bands inside the shared coefficient block
+    int m_lo[3], n_m[3];        // synthesis: first pair index and number of pairs along each axis
+    FastDiv by_t2, by_d0, by_d0d1;
+    PassPlan sx, sy, sz, az, ay, ax;   // synthesis x / y / z, adjoint z^T / y^T / x^T
+};
 
 struct Args {
     int n_coeff, C, Cp, ntaps;
     float lo[LFGC_MAX_TAPS], hi[LFGC_MAX_TAPS];
-    int d[LFGC_MAX_LEVELS][3], t[LFGC_MAX_LEVELS][3], off[LFGC_MAX_LEVELS][3];
-    int cg_off[LFGC_MAX_LEVELS];      // offset (floats) of level l's detail bands inside the shared coefficient block
+    int d0[3];                        // extent of coefficient tensor 0
+    LevelPlan lv[kMaxCoeff];          // [l] for synthesis level l >= 1
     int sL, sX, sY, sC;               // shared-memory partition sizes (floats): low-pass, x-pass, y-pass, coefficients
     int n_srcs;
     const float* grad_grid[LFGC_MAX_PEERS];
@@ -51,7 +84,7 @@ struct Args {
     float* g;
     float* m;
     float* v;
-    long long coeff_off[LFGC_MAX_LEVELS];
+    long long coeff_off[kMaxCoeff];
     long long mlp_off;
     float* loss_out;
     const float* lr;
@@ -70,198 +103,143 @@ struct Bufs {
     float* X;    // x-pass intermediate: [4 (a,b)][d0][d1][t2]
     float* Y;    // y-pass intermediate: [2 (a)][d0][t1][t2]
     float* Cg;   // detail bands of every level: gradient after the adjoint, updated value after Adam
-    const float* lo;   // reconstruction taps (shared-memory copies in the kernel: the tap index differs between the
-    const float* hi;   // lanes of a warp, which would serialise constant-bank reads)
 };
 
 // Every pass is organised by COLUMNS: a work unit is one 1-D line of the pass (fixed position in the two untouched
-// dimensions) times a range [o0, o1) of output positions along the filtered dimension.  The index decomposition happens
-// once per unit, the inner loops are division-free and the filter-tap selection is uniform over a warp.  (A first version
-// decomposed a flat index per OUTPUT ELEMENT: six integer divisions per element made the kernel 44 us, slower than the
-// six launches it replaces.)
+// dimensions) times a range of positions along the filtered dimension.  The index decomposition happens once per unit
+// (multiply-high instead of integer division), the filter length is a template parameter (taps in registers, loops
+// unrolled), and values loaded once are shared: a synthesis position m produces the output pair (2m, 2m+1) - off from the
+// same NT/2 inputs of each band; an adjoint position i produces BOTH bands from the same NT outputs.  (A first version
+// decomposed a flat index per output element with six integer divisions and a runtime tap loop: 44 us, slower than the
+// six launches it replaces; the second, column-organised one still executed ~100 instructions per output: 45 us.)
 
-// ---- synthesis level l, separable: x pass -> y pass -> z pass ----------------------------------------------------------
+// synthesis along one axis: inputs LO / HI (band low / high of this axis, element stride si, extent d), outputs OUT
+// (stride so, extent t); out[o] = sum_a lo[(o + off) / 2 - a] f_lo[(o + off) % 2 + 2 a] + the same with hi
+// (Torch_Wavelet_Transform.py:39-57,91-104: conv_transpose, stride 2, cropped by off)
+template <int NT>
+__host__ __device__ __forceinline__ void synth_line(const float* LO, const float* HI, int si, int d, float* OUT, int so,
+                                                    int t, int off, int m0, int m1, const float (&flo)[NT],
+                                                    const float (&fhi)[NT]) {
+    for (int m = m0; m < m1; ++m) {
+        float ev = 0.0f, od = 0.0f;
+#pragma unroll
+        for (int a = 0; a < NT / 2; ++a) {
+            const int i = m - a;
+            const bool ok = (unsigned)i < (unsigned)d;
+            const int ii = ok ? i * si : 0;
+            const float l = ok ? LO[ii] : 0.0f;
+            const float h = ok ? HI[ii] : 0.0f;
+            ev = fmaf(l, flo[2 * a], ev);
+            ev = fmaf(h, fhi[2 * a], ev);
+            od = fmaf(l, flo[2 * a + 1], od);
+            od = fmaf(h, fhi[2 * a + 1], od);
+        }
+        const int oe = 2 * m - off;
+        if ((unsigned)oe < (unsigned)t) OUT[oe * so] = ev;
+        if ((unsigned)(oe + 1) < (unsigned)t) OUT[(oe + 1) * so] = od;
+    }
+}
+// adjoint along one axis: g_lo[i] = sum_tt G[2 i + tt - off] f_lo[tt], g_hi likewise, both from the same NT loads
+template <int NT>
+__host__ __device__ __forceinline__ void adj_line(const float* G, int sg, int t, int off, float* OLO, float* OHI, int so,
+                                                  int i0, int i1, const float (&flo)[NT], const float (&fhi)[NT]) {
+    for (int i = i0; i < i1; ++i) {
+        float lo = 0.0f, hi = 0.0f;
+        const int q0 = 2 * i - off;
+#pragma unroll
+        for (int tt = 0; tt < NT; ++tt) {
+            const int q = q0 + tt;
+            const bool ok = (unsigned)q < (unsigned)t;
+            const float gq = ok ? G[ok ? q * sg : 0] : 0.0f;
+            lo = fmaf(gq, flo[tt], lo);
+            hi = fmaf(gq, fhi[tt], hi);
+        }
+        OLO[i * so] = lo;
+        OHI[i * so] = hi;
+    }
+}
+
 // band k = 4a + 2b + c, (a, b, c) = filter along (dim0, dim1, dim2), 0 = low / 1 = high; k = 0 is the running low-pass
-// (Torch_Wavelet_Transform.py:39-57,91-104).  out[o] = sum_i in[i] * f[o + off - 2 i].
-// x pass: column = (ab, iz, iy), 4 d0 d1 of them; outputs ox in [o0, o1) of t2
-__host__ __device__ __forceinline__ void synth_x(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
-    const int d0 = A.d[l][0], d1 = A.d[l][1], d2 = A.d[l][2], t2 = A.t[l][2];
-    const int dvol = d0 * d1 * d2;
-    const int ab = col / (d0 * d1);
-    const int zy = col - ab * d0 * d1;   // iz * d1 + iy
-    const float* b0 = (ab == 0 ? S.L : S.Cg + A.cg_off[l] + (2 * ab - 1) * dvol) + zy * d2;   // band (a, b, 0)
-    const float* b1 = S.Cg + A.cg_off[l] + (2 * ab) * dvol + zy * d2;                         // band (a, b, 1)
-    float* out = S.X + col * t2;
-    for (int ox = o0; ox < o1; ++ox) {
-        const int o = ox + A.off[l][2];
-        float acc = 0.0f;
-        for (int a = 0; 2 * a < A.ntaps; ++a) {
-            const int i = (o >> 1) - a;
-            const int tt = (o & 1) + 2 * a;
-            if (i >= 0 && i < d2) {
-                acc = fmaf(b0[i], S.lo[tt], acc);
-                acc = fmaf(b1[i], S.hi[tt], acc);
-            }
-        }
-        out[ox] = acc;
+template <int NT>
+struct Pass {
+    // synthesis, x pass: column = (ab, iz, iy), 4 d0 d1 of them
+    static __host__ __device__ __forceinline__ void sx(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
+                                                       int r1, const float (&flo)[NT], const float (&fhi)[NT]) {
+        const int d0d1 = P.d[0] * P.d[1], d2 = P.d[2], dvol = d0d1 * d2;
+        const int ab = fdiv(col, P.by_d0d1);
+        const int zy = col - ab * d0d1;
+        const float* b0 = (ab == 0 ? S.L : S.Cg + P.cg_off + (2 * ab - 1) * dvol) + zy * d2;
+        const float* b1 = S.Cg + P.cg_off + (2 * ab) * dvol + zy * d2;
+        synth_line<NT>(b0, b1, 1, d2, S.X + col * P.t[2], 1, P.t[2], P.off[2], P.m_lo[2] + r0, P.m_lo[2] + r1, flo, fhi);
     }
-}
-// y pass: column = (a, iz, ox), 2 d0 t2 of them; outputs oy in [o0, o1) of t1
-__host__ __device__ __forceinline__ void synth_y(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
-    const int d0 = A.d[l][0], d1 = A.d[l][1], t1 = A.t[l][1], t2 = A.t[l][2];
-    const int az = col / t2;             // a * d0 + iz
-    const int ox = col - az * t2;
-    const int a_ = az / d0;
-    const int iz = az - a_ * d0;
-    const int plane = d0 * d1 * t2;
-    const float* x0 = S.X + (2 * a_) * plane + iz * d1 * t2 + ox;       // (a, b = 0)
-    const float* x1 = x0 + plane;                                        // (a, b = 1)
-    float* out = S.Y + az * t1 * t2 + ox;
-    for (int oy = o0; oy < o1; ++oy) {
-        const int o = oy + A.off[l][1];
-        float acc = 0.0f;
-        for (int a = 0; 2 * a < A.ntaps; ++a) {
-            const int i = (o >> 1) - a;
-            const int tt = (o & 1) + 2 * a;
-            if (i >= 0 && i < d1) {
-                acc = fmaf(x0[i * t2], S.lo[tt], acc);
-                acc = fmaf(x1[i * t2], S.hi[tt], acc);
-            }
-        }
-        out[oy * t2] = acc;
+    // synthesis, y pass: column = (a, iz, ox), 2 d0 t2 of them
+    static __host__ __device__ __forceinline__ void sy(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
+                                                       int r1, const float (&flo)[NT], const float (&fhi)[NT]) {
+        const int d0 = P.d[0], d1 = P.d[1], t1 = P.t[1], t2 = P.t[2];
+        const int az = fdiv(col, P.by_t2);
+        const int ox = col - az * t2;
+        const int a_ = fdiv(az, P.by_d0);
+        const int iz = az - a_ * d0;
+        const int plane = d0 * d1 * t2;
+        const float* x0 = S.X + (2 * a_) * plane + iz * d1 * t2 + ox;
+        synth_line<NT>(x0, x0 + plane, t2, d1, S.Y + az * t1 * t2 + ox, t2, t1, P.off[1], P.m_lo[1] + r0, P.m_lo[1] + r1,
+                       flo, fhi);
     }
-}
-// z pass: column = (oy, ox), t1 t2 of them; outputs oz in [o0, o1) of t0
-__host__ __device__ __forceinline__ void synth_z(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
-    const int d0 = A.d[l][0], t1 = A.t[l][1], t2 = A.t[l][2];
-    const int pl = t1 * t2;
-    const float* y0 = S.Y + col;
-    const float* y1 = y0 + d0 * pl;
-    for (int oz = o0; oz < o1; ++oz) {
-        const int o = oz + A.off[l][0];
-        float acc = 0.0f;
-        for (int a = 0; 2 * a < A.ntaps; ++a) {
-            const int i = (o >> 1) - a;
-            const int tt = (o & 1) + 2 * a;
-            if (i >= 0 && i < d0) {
-                acc = fmaf(y0[i * pl], S.lo[tt], acc);
-                acc = fmaf(y1[i * pl], S.hi[tt], acc);
-            }
-        }
-        S.L[oz * pl + col] = acc;
+    // synthesis, z pass: column = (oy, ox), t1 t2 of them
+    static __host__ __device__ __forceinline__ void sz(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
+                                                       int r1, const float (&flo)[NT], const float (&fhi)[NT]) {
+        const int pl = P.t[1] * P.t[2];
+        const float* y0 = S.Y + col;
+        synth_line<NT>(y0, y0 + P.d[0] * pl, pl, P.d[0], S.L + col, pl, P.t[0], P.off[0], P.m_lo[0] + r0, P.m_lo[0] + r1,
+                       flo, fhi);
     }
-}
-
-// ---- adjoint of synthesis level l, separable: z^T pass -> y^T pass -> x^T pass ------------------------------------------
-// g_in[i] = sum_tt g_out[2 i + tt - off] * f[tt]
-// z^T pass: column = (oy, ox), t1 t2 of them; outputs (a, iz) = o in [o0, o1) of 2 d0
-__host__ __device__ __forceinline__ void adj_z(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
-    const int d0 = A.d[l][0], t0 = A.t[l][0], t1 = A.t[l][1], t2 = A.t[l][2];
-    const int pl = t1 * t2;
-    for (int o = o0; o < o1; ++o) {
-        const int a_ = o >= d0;
-        const int iz = o - a_ * d0;
-        const float* f = a_ ? S.hi : S.lo;
-        float acc = 0.0f;
-        for (int tt = 0; tt < A.ntaps; ++tt) {
-            const int q = 2 * iz + tt - A.off[l][0];
-            if (q >= 0 && q < t0) acc = fmaf(S.L[q * pl + col], f[tt], acc);
-        }
-        S.Y[o * pl + col] = acc;
+    // adjoint, z^T pass: column = (oy, ox)
+    static __host__ __device__ __forceinline__ void az(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
+                                                       int r1, const float (&flo)[NT], const float (&fhi)[NT]) {
+        const int pl = P.t[1] * P.t[2];
+        adj_line<NT>(S.L + col, pl, P.t[0], P.off[0], S.Y + col, S.Y + P.d[0] * pl + col, pl, r0, r1, flo, fhi);
     }
-}
-// y^T pass: column = (a, iz, ox), 2 d0 t2 of them; outputs (b, iy) = o in [o0, o1) of 2 d1
-__host__ __device__ __forceinline__ void adj_y(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
-    const int d0 = A.d[l][0], d1 = A.d[l][1], t1 = A.t[l][1], t2 = A.t[l][2];
-    const int az = col / t2;             // a * d0 + iz
-    const int ox = col - az * t2;
-    const int a_ = az / d0;
-    const int iz = az - a_ * d0;
-    const float* y = S.Y + az * t1 * t2 + ox;
-    for (int o = o0; o < o1; ++o) {
-        const int b_ = o >= d1;
-        const int iy = o - b_ * d1;
-        const float* f = b_ ? S.hi : S.lo;
-        float acc = 0.0f;
-        for (int tt = 0; tt < A.ntaps; ++tt) {
-            const int q = 2 * iy + tt - A.off[l][1];
-            if (q >= 0 && q < t1) acc = fmaf(y[q * t2], f[tt], acc);
-        }
-        S.X[(((2 * a_ + b_) * d0 + iz) * d1 + iy) * t2 + ox] = acc;
+    // adjoint, y^T pass: column = (a, iz, ox)
+    static __host__ __device__ __forceinline__ void ay(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
+                                                       int r1, const float (&flo)[NT], const float (&fhi)[NT]) {
+        const int d0 = P.d[0], d1 = P.d[1], t1 = P.t[1], t2 = P.t[2];
+        const int az_ = fdiv(col, P.by_t2);
+        const int ox = col - az_ * t2;
+        const int a_ = fdiv(az_, P.by_d0);
+        const int iz = az_ - a_ * d0;
+        const int plane = d0 * d1 * t2;
+        float* o0 = S.X + (2 * a_) * plane + iz * d1 * t2 + ox;
+        adj_line<NT>(S.Y + az_ * t1 * t2 + ox, t2, t1, P.off[1], o0, o0 + plane, t2, r0, r1, flo, fhi);
     }
-}
-// x^T pass: column = (ab, iz, iy), 4 d0 d1 of them; outputs (c, ix) = o in [o0, o1) of 2 d2
-__host__ __device__ __forceinline__ void adj_x(const Args& A, const Bufs& S, int l, int col, int o0, int o1) {
-    const int d0 = A.d[l][0], d1 = A.d[l][1], d2 = A.d[l][2], t2 = A.t[l][2];
-    const int dvol = d0 * d1 * d2;
-    const int ab = col / (d0 * d1);
-    const int zy = col - ab * d0 * d1;
-    const float* x = S.X + col * t2;
-    for (int o = o0; o < o1; ++o) {
-        const int c_ = o >= d2;
-        const int ix = o - c_ * d2;
-        const float* f = c_ ? S.hi : S.lo;
-        float acc = 0.0f;
-        for (int tt = 0; tt < A.ntaps; ++tt) {
-            const int q = 2 * ix + tt - A.off[l][2];
-            if (q >= 0 && q < t2) acc = fmaf(x[q], f[tt], acc);
-        }
-        const int k = 2 * ab + c_;
-        const int pos = zy * d2 + ix;
-        if (k == 0) S.L[pos] = acc;                                   // gradient of the low-pass input of this level
-        else S.Cg[A.cg_off[l] + (k - 1) * dvol + pos] = acc;          // gradient of detail band k
+    // adjoint, x^T pass: column = (ab, iz, iy)
+    static __host__ __device__ __forceinline__ void ax(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
+                                                       int r1, const float (&flo)[NT], const float (&fhi)[NT]) {
+        const int d0d1 = P.d[0] * P.d[1], d2 = P.d[2], dvol = d0d1 * d2;
+        const int ab = fdiv(col, P.by_d0d1);
+        const int zy = col - ab * d0d1;
+        float* o0 = (ab == 0 ? S.L : S.Cg + P.cg_off + (2 * ab - 1) * dvol) + zy * d2;   // band (a, b, 0)
+        float* o1 = S.Cg + P.cg_off + (2 * ab) * dvol + zy * d2;                          // band (a, b, 1)
+        adj_line<NT>(S.X + col * P.t[2], 1, P.t[2], P.off[2], o0, o1, 1, r0, r1, flo, fhi);
     }
-}
-
-// Work distribution of one pass over `nthreads` workers: ncols columns x n_out outputs; when there are fewer columns
-// than workers the output range is cut into groups so that (almost) every worker has something to do.
-struct PassPlan {
-    int ncols, n_out, groups, per;
 };
-__host__ __device__ __forceinline__ PassPlan plan_pass(int ncols, int n_out, int nthreads) {
-    PassPlan p;
-    p.ncols = ncols;
-    p.n_out = n_out;
-    int g = ncols > 0 ? nthreads / ncols : 1;
-    if (g < 1) g = 1;
-    if (g > n_out) g = n_out;
-    p.groups = g;
-    p.per = (n_out + g - 1) / g;
-    return p;
-}
-#define LFGC_PASS(fn, ncols_, nout_)                                                           \
-    {                                                                                          \
-        const PassPlan pp = plan_pass((ncols_), (nout_), kThreads);                            \
-        for (int u = tid; u < pp.ncols * pp.groups; u += kThreads) {                           \
-            const int grp = u / pp.ncols;                                                      \
-            const int col = u - grp * pp.ncols;                                                \
-            const int b0_ = grp * pp.per;                                                      \
-            const int b1_ = b0_ + pp.per < pp.n_out ? b0_ + pp.per : pp.n_out;                 \
-            fn(A, S, l, col, b0_, b1_);                                                        \
-        }                                                                                      \
-        __syncthreads();                                                                       \
-    }
-
-// Adam on element e of coefficient tensor l of channel c; the gradient sits in shared memory and is replaced there by
-// the updated coefficient (what the synthesis below reads)
-__host__ __device__ __forceinline__ void adam_coeff(const Args& A, const Bufs& S, int l, int c, int e, int n_l,
-                                                    float step_size, float bc2_sqrt) {
-    float* slot = l == 0 ? S.L + e : S.Cg + A.cg_off[l] + e;
-    const long long i = A.coeff_off[l] + (long long)c * n_l + e;
-    float pi = A.p[i], mi = A.m[i], vi = A.v[i];
-    const float gi = fmaf(A.w2x2, pi, *slot);
-    adam_update(pi, gi, mi, vi, A.c, step_size, bc2_sqrt);
-    A.p[i] = pi;
-    A.m[i] = mi;
-    A.v[i] = vi;
-    A.g[i] = gi;
-    *slot = pi;
-}
 
 __host__ __device__ __forceinline__ int coeff_elems(const Args& A, int l) {
-    const int dv = A.d[l][0] * A.d[l][1] * A.d[l][2];
-    return l == 0 ? dv : 7 * dv;
+    if (l == 0) return A.d0[0] * A.d0[1] * A.d0[2];
+    return 7 * A.lv[l].d[0] * A.lv[l].d[1] * A.lv[l].d[2];
 }
+
+// run one pass: unit u of `nworkers` strided workers -> (group, column) -> position range
+#define LFGC_RUN_PASS(fn, plan_, first_, stride_)                                              \
+    {                                                                                          \
+        const PassPlan& pp = (plan_);                                                          \
+        for (int u = (first_); u < pp.ncols * pp.groups; u += (stride_)) {                     \
+            const int grp = fdiv(u, pp.by_ncols);                                              \
+            const int col = u - grp * pp.ncols;                                                \
+            const int r0_ = grp * pp.per;                                                      \
+            const int r1_ = r0_ + pp.per < pp.n ? r0_ + pp.per : pp.n;                         \
+            Pass<NT>::fn(A, S, P, col, r0_, r1_, flo, fhi);                                    \
+        }                                                                                      \
+    }
 
 #ifdef __CUDACC__
 // Data-parallel barrier INSIDE the kernel (no separate collective, no extra launch): every rank's kernel announces its
@@ -288,18 +266,14 @@ __device__ __forceinline__ void peer_barrier(const Args& A, int tid) {
     __syncthreads();
 }
 
+template <int NT>
 __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_constant__ Args A) {
     LFGC_PDL_PROLOGUE();
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_step_size, s_bc2_sqrt;
     __shared__ int s_step;
-    __shared__ float s_lo[LFGC_MAX_TAPS], s_hi[LFGC_MAX_TAPS];
     const int tid = threadIdx.x;
     if (A.sync_epoch) peer_barrier(A, tid);
-    if (tid < LFGC_MAX_TAPS) {
-        s_lo[tid] = A.lo[tid];
-        s_hi[tid] = A.hi[tid];
-    }
     if (tid == 0) {
         const int step = *reinterpret_cast<volatile int*>(A.step) + 1;
         float step_size, bc2_sqrt;
@@ -315,12 +289,15 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
         S.X = S.L + A.sL;
         S.Y = S.X + A.sX;
         S.Cg = S.Y + A.sY;
-        S.lo = s_lo;
-        S.hi = s_hi;
+        float flo[NT], fhi[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            flo[i] = A.lo[i];
+            fhi[i] = A.hi[i];
+        }
         const int last = A.n_coeff - 1;
         // ---- this channel's slice of the grid gradient (summed over the ranks in rank order), accumulator cleared ----------
-        const int* G = last >= 1 ? A.t[last] : A.d[0];
-        const int nvox = G[0] * G[1] * G[2];
+        const int nvox = last >= 1 ? A.lv[last].t[0] * A.lv[last].t[1] * A.lv[last].t[2] : A.d0[0] * A.d0[1] * A.d0[2];
         for (int i = tid; i < nvox; i += kThreads) {
             const long long a = (long long)i * A.Cp + c;
             float gsum = __ldcv(A.grad_grid[0] + a);          // rewritten every step (also by peers): never from L1
@@ -329,22 +306,25 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
             if (A.zero_grid) A.zero_grid[a] = 0.0f;
         }
         if (A.zero_grid && c == A.C - 1) {                      // pad channels of the accumulator stay zero anyway; keep them so
-            for (int i = tid; i < nvox * (A.Cp - A.C); i += kThreads)
-                A.zero_grid[(long long)(i / (A.Cp - A.C)) * A.Cp + A.C + i % (A.Cp - A.C)] = 0.0f;
+            const int np = A.Cp - A.C;
+            for (int i = tid; i < nvox * np; i += kThreads) A.zero_grid[(long long)(i / np) * A.Cp + A.C + i % np] = 0.0f;
         }
         __syncthreads();
         // ---- adjoint, finest -> coarsest --------------------------------------------------------------------------------------
         for (int l = last; l >= 1; --l) {
-            const int d0 = A.d[l][0], d1 = A.d[l][1], d2 = A.d[l][2], t1 = A.t[l][1], t2 = A.t[l][2];
-            LFGC_PASS(adj_z, t1 * t2, 2 * d0)
-            LFGC_PASS(adj_y, 2 * d0 * t2, 2 * d1)
-            LFGC_PASS(adj_x, 4 * d0 * d1, 2 * d2)
+            const LevelPlan& P = A.lv[l];
+            LFGC_RUN_PASS(az, P.az, tid, kThreads)
+            __syncthreads();
+            LFGC_RUN_PASS(ay, P.ay, tid, kThreads)
+            __syncthreads();
+            LFGC_RUN_PASS(ax, P.ax, tid, kThreads)
+            __syncthreads();
         }
         // ---- Adam on this channel's coefficients ---------------------------------------------------------------------------------
         const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
         for (int l = 0; l <= last; ++l) {
             const int n_l = coeff_elems(A, l);
-            float* slots = l == 0 ? S.L : S.Cg + A.cg_off[l];
+            float* slots = l == 0 ? S.L : S.Cg + A.lv[l].cg_off;
             const long long base = A.coeff_off[l] + (long long)c * n_l;
             for (int e0 = 0; e0 < n_l; e0 += 4 * kThreads) {       // four elements per thread: 12 loads in flight
                 float pi[4], mi[4], vi[4];
@@ -375,15 +355,18 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
         __syncthreads();
         // ---- synthesis of the updated coefficients, coarsest -> finest ------------------------------------------------------------
         for (int l = 1; l <= last; ++l) {
-            const int d0 = A.d[l][0], d1 = A.d[l][1], t0 = A.t[l][0], t1 = A.t[l][1], t2 = A.t[l][2];
-            LFGC_PASS(synth_x, 4 * d0 * d1, t2)
-            LFGC_PASS(synth_y, 2 * d0 * t2, t1)
-            LFGC_PASS(synth_z, t1 * t2, t0)
+            const LevelPlan& P = A.lv[l];
+            LFGC_RUN_PASS(sx, P.sx, tid, kThreads)
+            __syncthreads();
+            LFGC_RUN_PASS(sy, P.sy, tid, kThreads)
+            __syncthreads();
+            LFGC_RUN_PASS(sz, P.sz, tid, kThreads)
+            __syncthreads();
         }
         for (int i = tid; i < nvox; i += kThreads) A.grid_cl[(long long)i * A.Cp + c] = S.L[i];
         if (c == A.C - 1) {
-            for (int i = tid; i < nvox * (A.Cp - A.C); i += kThreads)
-                A.grid_cl[(long long)(i / (A.Cp - A.C)) * A.Cp + A.C + i % (A.Cp - A.C)] = 0.0f;
+            const int np = A.Cp - A.C;
+            for (int i = tid; i < nvox * np; i += kThreads) A.grid_cl[(long long)(i / np) * A.Cp + A.C + i % np] = 0.0f;
         }
     } else {
         // ---- MLP block: fixed-order reduction of the partial sums (deterministic), then Adam.  64 parameters x 16 slice
@@ -443,8 +426,22 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
 
 using namespace lfgc;
 
-// Shared-memory partition sizes; returns the total in floats (0: no coefficient tensor)
+static gstep::PassPlan make_plan(int ncols, int n) {
+    gstep::PassPlan p;
+    p.ncols = ncols;
+    p.n = n;
+    int g = ncols > 0 ? gstep::kThreads / ncols : 1;
+    if (g < 1) g = 1;
+    if (g > n) g = n > 0 ? n : 1;
+    p.groups = g;
+    p.per = (n + g - 1) / g;
+    p.by_ncols = gstep::make_fastdiv((unsigned)(ncols > 0 ? ncols : 1));
+    return p;
+}
+
+// Level plans and shared-memory partition sizes; returns the total in floats
 static size_t gstep_layout(gstep::Args& A, const lfgc_wavelet_desc* w) {
+    using namespace gstep;
     A.n_coeff = w->n_coeff;
     A.C = w->C;
     A.ntaps = w->n_taps;
@@ -452,27 +449,37 @@ static size_t gstep_layout(gstep::Args& A, const lfgc_wavelet_desc* w) {
         A.lo[i] = i < w->n_taps ? w->rec_lo[i] : 0.0f;
         A.hi[i] = i < w->n_taps ? w->rec_hi[i] : 0.0f;
     }
-    size_t sL = 0, sX = 0, sY = 0, sC = 0;
-    for (int l = 0; l < LFGC_MAX_LEVELS; ++l) {
+    for (int a = 0; a < 3; ++a) A.d0[a] = w->dims[0][a];
+    size_t sL = (size_t)A.d0[0] * A.d0[1] * A.d0[2], sX = 0, sY = 0, sC = 0;
+    for (int l = 0; l < kMaxCoeff; ++l) {
+        LevelPlan& P = A.lv[l];
+        P = LevelPlan();
+        if (l < 1 || l >= w->n_coeff) continue;
         for (int a = 0; a < 3; ++a) {
-            A.d[l][a] = l < w->n_coeff ? w->dims[l][a] : 0;
-            A.t[l][a] = (l >= 1 && l < w->n_coeff) ? w->target[l][a] : 0;
-            A.off[l][a] = (l >= 1 && l < w->n_coeff) ? (2 * A.d[l][a] + A.ntaps - 2 - A.t[l][a]) / 2 : 0;
+            P.d[a] = w->dims[l][a];
+            P.t[a] = w->target[l][a];
+            P.off[a] = (2 * P.d[a] + A.ntaps - 2 - P.t[a]) / 2;
+            P.m_lo[a] = P.off[a] >> 1;
+            P.n_m[a] = ((P.off[a] + P.t[a] - 1) >> 1) - P.m_lo[a] + 1;
         }
-        A.cg_off[l] = 0;
-        if (l >= w->n_coeff) continue;
-        const size_t dv = (size_t)A.d[l][0] * A.d[l][1] * A.d[l][2];
+        const int d0 = P.d[0], d1 = P.d[1], d2 = P.d[2], t0 = P.t[0], t1 = P.t[1], t2 = P.t[2];
+        const size_t dv = (size_t)d0 * d1 * d2, tv = (size_t)t0 * t1 * t2;
         if (dv > sL) sL = dv;
-        if (l >= 1) {
-            const size_t tv = (size_t)A.t[l][0] * A.t[l][1] * A.t[l][2];
-            if (tv > sL) sL = tv;
-            const size_t x = 4 * (size_t)A.d[l][0] * A.d[l][1] * A.t[l][2];
-            const size_t y = 2 * (size_t)A.d[l][0] * A.t[l][1] * A.t[l][2];
-            if (x > sX) sX = x;
-            if (y > sY) sY = y;
-            A.cg_off[l] = (int)sC;
-            sC += 7 * dv;
-        }
+        if (tv > sL) sL = tv;
+        const size_t x = 4 * (size_t)d0 * d1 * t2, y = 2 * (size_t)d0 * t1 * t2;
+        if (x > sX) sX = x;
+        if (y > sY) sY = y;
+        P.cg_off = (int)sC;
+        sC += 7 * dv;
+        P.by_t2 = make_fastdiv((unsigned)t2);
+        P.by_d0 = make_fastdiv((unsigned)d0);
+        P.by_d0d1 = make_fastdiv((unsigned)(d0 * d1));
+        P.sx = make_plan(4 * d0 * d1, P.n_m[2]);
+        P.sy = make_plan(2 * d0 * t2, P.n_m[1]);
+        P.sz = make_plan(t1 * t2, P.n_m[0]);
+        P.az = make_plan(t1 * t2, d0);
+        P.ay = make_plan(2 * d0 * t2, d1);
+        P.ax = make_plan(4 * d0 * d1, d2);
     }
     auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
     A.sL = (int)up4(sL);
@@ -485,8 +492,9 @@ static size_t gstep_layout(gstep::Args& A, const lfgc_wavelet_desc* w) {
 static int gstep_check_desc(const lfgc_wavelet_desc* w) {
     if (!w) return fail(LFGC_E_INVALID, "grid_step: null descriptor");
     if (w->n_coeff < 1 || w->n_coeff > LFGC_MAX_LEVELS || w->C < 1) return fail(LFGC_E_INVALID, "grid_step: bad descriptor");
-    if (w->n_coeff > 1 && (w->n_taps < 2 || w->n_taps > LFGC_MAX_TAPS || (w->n_taps & 1)))
-        return fail(LFGC_E_INVALID, "grid_step: bad filter length %d", w->n_taps);
+    if (w->n_coeff > gstep::kMaxCoeff) return fail(LFGC_E_UNSUPPORTED, "grid_step: %d coefficient tensors (<= %d)", w->n_coeff, gstep::kMaxCoeff);
+    if (w->n_coeff > 1 && w->n_taps != 2 && w->n_taps != 4)   // what the oracle pins (haar, db2); longer filters: separate kernels
+        return fail(LFGC_E_UNSUPPORTED, "grid_step: filter length %d (2 or 4 taps)", w->n_taps);
     return LFGC_OK;
 }
 
@@ -526,7 +534,7 @@ static int gstep_fill(gstep::Args& A, const lfgc_wavelet_desc* w, int Cp, const 
     A.g = a->g;
     A.m = a->m;
     A.v = a->v;
-    for (int l = 0; l < LFGC_MAX_LEVELS; ++l) {
+    for (int l = 0; l < gstep::kMaxCoeff; ++l) {
         A.coeff_off[l] = l < w->n_coeff ? a->coeff_off[l] : 0;
         if (l < w->n_coeff && a->coeff_off[l] < 0) return fail(LFGC_E_INVALID, "grid_step: negative coefficient offset");
     }
@@ -553,7 +561,8 @@ extern "C" int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_gri
     if (rc) return rc;
     const size_t smem = lfgc_grid_step_smem_bytes(w);
     if (smem == 0) return fail(LFGC_E_UNSUPPORTED, "grid_step: the per-channel wavelet pyramid does not fit in shared memory");
-    auto kern = gstep::grid_step_kernel;
+    void (*kern)(const gstep::Args) = gstep::grid_step_kernel<4>;
+    if (w->n_coeff == 1 || w->n_taps == 2) kern = gstep::grid_step_kernel<2>;
     LFGC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     (void)launch_pdl(kern, dim3((unsigned)(A.C + A.n_mlp_ctas)), dim3(gstep::kThreads), smem, (cudaStream_t)stream, A);
     LFGC_LAUNCH_OK();
@@ -561,24 +570,12 @@ extern "C" int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_gri
 }
 
 #ifdef LFGC_GRID_STEP_HOST_TEST
-// Test hook (only in builds made by tests/test_grid_step_host.py, never in liblfgc.so): the SAME per-element functions in
-// the same phase order, run sequentially on HOST memory, so the separable index arithmetic can be checked against the
-// numpy oracle without a GPU.  All pointers are host pointers here.
-#define HOST_PASS(fn, ncols_, nout_)                                                           \
-    {                                                                                          \
-        const PassPlan pp = plan_pass((ncols_), (nout_), kThreads);                            \
-        for (int u = 0; u < pp.ncols * pp.groups; ++u) {                                       \
-            const int grp = u / pp.ncols, col = u - grp * pp.ncols;                            \
-            const int b0_ = grp * pp.per;                                                      \
-            const int b1_ = b0_ + pp.per < pp.n_out ? b0_ + pp.per : pp.n_out;                 \
-            fn(A, S, l, col, b0_, b1_);                                                        \
-        }                                                                                      \
-    }
-extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a) {
+// Test hook (only in builds made by tests/test_grid_step_host.py, never in liblfgc.so): the SAME per-column functions, the
+// same plans and the same phase order, run sequentially on HOST memory, so the separable index arithmetic can be checked
+// against the numpy oracle without a GPU.  All pointers are host pointers here.
+template <int NT>
+static void gstep_run_host(const gstep::Args& A) {
     using namespace gstep;
-    Args A;
-    const int rc = gstep_fill(A, w, Cp, a);
-    if (rc) return rc;
     const size_t total = (size_t)A.sL + A.sX + A.sY + A.sC;
     float* mem = (float*)calloc(total + 4, sizeof(float));
     Bufs S;
@@ -586,14 +583,16 @@ extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfg
     S.X = S.L + A.sL;
     S.Y = S.X + A.sX;
     S.Cg = S.Y + A.sY;
-    S.lo = A.lo;
-    S.hi = A.hi;
+    float flo[NT], fhi[NT];
+    for (int i = 0; i < NT; ++i) {
+        flo[i] = A.lo[i];
+        fhi[i] = A.hi[i];
+    }
     const int step = A.step[0] + 1;
     float step_size, bc2_sqrt;
     adam_step_scalars(A.c, step, *A.lr, step_size, bc2_sqrt);
     const int last = A.n_coeff - 1;
-    const int* G = last >= 1 ? A.t[last] : A.d[0];
-    const int nvox = G[0] * G[1] * G[2];
+    const int nvox = last >= 1 ? A.lv[last].t[0] * A.lv[last].t[1] * A.lv[last].t[2] : A.d0[0] * A.d0[1] * A.d0[2];
     for (int c = 0; c < A.C; ++c) {
         for (int i = 0; i < nvox; ++i) {
             float gsum = 0.0f;
@@ -601,21 +600,35 @@ extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfg
             S.L[i] = gsum;
         }
         for (int l = last; l >= 1; --l) {
-            const int d0 = A.d[l][0], d1 = A.d[l][1], d2 = A.d[l][2], t1 = A.t[l][1], t2 = A.t[l][2];
-            // same column / group decomposition as the kernel (plan_pass with the kernel's thread count)
-            HOST_PASS(adj_z, t1 * t2, 2 * d0)
-            HOST_PASS(adj_y, 2 * d0 * t2, 2 * d1)
-            HOST_PASS(adj_x, 4 * d0 * d1, 2 * d2)
+            const LevelPlan& P = A.lv[l];
+            for (size_t i = 0; i < (size_t)A.sX; ++i) S.X[i] = 1e30f;   // poison: every element read must have been written
+            for (size_t i = 0; i < (size_t)A.sY; ++i) S.Y[i] = 1e30f;
+            LFGC_RUN_PASS(az, P.az, 0, 1)
+            LFGC_RUN_PASS(ay, P.ay, 0, 1)
+            LFGC_RUN_PASS(ax, P.ax, 0, 1)
         }
         for (int l = 0; l <= last; ++l) {
             const int n_l = coeff_elems(A, l);
-            for (int e = 0; e < n_l; ++e) adam_coeff(A, S, l, c, e, n_l, step_size, bc2_sqrt);
+            float* slots = l == 0 ? S.L : S.Cg + A.lv[l].cg_off;
+            const long long base = A.coeff_off[l] + (long long)c * n_l;
+            for (int e = 0; e < n_l; ++e) {
+                float pi = A.p[base + e], mi = A.m[base + e], vi = A.v[base + e];
+                const float gi = fmaf(A.w2x2, pi, slots[e]);
+                adam_update(pi, gi, mi, vi, A.c, step_size, bc2_sqrt);
+                A.p[base + e] = pi;
+                A.m[base + e] = mi;
+                A.v[base + e] = vi;
+                A.g[base + e] = gi;
+                slots[e] = pi;
+            }
         }
         for (int l = 1; l <= last; ++l) {
-            const int d0 = A.d[l][0], d1 = A.d[l][1], t0 = A.t[l][0], t1 = A.t[l][1], t2 = A.t[l][2];
-            HOST_PASS(synth_x, 4 * d0 * d1, t2)
-            HOST_PASS(synth_y, 2 * d0 * t2, t1)
-            HOST_PASS(synth_z, t1 * t2, t0)
+            const LevelPlan& P = A.lv[l];
+            for (size_t i = 0; i < (size_t)A.sX; ++i) S.X[i] = 1e30f;
+            for (size_t i = 0; i < (size_t)A.sY; ++i) S.Y[i] = 1e30f;
+            LFGC_RUN_PASS(sx, P.sx, 0, 1)
+            LFGC_RUN_PASS(sy, P.sy, 0, 1)
+            LFGC_RUN_PASS(sz, P.sz, 0, 1)
         }
         for (int i = 0; i < nvox; ++i) A.grid_cl[(long long)i * A.Cp + c] = S.L[i];
     }
@@ -623,11 +636,10 @@ extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfg
         for (int c = A.C; c < A.Cp; ++c) A.grid_cl[(long long)i * A.Cp + c] = 0.0f;
     if (A.zero_grid)
         for (long long i = 0; i < (long long)nvox * A.Cp; ++i) A.zero_grid[i] = 0.0f;
-    const int ns = A.nslices;
     for (int j = 0; j <= A.pcount; ++j) {
         float t = 0.0f;
         for (int r = 0; r < A.n_srcs; ++r)
-            for (int b = 0; b < ns; ++b) t += A.mlp_partials[r][(size_t)b * A.pstride + j];
+            for (int b = 0; b < A.nslices; ++b) t += A.mlp_partials[r][(size_t)b * A.pstride + j];
         if (j < A.pcount) {
             const long long i = A.mlp_off + j;
             float pi = A.p[i], mi = A.m[i], vi = A.v[i];
@@ -642,6 +654,14 @@ extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfg
     }
     A.step[0] = step;
     free(mem);
+}
+
+extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a) {
+    gstep::Args A;
+    const int rc = gstep_fill(A, w, Cp, a);
+    if (rc) return rc;
+    if (w->n_coeff == 1 || w->n_taps == 2) gstep_run_host<2>(A);
+    else gstep_run_host<4>(A);
     return LFGC_OK;
 }
 #endif

@@ -403,9 +403,10 @@ template <int HP, int FUSED>
 static int launch_backward(BwdArgs& A, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
                            cudaStream_t st) {
     {
-        // tensor-core kernel first (LFGC_BACKWARD_TC=0 forces the FFMA2 kernels); it covers the MSE / backward-only modes
+        // tensor-core kernel first (LFGC_BACKWARD_TC=0 forces the FFMA2 kernels); it covers the MSE, log-likelihood and
+        // backward-only modes of the SnakeAlt model (the ReLU Variance_Model stays on the FFMA2 kernel)
         const char* e = getenv("LFGC_BACKWARD_TC");
-        if (!(e && e[0] == '0') && !A.log_sigma && !(A.P.flags & kFlagPlainRelu)) {
+        if (!(e && e[0] == '0') && !(A.P.flags & kFlagPlainRelu)) {
             const int rc = launch_backward_tc(A, FUSED, grad_mlp, accumulate, workspace, workspace_bytes, st);
             if (rc != 1) return rc;
         }

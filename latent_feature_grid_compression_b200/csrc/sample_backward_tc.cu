@@ -14,9 +14,12 @@
 //   produced it, so the pair is operand and stash at once:
 //       [  0, 32)  working accumulator: z_l in the forward, dh_l / d(features) in the backward
 //       [ 32,224)  h_1, h_2, h_3 as (hi | lo), 64 columns each; the layer-0 input (K0p <= 56 columns) borrows the
-//                  h_2 (hi) and h_3 (lo) slots, which are free until layers 2 / 3 are reached
-//       [224,288)  dz_l (hi | lo)                [288,352)  layer-0 input, fp32 (re-split for dW_0 in the backward)
-//       [352,480)  dW_l^T accumulators, one 32-column block per layer, kept across the whole persistent loop
+//                  h_2 (hi) and h_3 (lo) slots, which are free until layers 2 / 3 are reached; in the backward the h_3
+//                  slot carries dz_l (hi | lo) (h_3 is read out for its weight-gradient operand first)
+//       [224,480)  dW_l^T accumulators, one 64-column block per layer ([A dz_hi | A dz_lo]), kept across the whole
+//                  persistent loop
+//   The fp32 copy of the layer-0 input (re-split for dW_0 in the backward) lives in shared memory, written and read by
+//   the same threads.
 //   Forward, layer l:      z_l = h_l W_l^T          A = h_l (TMEM),            B = W_l   K-major panels (smem)
 //   Backward, layer l:     dh_l = dz_l W_l          A = dz_l (TMEM),           B = W_l^T K-major panels (smem)
 //                          dW_l^T += [h_l | 1]^T dz_l   A = h_l MN-major (smem), B = dz_l MN-major (smem), K = samples
@@ -26,8 +29,10 @@
 //   The ones column appended to h_l (row 63 of the accumulator) makes the bias gradient part of the same MMA.
 //
 //   Weight-gradient operands: the A block is [h hi g0 | h hi g1 | h lo g0 | h lo g1] (four 32-column groups), read
-//   as ONE M = 128 operand, so the "hi" MMA already yields hi*dz in rows 0..63 and lo*dz in rows 64..127; two MMAs per
-//   K step (B = dz hi, B = dz lo) give hi*hi + lo*hi + hi*lo (+ the negligible lo*lo), and the flush adds rows r, r+64.
+//   as ONE M = 128 operand, and the B block is [dz hi | dz lo] read as ONE N = 64 operand, so a single MMA per K step
+//   yields hi*dz_hi (rows 0..63, columns 0..31), hi*dz_lo (rows 0..63, columns 32..63), lo*dz_hi and the negligible
+//   lo*dz_lo (rows 64..127); the flush adds the four quadrants.  (Round 1 issued two N = 32 MMAs per K step, reading the
+//   4 KB A block twice: the weight-gradient MMAs are shared-memory-bandwidth bound, 6 KB instead of 10 KB per K step.)
 //
 //   tf32 operands read MN-major (contraction over the samples) only work in the SWIZZLE_128B_BASE32B layout on sm_100a
 //   (measured, profiles/microbench/umma_addr.cu: every other layout type returns zeros for kind::tf32 with a transposed operand):
@@ -61,7 +66,7 @@ constexpr int kBlkMN = TILE * 128;   // bytes of one MN-major [128 samples][32 c
 constexpr int kOnesRow = 63;         // accumulator row that receives the bias gradient (column 31 of MN group 1)
 
 // TMEM column map
-constexpr int cAcc = 0, cA1 = 32, cDz = 224, cH0 = 288, cW = 352, kTmemCols = 512;
+constexpr int cAcc = 0, cA1 = 32, cDz = 160, cW = 224, kWAcc = 64, kTmemCols = 512;   // cDz aliases the h_3 slot
 __host__ __device__ constexpr int colA_hi(int l) { return l == 0 ? cA1 + 64 : cA1 + 64 * (l - 1); }
 __host__ __device__ constexpr int colA_lo(int l) { return l == 0 ? cA1 + 128 : cA1 + 64 * (l - 1) + 32; }
 
@@ -238,7 +243,7 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 
 // ---- shared-memory layout (bytes) ---------------------------------------------------------------------------------------
 struct Layout {
-    int ctrl, bias, wf, yx, Hm, Dm, Wf, Wb, total;
+    int ctrl, bias, wf, yx, Hm, Dm, X0, Wf, Wb, total;
     int Np0;       // rows of the layer-0 backward weight operand (feature columns, multiple of 16)
     int wb0;       // bytes of the layer-0 backward weight operand (one of hi / lo)
     int wfBytes, wbBytes;  // bytes of one of hi / lo
@@ -258,6 +263,7 @@ __host__ __device__ inline Layout make_layout(const SampleParams& P, int K0p, in
     p = (p + 1023) & ~1023;
     o.Hm = p;   p += 4 * kBlkMN;              // MN-major [h hi g0 | h hi g1 (+ones) | h lo g0 | h lo g1]
     o.Dm = p;   p += 2 * kBlkMN;              // MN-major dz_l (hi | lo); parameter staging at start-up, flush scratch
+    o.X0 = p;   p += (K0p / 4) * TILE * 16;   // fp32 layer-0 input, [K chunk][sample] float4 (re-split for dW_0)
     o.Wf = p;   p += 2 * o.wfBytes;
     o.Wb = p;   p += 2 * o.wbBytes;
     o.total = p;
@@ -282,6 +288,7 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     unsigned char* Hm = smem + Lo.Hm;
     unsigned char* DmHi = smem + Lo.Dm;
     unsigned char* DmLo = DmHi + kBlkMN;
+    float4* X0s = reinterpret_cast<float4*>(smem + Lo.X0);
     unsigned char* WfHi = smem + Lo.Wf;
     unsigned char* WfLo = WfHi + Lo.wfBytes;
     unsigned char* WbHi = smem + Lo.Wb;
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             for (int i = 0; i < 4; ++i) split_tf32(v4[i], hi[i], lo[i]);
             tmem_st<4>(trow + colA_hi(0) + 4 * c, hi);
             tmem_st<4>(trow + colA_lo(0) + 4 * c, lo);
-            tmem_st<4>(trow + cH0 + 4 * c, v4);
+            X0s[c * TILE + s] = make_float4(v4[0], v4[1], v4[2], v4[3]);
         };
         // feature chunks two at a time: 16 independent 128-bit gathers in flight per thread
         for (int c = q; 4 * c < Cp; c += 2 * TPS) {
@@ -551,6 +558,11 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
                 const float e = y - aux;
                 dy = valid ? A.loss_scale2 * e : 0.0f;
                 if (q == 0 && valid) loss_part = fmaf(e, e, loss_part);
+                if (A.log_sigma && valid) {   // Gaussian likelihood with per-sample log sigma (VariationalDropoutLoss,
+                    const float w = expf(-2.0f * __ldg(A.log_sigma + sg));   // Variational_Dropout_Layer.py:24-30)
+                    dy *= w;
+                    if (A.dlog_sigma && q == 0) A.dlog_sigma[sg] = A.loss_scale2 * (1.0f - e * e * w);
+                }
             } else {
                 dy = valid ? aux : 0.0f;
             }
@@ -573,6 +585,25 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
                     pendingB = false;
                 }
                 BT_MARK(11)  // dW wait
+                // h_l -> MN-major operand (group 0; the layer-0 input also fills its columns >= 32 of group 1).  Read BEFORE
+                // dz_l is written: dz shares the TMEM slot of h_3 (same lanes and columns per thread)
+                if (l > 0) {
+                    float hi[CW], lo[CW];
+                    tmem_ld<CW>(trow + colA_hi(l) + col0, hi);
+                    tmem_ld<CW>(trow + colA_lo(l) + col0, lo);
+#pragma unroll
+                    for (int c = 0; c < CW / 4; ++c)
+                        put_mn(Hm, Hm + 2 * kBlkMN, col0 + 4 * c, make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]),
+                               make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]));
+                } else {
+                    for (int c = q; c < K0p / 4; c += TPS) {
+                        const float4 hv = X0s[c * TILE + s];
+                        float4 hi, lo;
+                        split4(hv, hi, lo);
+                        const int g = (4 * c) >> 5;   // 32-column group
+                        put_mn(Hm + g * kBlkMN, Hm + (2 + g) * kBlkMN, (4 * c) & 31, hi, lo);
+                    }
+                }
                 // dz_l: TMEM operand of dh_l (hi | lo) and MN-major operand of dW_l
                 {
                     float hi[CW], lo[CW];
@@ -584,26 +615,6 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
                     for (int c = 0; c < CW / 4; ++c)
                         put_mn(DmHi, DmLo, col0 + 4 * c, make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]),
                                make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]));
-                }
-                // h_l -> MN-major operand (group 0; the layer-0 input also fills its columns >= 32 of group 1)
-                if (l > 0) {
-                    float hi[CW], lo[CW];
-                    tmem_ld<CW>(trow + colA_hi(l) + col0, hi);
-                    tmem_ld<CW>(trow + colA_lo(l) + col0, lo);
-#pragma unroll
-                    for (int c = 0; c < CW / 4; ++c)
-                        put_mn(Hm, Hm + 2 * kBlkMN, col0 + 4 * c, make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]),
-                               make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]));
-                } else {
-                    for (int c = q; c < K0p / 4; c += TPS) {
-                        float hv[4], hi[4], lo[4];
-                        tmem_ld<4>(trow + cH0 + 4 * c, hv);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) split_tf32(hv[i], hi[i], lo[i]);
-                        const int g = (4 * c) >> 5;   // 32-column group
-                        put_mn(Hm + g * kBlkMN, Hm + (2 + g) * kBlkMN, (4 * c) & 31, make_float4(hi[0], hi[1], hi[2], hi[3]),
-                               make_float4(lo[0], lo[1], lo[2], lo[3]));
-                    }
                 }
                 tmem_st_wait();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -627,16 +638,15 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
                         }
                         mma_commit(barA);
                     }
-                    // dW_l^T += [h_l | 1]^T dz_l, contraction over the 128 samples (8 per MMA); rows 0..63 of the accumulator
-                    // collect hi * dz, rows 64..127 lo * dz
+                    // dW_l^T += [h_l | 1]^T [dz_hi | dz_lo], contraction over the 128 samples (8 per MMA); rows 0..63 of the
+                    // accumulator collect hi * dz, rows 64..127 lo * dz; columns 0..31 dz_hi, 32..63 dz_lo
                     {
-                        constexpr uint32_t id = idesc(HP, 1, 1);
-                        const uint32_t d = tmem + cW + l * HP;
-                        const uint64_t a0 = desc_mn(aHm), bh0 = desc_mn(aDmHi), bl0 = desc_mn(aDmLo);
+                        constexpr uint32_t id = idesc(2 * HP, 1, 1);
+                        const uint32_t d = tmem + cW + l * kWAcc;
+                        const uint64_t a0 = desc_mn(aHm), b0 = desc_mn(aDmHi);   // DmLo follows DmHi: the second N group
                         for (int ks = 0; ks < TILE / 8; ++ks) {
                             const uint64_t adv = (uint64_t)((ks * 1024) >> 4);
-                            mma_tf32(d, a0 + adv, bh0 + adv, id, (first_tile && ks == 0) ? 0u : 1u);
-                            mma_tf32(d, a0 + adv, bl0 + adv, id, 1u);
+                            mma_tf32(d, a0 + adv, b0 + adv, id, (first_tile && ks == 0) ? 0u : 1u);
                         }
                         mma_commit(barB);
                     }
@@ -690,11 +700,13 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     if ((warp & 3) >= 2) {
         const int row = (((warp & 3) - 2) << 5) | lane;
         for (int l = q; l < L; l += TPS) {
-            float r[32];
-            tmem_ld<32>(trow + cW + l * HP, r);
+            float r[32], r2[32];
+            tmem_ld<32>(trow + cW + l * kWAcc, r);
+            tmem_ld<32>(trow + cW + l * kWAcc + HP, r2);
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(xch + (l * 64 + row) * 32 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                *reinterpret_cast<float4*>(xch + (l * 64 + row) * 32 + j) =
+                    make_float4(r[j] + r2[j], r[j + 1] + r2[j + 1], r[j + 2] + r2[j + 2], r[j + 3] + r2[j + 3]);
         }
     }
     __syncthreads();
@@ -702,7 +714,13 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         const int row = ((warp & 3) << 5) | lane;
         for (int l = q; l < L; l += TPS) {
             float r[32];
-            tmem_ld<32>(trow + cW + l * HP, r);
+            {
+                float r2[32];
+                tmem_ld<32>(trow + cW + l * kWAcc, r);
+                tmem_ld<32>(trow + cW + l * kWAcc + HP, r2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] += r2[j];
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 o = *reinterpret_cast<const float4*>(xch + (l * 64 + row) * 32 + j);

@@ -40,9 +40,10 @@ def axis_tables(dataset, tiled_res=32, device='cuda'):
     return tables
 
 
-def field_from_net(dataset, net, is_cuda=True, tiled_res=32, verbose=False, slab=None, to_cpu=True):
+def field_from_net(dataset, net, is_cuda=True, tiled_res=32, verbose=False, slab=None, to_cpu=True, host_out=None):
     """Reconstructed volume (R0, R1, R2).  ``slab=(begin, end)`` restricts the work to rows [begin, end) of dim 0
-    and returns only that slab (the multi-GPU sharding unit)."""
+    and returns only that slab (the multi-GPU sharding unit).  ``host_out``: a (pinned) CPU tensor of the slab's shape
+    that receives the result (one asynchronous D2H copy + a stream synchronise instead of a pageable ``.cpu()``)."""
     if not th.cuda.is_available():
         raise ops.L.LfgcError('field_from_net runs on CUDA only (no CPU fallback)')
     res = tuple(int(r) for r in dataset.vol_res_touple)
@@ -54,6 +55,10 @@ def field_from_net(dataset, net, is_cuda=True, tiled_res=32, verbose=False, slab
         grid_cl = ops.decode_fwd(geom, [f.detach().contiguous() for f in net.feature_grid], mults)
         out = ops.reconstruct(geom, grid_cl, net.mlp_flat(), res, axis_tables(dataset, tiled_res, dev), begin, end,
                               clamp=True)
+    if host_out is not None:
+        host_out.copy_(out, non_blocking=True)
+        th.cuda.current_stream().synchronize()
+        return host_out
     return out.cpu() if to_cpu else out
 
 
