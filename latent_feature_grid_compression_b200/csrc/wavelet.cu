@@ -444,6 +444,14 @@ static int check_desc(const lfgc_wavelet_desc* w) {
     return LFGC_OK;
 }
 
+// wavelet_sep.cu: separable two-kernels-per-level path for large mask-free pyramids
+size_t wavelet_sep_scratch_elems(const lfgc_wavelet_desc* w);
+bool wavelet_sep_preferred(const lfgc_wavelet_desc* w);
+int wavelet_sep_fwd(const lfgc_wavelet_desc* w, const float* const* coeff, float* scratch, float* grid_cl, int Cp,
+                    float* also_zero, cudaStream_t st);
+int wavelet_sep_bwd(const lfgc_wavelet_desc* w, const float* grad_grid_cl, int Cp, float* scratch, float* const* grad_coeff,
+                    cudaStream_t st);
+
 static size_t intermediate_elems(const lfgc_wavelet_desc* w) {
     size_t mx = 0;
     for (int l = 1; l < w->n_coeff - 1; ++l) {
@@ -495,7 +503,9 @@ extern "C" int lfgc_smallify_ema(const float* betas, float* ema, float* emavar, 
 
 extern "C" size_t lfgc_decode_scratch_bytes(const lfgc_wavelet_desc* w) {
     if (!w || check_desc(w) != LFGC_OK) return 0;
-    return 2 * intermediate_elems(w) * sizeof(float) + 16;
+    size_t elems = 2 * intermediate_elems(w);
+    if (wavelet_sep_preferred(w) && wavelet_sep_scratch_elems(w) > elems) elems = wavelet_sep_scratch_elems(w);
+    return elems * sizeof(float) + 16;
 }
 
 extern "C" int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* coeff, const float* const* mult,
@@ -511,6 +521,14 @@ extern "C" int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* c
                                                                                         grid_cl, also_zero, w->C, Cp, nvox);
         LFGC_LAUNCH_OK();
         return LFGC_OK;
+    }
+    {   // large mask-free pyramids: separable passes (wavelet_sep.cu)
+        bool masked = false;
+        for (int l = 0; mult && l < w->n_coeff; ++l) masked = masked || mult[l] != nullptr;
+        if (!masked && wavelet_sep_preferred(w)) {
+            if (!scratch) return fail(LFGC_E_WORKSPACE, "decode_fwd: scratch required");
+            return wavelet_sep_fwd(w, coeff, scratch, grid_cl, Cp, also_zero, st);
+        }
     }
     const size_t inter = intermediate_elems(w);
     if (inter && !scratch) return fail(LFGC_E_WORKSPACE, "decode_fwd: scratch required");
@@ -561,6 +579,17 @@ extern "C" int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_gri
             Cp, nvox, accumulate);
         LFGC_LAUNCH_OK();
         return LFGC_OK;
+    }
+    {   // large mask-free pyramids: separable passes (wavelet_sep.cu)
+        bool masked = false;
+        for (int l = 0; l < w->n_coeff; ++l)
+            masked = masked || (gmul && gmul[l] != nullptr) || (grad_mult && grad_mult[l] != nullptr);
+        if (!masked && !accumulate && wavelet_sep_preferred(w)) {
+            if (!scratch) return fail(LFGC_E_WORKSPACE, "decode_bwd: scratch required");
+            for (int l = 0; l < w->n_coeff; ++l)
+                if (!grad_coeff[l]) return fail(LFGC_E_INVALID, "decode_bwd: grad_coeff[%d] null", l);
+            return wavelet_sep_bwd(w, grad_grid_cl, Cp, scratch, grad_coeff, st);
+        }
     }
     const size_t inter = intermediate_elems(w);
     if (inter && !scratch) return fail(LFGC_E_WORKSPACE, "decode_bwd: scratch required");
