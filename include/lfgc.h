@@ -304,10 +304,15 @@ typedef struct lfgc_grid_step_args {
     int32_t rank;
     int32_t* sync_flags[LFGC_MAX_PEERS];          /* flag array (int32[n_srcs]) of every rank, as mapped on THIS device */
     int32_t* sync_epoch;                          /* this rank's launch counter (device int32) */
+    /* Optional global-memory scratch of lfgc_grid_step_scratch_bytes(): with it every channel is worked on by a cluster of
+     * 8 CTAs (passes through L2, hardware cluster barriers) instead of one CTA with the pyramid in shared memory. */
+    float* scratch;
+    size_t scratch_bytes;
 } lfgc_grid_step_args;
 int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a, void* stream);
 /* dynamic shared memory lfgc_grid_step needs for this pyramid; 0 = not supported (does not fit: use the separate kernels) */
 size_t lfgc_grid_step_smem_bytes(const lfgc_wavelet_desc* w);
+size_t lfgc_grid_step_scratch_bytes(const lfgc_wavelet_desc* w);
 
 /* Gradient of the KL regulariser of VariationalDropoutLoss (model/Variational_Dropout_Layer.py:54-69,115-122) added
  * in place to the mask-parameter gradients, and the per-step ramp of its weight (:57-58).  mask_params / mask_grads

@@ -49,7 +49,8 @@ class GridStepArgs(C.Structure):
                 ('grid_cl', _f), ('p', _f), ('g', _f), ('m', _f), ('v', _f), ('coeff_off', _i64 * MAX_LEVELS),
                 ('mlp_off', _i64), ('loss_out', _f), ('lr', _f), ('step_count', _f), ('beta1', C.c_double),
                 ('beta2', C.c_double), ('eps', C.c_double), ('grad_scale', C.c_double), ('weight_l2', C.c_double),
-                ('rank', C.c_int32), ('sync_flags', _f * MAX_PEERS), ('sync_epoch', _f)]
+                ('rank', C.c_int32), ('sync_flags', _f * MAX_PEERS), ('sync_epoch', _f), ('scratch', _f),
+                ('scratch_bytes', C.c_size_t)]
 
 
 _SIGNATURES = {
@@ -93,6 +94,7 @@ _SIGNATURES = {
                                            C.POINTER(C.c_int32), _f]),
     'lfgc_grid_step': (C.c_int, [C.POINTER(WaveletDesc), C.c_int, C.POINTER(GridStepArgs), _f]),
     'lfgc_grid_step_smem_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
+    'lfgc_grid_step_scratch_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
     'lfgc_variational_dkl_grad': (C.c_int, [_f, _f, C.c_int, C.POINTER(C.c_int64), _f, _f, C.c_double, C.c_double,
                                             C.c_float, _f]),
 }

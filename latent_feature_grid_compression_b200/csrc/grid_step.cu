@@ -75,6 +75,7 @@ struct Args {
     AdamCoef c;
     float w2x2;                       // 2 * weight_l2
     int n_mlp_ctas;
+    float* scratch;                   // cluster variant: per-channel [sL | sX | sY | sC] floats in global memory
     int rank;                         // data-parallel peer barrier (sync_epoch != nullptr): this rank's index, ...
     int* sync_flags[LFGC_MAX_PEERS];  // ... every rank's flag array (int[n_srcs], peer memory; [rank] is the local one)
     int* sync_epoch;                  // ... and this rank's launch counter (device int, monotonic)
@@ -97,7 +98,7 @@ struct Bufs {
 // six launches it replaces; the second, column-organised one still executed ~100 instructions per output: 45 us.)
 
 // band k = 4a + 2b + c, (a, b, c) = filter along (dim0, dim1, dim2), 0 = low / 1 = high; k = 0 is the running low-pass
-template <int NT>
+template <int NT, bool CG = false>
 struct Pass {
     // synthesis, x pass: column = (ab, iz, iy), 4 d0 d1 of them
     static __host__ __device__ __forceinline__ void sx(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
@@ -107,7 +108,7 @@ struct Pass {
         const int zy = col - ab * d0d1;
         const float* b0 = (ab == 0 ? S.L : S.Cg + P.cg_off + (2 * ab - 1) * dvol) + zy * d2;
         const float* b1 = S.Cg + P.cg_off + (2 * ab) * dvol + zy * d2;
-        synth_line<NT>(b0, b1, 1, d2, S.X + col * P.t[2], 1, P.t[2], P.off[2], P.m_lo[2] + r0, P.m_lo[2] + r1, flo, fhi);
+        synth_line<NT, CG>(b0, b1, 1, d2, S.X + col * P.t[2], 1, P.t[2], P.off[2], P.m_lo[2] + r0, P.m_lo[2] + r1, flo, fhi);
     }
     // synthesis, y pass: column = (a, iz, ox), 2 d0 t2 of them
     static __host__ __device__ __forceinline__ void sy(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
@@ -119,7 +120,7 @@ struct Pass {
         const int iz = az - a_ * d0;
         const int plane = d0 * d1 * t2;
         const float* x0 = S.X + (2 * a_) * plane + iz * d1 * t2 + ox;
-        synth_line<NT>(x0, x0 + plane, t2, d1, S.Y + az * t1 * t2 + ox, t2, t1, P.off[1], P.m_lo[1] + r0, P.m_lo[1] + r1,
+        synth_line<NT, CG>(x0, x0 + plane, t2, d1, S.Y + az * t1 * t2 + ox, t2, t1, P.off[1], P.m_lo[1] + r0, P.m_lo[1] + r1,
                        flo, fhi);
     }
     // synthesis, z pass: column = (oy, ox), t1 t2 of them
@@ -127,14 +128,14 @@ struct Pass {
                                                        int r1, const float (&flo)[NT], const float (&fhi)[NT]) {
         const int pl = P.t[1] * P.t[2];
         const float* y0 = S.Y + col;
-        synth_line<NT>(y0, y0 + P.d[0] * pl, pl, P.d[0], S.L + col, pl, P.t[0], P.off[0], P.m_lo[0] + r0, P.m_lo[0] + r1,
+        synth_line<NT, CG>(y0, y0 + P.d[0] * pl, pl, P.d[0], S.L + col, pl, P.t[0], P.off[0], P.m_lo[0] + r0, P.m_lo[0] + r1,
                        flo, fhi);
     }
     // adjoint, z^T pass: column = (oy, ox)
     static __host__ __device__ __forceinline__ void az(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
                                                        int r1, const float (&flo)[NT], const float (&fhi)[NT]) {
         const int pl = P.t[1] * P.t[2];
-        adj_line<NT>(S.L + col, pl, P.t[0], P.off[0], S.Y + col, S.Y + P.d[0] * pl + col, pl, r0, r1, flo, fhi);
+        adj_line<NT, CG>(S.L + col, pl, P.t[0], P.off[0], S.Y + col, S.Y + P.d[0] * pl + col, pl, r0, r1, flo, fhi);
     }
     // adjoint, y^T pass: column = (a, iz, ox)
     static __host__ __device__ __forceinline__ void ay(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
@@ -146,7 +147,7 @@ struct Pass {
         const int iz = az_ - a_ * d0;
         const int plane = d0 * d1 * t2;
         float* o0 = S.X + (2 * a_) * plane + iz * d1 * t2 + ox;
-        adj_line<NT>(S.Y + az_ * t1 * t2 + ox, t2, t1, P.off[1], o0, o0 + plane, t2, r0, r1, flo, fhi);
+        adj_line<NT, CG>(S.Y + az_ * t1 * t2 + ox, t2, t1, P.off[1], o0, o0 + plane, t2, r0, r1, flo, fhi);
     }
     // adjoint, x^T pass: column = (ab, iz, iy)
     static __host__ __device__ __forceinline__ void ax(const Args& A, const Bufs& S, const LevelPlan& P, int col, int r0,
@@ -156,7 +157,7 @@ struct Pass {
         const int zy = col - ab * d0d1;
         float* o0 = (ab == 0 ? S.L : S.Cg + P.cg_off + (2 * ab - 1) * dvol) + zy * d2;   // band (a, b, 0)
         float* o1 = S.Cg + P.cg_off + (2 * ab) * dvol + zy * d2;                          // band (a, b, 1)
-        adj_line<NT>(S.X + col * P.t[2], 1, P.t[2], P.off[2], o0, o1, 1, r0, r1, flo, fhi);
+        adj_line<NT, CG>(S.X + col * P.t[2], 1, P.t[2], P.off[2], o0, o1, 1, r0, r1, flo, fhi);
     }
 };
 
@@ -174,7 +175,7 @@ __host__ __device__ __forceinline__ int coeff_elems(const Args& A, int l) {
             const int col = u - grp * pp.ncols;                                                \
             const int r0_ = grp * pp.per;                                                      \
             const int r1_ = r0_ + pp.per < pp.n ? r0_ + pp.per : pp.n;                         \
-            Pass<NT>::fn(A, S, P, col, r0_, r1_, flo, fhi);                                    \
+            PassT::fn(A, S, P, col, r0_, r1_, flo, fhi);                                       \
         }                                                                                      \
     }
 
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
         s_bc2_sqrt = bc2_sqrt;
     }
     const int c = blockIdx.x;
+    using PassT = Pass<NT, false>;
     if (c < A.C) {
         Bufs S;
         S.L = smem;
@@ -356,6 +358,162 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
         }
     }
 }
+
+// ---- cluster variant ------------------------------------------------------------------------------------------------------------
+// One CTA per channel executes ~60 k warp instructions (the passes are issue-bound: 29 us measured for the kernel above at
+// C16/G15, no better than the launches it replaces).  Here a thread-block CLUSTER of 8 CTAs (8 SMs) works on each channel:
+// the same passes, the same plans scaled to 8 x 512 workers, but the per-channel buffers live in global memory (L2) and
+// the phases are separated by hardware cluster barriers (barrier.cluster, release / acquire at cluster scope).  With
+// <= 1 position per thread a pass is one L2 round trip plus a barrier instead of ~1600 issue cycles.
+constexpr int kClusterSize = 8;
+constexpr int kClusterThreads = 512;
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+#define LFGC_CL_PASS(fn, plan_)            \
+    LFGC_RUN_PASS(fn, plan_, wid, nworkers) \
+    cluster_sync_all();
+
+template <int NT>
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClusterThreads, 1)
+    grid_step_cluster_kernel(const __grid_constant__ Args A) {
+    LFGC_PDL_PROLOGUE();
+    __shared__ float s_step_size, s_bc2_sqrt;
+    __shared__ int s_step;
+    __shared__ float s_red[kClusterThreads];
+    const int tid = threadIdx.x;
+    if (A.sync_epoch) peer_barrier(A, tid);
+    if (tid == 0) {
+        const int step = *reinterpret_cast<volatile int*>(A.step) + 1;
+        float step_size, bc2_sqrt;
+        adam_step_scalars(A.c, step, *A.lr, step_size, bc2_sqrt);
+        s_step = step;
+        s_step_size = step_size;
+        s_bc2_sqrt = bc2_sqrt;
+    }
+    __syncthreads();
+    const int c = blockIdx.x / kClusterSize;
+    const int rank = (int)cluster_ctarank();
+    using PassT = Pass<NT, true>;
+    if (c < A.C) {
+        constexpr int nworkers = kClusterSize * kClusterThreads;
+        const int wid = rank * kClusterThreads + tid;
+        Bufs S;
+        S.L = A.scratch + (size_t)c * ((size_t)A.sL + A.sX + A.sY + A.sC);
+        S.X = S.L + A.sL;
+        S.Y = S.X + A.sX;
+        S.Cg = S.Y + A.sY;
+        float flo[NT], fhi[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            flo[i] = A.lo[i];
+            fhi[i] = A.hi[i];
+        }
+        const int last = A.n_coeff - 1;
+        const int nvox = last >= 1 ? A.lv[last].t[0] * A.lv[last].t[1] * A.lv[last].t[2] : A.d0[0] * A.d0[1] * A.d0[2];
+        for (int i = wid; i < nvox; i += nworkers) {
+            const long long a = (long long)i * A.Cp + c;
+            float gsum = __ldcv(A.grad_grid[0] + a);
+            for (int r = 1; r < A.n_srcs; ++r) gsum += __ldcv(A.grad_grid[r] + a);
+            S.L[i] = gsum;
+            if (A.zero_grid) A.zero_grid[a] = 0.0f;
+        }
+        if (A.zero_grid && c == A.C - 1) {
+            const int np = A.Cp - A.C;
+            for (int i = wid; i < nvox * np; i += nworkers) A.zero_grid[(long long)(i / np) * A.Cp + A.C + i % np] = 0.0f;
+        }
+        cluster_sync_all();
+        for (int l = last; l >= 1; --l) {
+            const LevelPlan& P = A.lv[l];
+            LFGC_CL_PASS(az, P.az)
+            LFGC_CL_PASS(ay, P.ay)
+            LFGC_CL_PASS(ax, P.ax)
+        }
+        const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+        for (int l = 0; l <= last; ++l) {
+            const int n_l = coeff_elems(A, l);
+            float* slots = l == 0 ? S.L : S.Cg + A.lv[l].cg_off;
+            const long long base = A.coeff_off[l] + (long long)c * n_l;
+            for (int e = wid; e < n_l; e += nworkers) {
+                float pi = A.p[base + e], mi = A.m[base + e], vi = A.v[base + e];
+                const float gi = fmaf(A.w2x2, pi, __ldcg(slots + e));
+                adam_update(pi, gi, mi, vi, A.c, step_size, bc2_sqrt);
+                A.p[base + e] = pi;
+                A.m[base + e] = mi;
+                A.v[base + e] = vi;
+                A.g[base + e] = gi;
+                slots[e] = pi;
+            }
+        }
+        cluster_sync_all();
+        for (int l = 1; l <= last; ++l) {
+            const LevelPlan& P = A.lv[l];
+            LFGC_CL_PASS(sx, P.sx)
+            LFGC_CL_PASS(sy, P.sy)
+            LFGC_CL_PASS(sz, P.sz)
+        }
+        for (int i = wid; i < nvox; i += nworkers) A.grid_cl[(long long)i * A.Cp + c] = __ldcg(S.L + i);
+        if (c == A.C - 1) {
+            const int np = A.Cp - A.C;
+            for (int i = wid; i < nvox * np; i += nworkers) A.grid_cl[(long long)(i / np) * A.Cp + A.C + i % np] = 0.0f;
+        }
+    } else {
+        // MLP block, 64 parameters x 8 slice groups per CTA (see grid_step_kernel)
+        constexpr int PX = 64, SY = kClusterThreads / PX;
+        const int px = tid % PX, sy = tid / PX;
+        const int j = ((c - A.C) * kClusterSize + rank) * PX + px;
+        float acc = 0.0f;
+        if (j <= A.pcount) {
+            for (int r = 0; r < A.n_srcs; ++r) {
+                const float* src = A.mlp_partials[r] + j;
+                for (int b = sy; b < A.nslices; b += 4 * SY) {
+                    float t0 = __ldcv(src + (size_t)b * A.pstride), t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+                    if (b + SY < A.nslices) t1 = __ldcv(src + (size_t)(b + SY) * A.pstride);
+                    if (b + 2 * SY < A.nslices) t2 = __ldcv(src + (size_t)(b + 2 * SY) * A.pstride);
+                    if (b + 3 * SY < A.nslices) t3 = __ldcv(src + (size_t)(b + 3 * SY) * A.pstride);
+                    acc += (t0 + t1) + (t2 + t3);
+                }
+            }
+        }
+        s_red[sy * PX + px] = acc;
+        __syncthreads();
+        if (sy == 0 && j <= A.pcount) {
+            float t = 0.0f;
+#pragma unroll
+            for (int g = 0; g < SY; ++g) t += s_red[g * PX + px];
+            if (j < A.pcount) {
+                const long long i = A.mlp_off + j;
+                float pi = A.p[i], mi = A.m[i], vi = A.v[i];
+                adam_update(pi, t, mi, vi, A.c, s_step_size, s_bc2_sqrt);
+                A.p[i] = pi;
+                A.m[i] = mi;
+                A.v[i] = vi;
+                A.g[i] = t;
+            } else if (A.loss_out) {
+                A.loss_out[0] = t;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(A.step + 1, 1);
+        if (ticket == (int)gridDim.x - 1) {
+            A.step[1] = 0;
+            if (A.sync_epoch) *A.sync_epoch += 1;
+            __threadfence();
+            A.step[0] = s_step;
+        }
+    }
+}
 #endif
 
 }  // namespace gstep
@@ -363,11 +521,11 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
 
 using namespace lfgc;
 
-static gstep::PassPlan make_plan(int ncols, int n) {
+static gstep::PassPlan make_plan(int ncols, int n, int nworkers) {
     gstep::PassPlan p;
     p.ncols = ncols;
     p.n = n;
-    int g = ncols > 0 ? gstep::kThreads / ncols : 1;
+    int g = ncols > 0 ? nworkers / ncols : 1;
     if (g < 1) g = 1;
     if (g > n) g = n > 0 ? n : 1;
     p.groups = g;
@@ -377,7 +535,7 @@ static gstep::PassPlan make_plan(int ncols, int n) {
 }
 
 // Level plans and shared-memory partition sizes; returns the total in floats
-static size_t gstep_layout(gstep::Args& A, const lfgc_wavelet_desc* w) {
+static size_t gstep_layout(gstep::Args& A, const lfgc_wavelet_desc* w, int nworkers = gstep::kThreads) {
     using namespace gstep;
     A.n_coeff = w->n_coeff;
     A.C = w->C;
@@ -411,12 +569,12 @@ static size_t gstep_layout(gstep::Args& A, const lfgc_wavelet_desc* w) {
         P.by_t2 = make_fastdiv((unsigned)t2);
         P.by_d0 = make_fastdiv((unsigned)d0);
         P.by_d0d1 = make_fastdiv((unsigned)(d0 * d1));
-        P.sx = make_plan(4 * d0 * d1, P.n_m[2]);
-        P.sy = make_plan(2 * d0 * t2, P.n_m[1]);
-        P.sz = make_plan(t1 * t2, P.n_m[0]);
-        P.az = make_plan(t1 * t2, d0);
-        P.ay = make_plan(2 * d0 * t2, d1);
-        P.ax = make_plan(4 * d0 * d1, d2);
+        P.sx = make_plan(4 * d0 * d1, P.n_m[2], nworkers);
+        P.sy = make_plan(2 * d0 * t2, P.n_m[1], nworkers);
+        P.sz = make_plan(t1 * t2, P.n_m[0], nworkers);
+        P.az = make_plan(t1 * t2, d0, nworkers);
+        P.ay = make_plan(2 * d0 * t2, d1, nworkers);
+        P.ax = make_plan(4 * d0 * d1, d2, nworkers);
     }
     auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
     A.sL = (int)up4(sL);
@@ -445,7 +603,21 @@ extern "C" size_t lfgc_grid_step_smem_bytes(const lfgc_wavelet_desc* w) {
     return bytes <= (size_t)cap - 64 ? bytes : 0;
 }
 
-static int gstep_fill(gstep::Args& A, const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a) {
+extern "C" size_t lfgc_grid_step_scratch_bytes(const lfgc_wavelet_desc* w) {
+    if (gstep_check_desc(w)) return 0;
+    gstep::Args A;
+    return (size_t)w->C * gstep_layout(A, w) * sizeof(float);
+}
+
+// the cluster variant (8 CTAs per channel, buffers in global memory) runs when the caller provides its scratch;
+// LFGC_GRID_STEP_CLUSTER=0 forces the one-CTA-per-channel kernel
+static bool gstep_use_cluster(const lfgc_wavelet_desc* w, const lfgc_grid_step_args* a) {
+    if (!a->scratch || a->scratch_bytes < lfgc_grid_step_scratch_bytes(w)) return false;
+    const char* e = getenv("LFGC_GRID_STEP_CLUSTER");
+    return !(e && e[0] == '0');
+}
+
+static int gstep_fill(gstep::Args& A, const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a, int nworkers) {
     const int rc = gstep_check_desc(w);
     if (rc) return rc;
     if (!a) return fail(LFGC_E_INVALID, "grid_step: null arguments");
@@ -453,8 +625,9 @@ static int gstep_fill(gstep::Args& A, const lfgc_wavelet_desc* w, int Cp, const 
     if (a->n_srcs < 1 || a->n_srcs > LFGC_MAX_PEERS) return fail(LFGC_E_UNSUPPORTED, "grid_step: %d gradient sources (1..%d)", a->n_srcs, LFGC_MAX_PEERS);
     if (!a->grid_cl || !a->p || !a->g || !a->m || !a->v || !a->lr || !a->step_count || a->pcount < 0 || a->pstride < a->pcount + 1 || a->nslices < 1)
         return fail(LFGC_E_INVALID, "grid_step: bad buffer arguments");
-    gstep_layout(A, w);
+    gstep_layout(A, w, nworkers);
     A.Cp = Cp;
+    A.scratch = a->scratch;
     A.n_srcs = a->n_srcs;
     for (int r = 0; r < LFGC_MAX_PEERS; ++r) {
         A.grad_grid[r] = r < a->n_srcs ? a->grad_grid[r] : nullptr;
@@ -494,7 +667,18 @@ static int gstep_fill(gstep::Args& A, const lfgc_wavelet_desc* w, int Cp, const 
 
 extern "C" int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a, void* stream) {
     gstep::Args A;
-    const int rc = gstep_fill(A, w, Cp, a);
+    if (a && w && gstep_check_desc(w) == LFGC_OK && gstep_use_cluster(w, a)) {
+        const int rc = gstep_fill(A, w, Cp, a, gstep::kClusterSize * gstep::kClusterThreads);
+        if (rc) return rc;
+        void (*kc)(const gstep::Args) = gstep::grid_step_cluster_kernel<4>;
+        if (w->n_coeff == 1 || w->n_taps == 2) kc = gstep::grid_step_cluster_kernel<2>;
+        const int mlp_clusters = (A.n_mlp_ctas + gstep::kClusterSize - 1) / gstep::kClusterSize;
+        (void)launch_pdl(kc, dim3((unsigned)((A.C + mlp_clusters) * gstep::kClusterSize)), dim3(gstep::kClusterThreads), (size_t)0,
+                         (cudaStream_t)stream, A);
+        LFGC_LAUNCH_OK();
+        return LFGC_OK;
+    }
+    const int rc = gstep_fill(A, w, Cp, a, gstep::kThreads);
     if (rc) return rc;
     const size_t smem = lfgc_grid_step_smem_bytes(w);
     if (smem == 0) return fail(LFGC_E_UNSUPPORTED, "grid_step: the per-channel wavelet pyramid does not fit in shared memory");
@@ -513,6 +697,7 @@ extern "C" int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_gri
 template <int NT>
 static void gstep_run_host(const gstep::Args& A) {
     using namespace gstep;
+    using PassT = Pass<NT, false>;
     const size_t total = (size_t)A.sL + A.sX + A.sY + A.sC;
     float* mem = (float*)calloc(total + 4, sizeof(float));
     Bufs S;
@@ -593,9 +778,9 @@ static void gstep_run_host(const gstep::Args& A) {
     free(mem);
 }
 
-extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a) {
+extern "C" int lfgc_grid_step_host(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a, int nworkers) {
     gstep::Args A;
-    const int rc = gstep_fill(A, w, Cp, a);
+    const int rc = gstep_fill(A, w, Cp, a, nworkers);
     if (rc) return rc;
     if (w->n_coeff == 1 || w->n_taps == 2) gstep_run_host<2>(A);
     else gstep_run_host<4>(A);

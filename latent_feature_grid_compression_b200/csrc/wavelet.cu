@@ -504,7 +504,7 @@ extern "C" int lfgc_smallify_ema(const float* betas, float* ema, float* emavar, 
 extern "C" size_t lfgc_decode_scratch_bytes(const lfgc_wavelet_desc* w) {
     if (!w || check_desc(w) != LFGC_OK) return 0;
     size_t elems = 2 * intermediate_elems(w);
-    if (wavelet_sep_preferred(w) && wavelet_sep_scratch_elems(w) > elems) elems = wavelet_sep_scratch_elems(w);
+    if (wavelet_sep_scratch_elems(w) > elems) elems = wavelet_sep_scratch_elems(w);   // whichever path is taken at run time
     return elems * sizeof(float) + 16;
 }
 

@@ -23,10 +23,19 @@ __host__ __device__ __forceinline__ int fdiv(int n, FastDiv f) {
 #endif
 }
 
+// CG = true: read through L2 only (ld.global.cg) -- for buffers other CTAs wrote earlier in the same kernel
+template <bool CG>
+__host__ __device__ __forceinline__ float ld_f(const float* p) {
+#ifdef __CUDA_ARCH__
+    if (CG) return __ldcg(p);
+#endif
+    return *p;
+}
+
 // synthesis along one axis: inputs LO / HI (band low / high of this axis, element stride si, extent d), outputs OUT
 // (stride so, extent t); out[o] = sum_a lo[(o + off) / 2 - a] f_lo[(o + off) % 2 + 2 a] + the same with hi
 // (Torch_Wavelet_Transform.py:39-57,91-104: conv_transpose, stride 2, cropped by off)
-template <int NT>
+template <int NT, bool CG = false>
 __host__ __device__ __forceinline__ void synth_line(const float* LO, const float* HI, int si, int d, float* OUT, int so,
                                                     int t, int off, int m0, int m1, const float (&flo)[NT],
                                                     const float (&fhi)[NT]) {
@@ -37,8 +46,8 @@ __host__ __device__ __forceinline__ void synth_line(const float* LO, const float
             const int i = m - a;
             const bool ok = (unsigned)i < (unsigned)d;
             const int ii = ok ? i * si : 0;
-            const float l = ok ? LO[ii] : 0.0f;
-            const float h = ok ? HI[ii] : 0.0f;
+            const float l = ok ? ld_f<CG>(LO + ii) : 0.0f;
+            const float h = ok ? ld_f<CG>(HI + ii) : 0.0f;
             ev = fmaf(l, flo[2 * a], ev);
             ev = fmaf(h, fhi[2 * a], ev);
             od = fmaf(l, flo[2 * a + 1], od);
@@ -50,7 +59,7 @@ __host__ __device__ __forceinline__ void synth_line(const float* LO, const float
     }
 }
 // adjoint along one axis: g_lo[i] = sum_tt G[2 i + tt - off] f_lo[tt], g_hi likewise, both from the same NT loads
-template <int NT>
+template <int NT, bool CG = false>
 __host__ __device__ __forceinline__ void adj_line(const float* G, int sg, int t, int off, float* OLO, float* OHI, int so,
                                                   int i0, int i1, const float (&flo)[NT], const float (&fhi)[NT]) {
     for (int i = i0; i < i1; ++i) {
@@ -60,7 +69,7 @@ __host__ __device__ __forceinline__ void adj_line(const float* G, int sg, int t,
         for (int tt = 0; tt < NT; ++tt) {
             const int q = q0 + tt;
             const bool ok = (unsigned)q < (unsigned)t;
-            const float gq = ok ? G[ok ? q * sg : 0] : 0.0f;
+            const float gq = ok ? ld_f<CG>(G + (ok ? q * sg : 0)) : 0.0f;
             lo = fmaf(gq, flo[tt], lo);
             hi = fmaf(gq, fhi[tt], hi);
         }

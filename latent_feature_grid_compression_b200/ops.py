@@ -405,9 +405,14 @@ def grid_step_supported(geom: Geometry) -> bool:
     return int(L.load().lfgc_grid_step_smem_bytes(ct.byref(geom.wavelet_desc))) > 0
 
 
+def grid_step_scratch_floats(geom: Geometry) -> int:
+    """Size of the optional global scratch that lets lfgc_grid_step use its 8-CTA-cluster-per-channel variant."""
+    return int(L.load().lfgc_grid_step_scratch_bytes(ct.byref(geom.wavelet_desc))) // 4
+
+
 def grid_step(geom: Geometry, grad_grids, mlp_partials, nslices: int, pstride: int, pcount: int, grid_cl, p, g, m, v,
               coeff_offs, mlp_off: int, lr_dev, step_dev, zero_grid=None, loss_out=None, beta1=0.9, beta2=0.999,
-              eps=1e-8, grad_scale=1.0, weight_l2=0.0, sync=None):
+              eps=1e-8, grad_scale=1.0, weight_l2=0.0, sync=None, scratch=None):
     """Everything of one optimiser step that is not per-sample, one launch (lfgc_grid_step): partial reduction +
     synthesis adjoint + Adam + synthesis of the updated coefficients.  ``grad_grids`` / ``mlp_partials``: lists (one
     entry per gradient source: this rank, or every data-parallel rank in rank order) of tensors or raw device
@@ -433,6 +438,9 @@ def grid_step(geom: Geometry, grad_grids, mlp_partials, nslices: int, pstride: i
     a.step_count = _p(step_dev)
     a.beta1, a.beta2, a.eps, a.grad_scale, a.weight_l2 = float(beta1), float(beta2), float(eps), float(grad_scale), \
         float(weight_l2)
+    if scratch is not None:
+        a.scratch = _p(_req(scratch, 'scratch'))
+        a.scratch_bytes = scratch.numel() * 4
     if sync is not None:
         a.rank = int(sync['rank'])
         for r, f in enumerate(sync['flags']):

@@ -168,6 +168,8 @@ class FastTrainer:
         # step (partial reduction + adjoint + Adam + next synthesis) is ONE launch, lfgc_grid_step (LFGC_GRID_STEP=0: off)
         self._gstep = gstep_ok
         self._gstep_primed = False
+        self._gstep_scratch = torch.zeros(max(ops.grid_step_scratch_floats(self.geom), 4), device=self.device) \
+            if gstep_ok else None
         self._coeff_offs = []
         off = 0
         for p in self.coeff_params:
@@ -308,7 +310,7 @@ class FastTrainer:
         common = dict(grid_cl=self.grid_cl, p=self.flat_p, g=self.flat_g, m=self.flat_m, v=self.flat_v,
                       coeff_offs=self._coeff_offs, mlp_off=self.mlp_off, lr_dev=self.lr_dev, step_dev=self.step_dev,
                       zero_grid=self.grad_grid, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
-                      weight_l2=self.weight_l2)
+                      weight_l2=self.weight_l2, scratch=self._gstep_scratch)
         if self.world == 1:
             ns = ops.train_step_partials(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl,
                                          self.mlp_flat, self.grad_grid, self.workspace, **kw)

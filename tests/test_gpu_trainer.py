@@ -157,7 +157,8 @@ def test_pipelined_host_fed_step_equals_serial_one():
 
 @pytest.mark.parametrize('wavelet,G,C,w2', [('db2', 15, 16, 0.0), ('haar', 16, 8, 0.0), ('db2', 5, 6, 0.0), ('db2', 15, 8, 1e-4),
                                            ('db2', 17, 5, 0.0)])
-def test_grid_step_path_equals_separate_kernels(wavelet, G, C, w2, monkeypatch):
+@pytest.mark.parametrize('cluster', ['1', '0'])
+def test_grid_step_path_equals_separate_kernels(wavelet, G, C, w2, cluster, monkeypatch):
     """lfgc_grid_step (partial reduction + adjoint + Adam + next synthesis in ONE launch, per-channel CTAs, separable
     levels) against the separate kernels over several optimiser steps, weight-decay term included."""
     from latent_feature_grid_compression_b200 import ops
@@ -173,6 +174,7 @@ def test_grid_step_path_equals_separate_kernels(wavelet, G, C, w2, monkeypatch):
     monkeypatch.setenv('LFGC_GRID_STEP', '0')
     ta = FastTrainer(a, vol, 3000, lr=0.008, seed=4, weight_l2=w2)
     monkeypatch.setenv('LFGC_GRID_STEP', '1')
+    monkeypatch.setenv('LFGC_GRID_STEP_CLUSTER', cluster)   # 8-CTA cluster per channel (default) / one CTA per channel
     tb = FastTrainer(b, vol, 3000, lr=0.008, seed=4, weight_l2=w2)
     assert tb._gstep and not ta._gstep
     for s in range(7):

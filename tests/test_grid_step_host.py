@@ -32,7 +32,8 @@ def hostlib(tmp_path_factory):
 
 @pytest.mark.parametrize('C,G,wavelet,n_srcs,w2', [(3, 15, 'db2', 1, 0.0), (2, 16, 'haar', 2, 0.0), (5, 17, 'db2', 1, 1e-3),
                                                  (2, 5, 'db2', 3, 0.0), (6, 12, 'db2', 1, 0.0)])
-def test_grid_step_against_the_oracle(hostlib, C, G, wavelet, n_srcs, w2):
+@pytest.mark.parametrize('nworkers', [1024, 4096])   # plans of the one-CTA and of the 8-CTA-cluster kernels
+def test_grid_step_against_the_oracle(hostlib, C, G, wavelet, n_srcs, w2, nworkers):
     from latent_feature_grid_compression_b200 import _lib as L
     from latent_feature_grid_compression_b200 import ops
     rng = np.random.default_rng(C * 100 + G)
@@ -85,8 +86,8 @@ def test_grid_step_against_the_oracle(hostlib, C, G, wavelet, n_srcs, w2):
     p0, m0, v0 = p.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
     fn = hostlib.lfgc_grid_step_host
     fn.restype = ct.c_int
-    fn.argtypes = [ct.POINTER(L.WaveletDesc), ct.c_int, ct.POINTER(L.GridStepArgs)]
-    assert fn(ct.byref(geom.wavelet_desc), Cp, ct.byref(a)) == 0
+    fn.argtypes = [ct.POINTER(L.WaveletDesc), ct.c_int, ct.POINTER(L.GridStepArgs), ct.c_int]
+    assert fn(ct.byref(geom.wavelet_desc), Cp, ct.byref(a), nworkers) == 0
 
     # oracle: adjoint of the summed grid gradient, regulariser, Adam, synthesis of the updated coefficients
     gsum = sum(gg.astype(np.float64) for gg in grad_grids)
