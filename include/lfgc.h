@@ -278,7 +278,7 @@ int lfgc_train_step_partials(const lfgc_model_desc* m, const float* volume, cons
  * evaluated separably; no grid-wide barrier.  step_count as for lfgc_adam ([0] steps taken, [1] ticket scratch = 0).
  * All pointers inside the struct are DEVICE pointers; the struct itself is read on the host at call time. */
 typedef struct lfgc_grid_step_args {
-    int32_t n_srcs;                               /* gradient sources summed in index order: 1, or the world size */
+    int32_t n_srcs;                               /* gradient sources summed in index order (normally 1) */
     const float* grad_grid[LFGC_MAX_PEERS];       /* channels-last grid gradients (G0,G1,G2,Cp), one per source */
     const float* mlp_partials[LFGC_MAX_PEERS];    /* per source: nslices rows of pstride floats (MLP gradient, loss at [pcount]) */
     int32_t nslices;                              /* rows per source (lfgc_train_step_partials' nslices_out; 1 after a reduction) */
@@ -295,17 +295,9 @@ typedef struct lfgc_grid_step_args {
     const float* lr;                              /* device scalar */
     int32_t* step_count;
     double beta1, beta2, eps, grad_scale, weight_l2;
-    /* Data-parallel barrier inside the kernel (sync_epoch != NULL; n_srcs = world size, the sources are the ranks'
-     * buffers in PEER memory): before any source is read, this rank stores its epoch (*sync_epoch + 1) into slot [rank]
-     * of every rank's flag array and waits until all n_srcs slots of its own array carry that epoch; the kernel then
-     * increments *sync_epoch.  Flags and epoch start at 0; every rank must issue the same sequence of launches.  The
-     * caller double-buffers the sources by epoch parity (a rank may only overwrite a buffer its peers read one epoch
-     * later), which is why one barrier per step is enough. */
-    int32_t rank;
-    int32_t* sync_flags[LFGC_MAX_PEERS];          /* flag array (int32[n_srcs]) of every rank, as mapped on THIS device */
-    int32_t* sync_epoch;                          /* this rank's launch counter (device int32) */
-    /* Optional global-memory scratch of lfgc_grid_step_scratch_bytes(): with it every channel is worked on by a cluster of
-     * 8 CTAs (passes through L2, hardware cluster barriers) instead of one CTA with the pyramid in shared memory. */
+    /* Optional scratch of lfgc_grid_step_scratch_bytes(): with it (and n_srcs == 1, >= 1 wavelet level) the FINEST level
+     * runs on the whole GPU -- its adjoint with the Adam update of its detail bands fused in, and its synthesis -- and only
+     * the coarser levels go through the per-channel shared-memory kernel: three dependent launches. */
     float* scratch;
     size_t scratch_bytes;
 } lfgc_grid_step_args;
@@ -313,6 +305,19 @@ int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args
 /* dynamic shared memory lfgc_grid_step needs for this pyramid; 0 = not supported (does not fit: use the separate kernels) */
 size_t lfgc_grid_step_smem_bytes(const lfgc_wavelet_desc* w);
 size_t lfgc_grid_step_scratch_bytes(const lfgc_wavelet_desc* w);
+/* 1 when lfgc_grid_step covers this pyramid (whole in shared memory, or split with the scratch), else 0 */
+int lfgc_grid_step_supported(const lfgc_wavelet_desc* w);
+
+/* Data-parallel gradient sum without a collective: out[i] = sum_r srcs[r][i] (rank order: all ranks get bit-identical sums),
+ * the sources being every rank's buffer as mapped into THIS process (peer memory, e.g. torch symmetric memory), behind a
+ * barrier inside the kernel: this rank stores its epoch (epoch[0] + 1) into slot [rank] of every rank's flag array
+ * (flags[r]: int32[n_srcs]) and waits until all n_srcs slots of its own array carry it; the kernel then publishes the new
+ * epoch (epoch: device int32[2] = {epochs so far, ticket scratch}, both 0 at the start).  Every rank must issue the same
+ * sequence of launches.  The caller double-buffers the sources by step parity, so one barrier per step suffices; `zero`
+ * (nullable, n floats: the other parity's local buffer) is cleared in the same pass.  n must be a multiple of 4 and the
+ * buffers 16-byte aligned.  Replaces the NCCL all-reduce of the path when the ranks share a node. */
+int lfgc_peer_sum(const float* const* srcs, int32_t* const* flags, int n_srcs, int rank, int32_t* epoch, float* out,
+                  float* zero, int64_t n, void* stream);
 
 /* Gradient of the KL regulariser of VariationalDropoutLoss (model/Variational_Dropout_Layer.py:54-69,115-122) added
  * in place to the mask-parameter gradients, and the per-step ramp of its weight (:57-58).  mask_params / mask_grads

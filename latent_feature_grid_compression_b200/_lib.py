@@ -49,8 +49,7 @@ class GridStepArgs(C.Structure):
                 ('grid_cl', _f), ('p', _f), ('g', _f), ('m', _f), ('v', _f), ('coeff_off', _i64 * MAX_LEVELS),
                 ('mlp_off', _i64), ('loss_out', _f), ('lr', _f), ('step_count', _f), ('beta1', C.c_double),
                 ('beta2', C.c_double), ('eps', C.c_double), ('grad_scale', C.c_double), ('weight_l2', C.c_double),
-                ('rank', C.c_int32), ('sync_flags', _f * MAX_PEERS), ('sync_epoch', _f), ('scratch', _f),
-                ('scratch_bytes', C.c_size_t)]
+                ('scratch', _f), ('scratch_bytes', C.c_size_t)]
 
 
 _SIGNATURES = {
@@ -87,6 +86,7 @@ _SIGNATURES = {
                                    C.c_int32, _f, C.c_int, _f]),
     'lfgc_deviation_stats': (C.c_int, [_f, _f, _i64, _f, _f]),
     'lfgc_adam': (C.c_int, [_f, _f, _f, _f, _i64, _f, _f, C.c_double, C.c_double, C.c_double, C.c_double, _f]),
+    'lfgc_peer_sum': (C.c_int, [C.POINTER(_f), C.POINTER(_f), C.c_int, C.c_int, _f, _f, _f, _i64, _f]),
     'lfgc_add_l2_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_add_l1_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_train_step_partials': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f,
@@ -95,6 +95,7 @@ _SIGNATURES = {
     'lfgc_grid_step': (C.c_int, [C.POINTER(WaveletDesc), C.c_int, C.POINTER(GridStepArgs), _f]),
     'lfgc_grid_step_smem_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
     'lfgc_grid_step_scratch_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
+    'lfgc_grid_step_supported': (C.c_int, [C.POINTER(WaveletDesc)]),
     'lfgc_variational_dkl_grad': (C.c_int, [_f, _f, C.c_int, C.POINTER(C.c_int64), _f, _f, C.c_double, C.c_double,
                                             C.c_float, _f]),
 }

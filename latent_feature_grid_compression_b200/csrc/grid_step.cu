@@ -1,6 +1,6 @@
 // "Grid step" kernel: everything of one optimiser step that is NOT per-sample, for mask-free models, in ONE launch:
 //
-//     [sum of the data-parallel ranks' gradient buffers, read over NVLink from peer memory]
+//     [sum of several gradient buffers, e.g. of data-parallel ranks mapped into this address space]
 //     reduction of the fused training kernel's MLP-gradient partial sums (+ the loss)
 //     synthesis adjoint, finest -> coarsest level        (autograd of Feature_Grid_Model.decode_volume,
 //                                                         model/Feature_Grid_Model.py:102-108, training/training.py:137)
@@ -35,12 +35,6 @@ namespace gstep {
 constexpr int kThreads = 1024;
 constexpr int kMaxCoeff = 8;   // coefficient tensors this kernel handles (pyramids that fit in shared memory have few)
 
-// Work distribution of one pass over the CTA's threads: ncols columns (1-D lines of the pass) x n positions along the
-// filtered dimension; with fewer columns than threads the positions are cut into `groups` ranges of `per`.
-struct PassPlan {
-    int ncols, n, groups, per;
-    FastDiv by_ncols;
-};
 
 struct LevelPlan {
     int d[3], t[3], off[3];
@@ -75,10 +69,6 @@ struct Args {
     AdamCoef c;
     float w2x2;                       // 2 * weight_l2
     int n_mlp_ctas;
-    float* scratch;                   // cluster variant: per-channel [sL | sX | sY | sC] floats in global memory
-    int rank;                         // data-parallel peer barrier (sync_epoch != nullptr): this rank's index, ...
-    int* sync_flags[LFGC_MAX_PEERS];  // ... every rank's flag array (int[n_srcs], peer memory; [rank] is the local one)
-    int* sync_epoch;                  // ... and this rank's launch counter (device int, monotonic)
 };
 
 // Shared-memory (or, in the host test, heap) partitions of one channel
@@ -180,30 +170,6 @@ __host__ __device__ __forceinline__ int coeff_elems(const Args& A, int l) {
     }
 
 #ifdef __CUDACC__
-// Data-parallel barrier INSIDE the kernel (no separate collective, no extra launch): every rank's kernel announces its
-// epoch to all ranks' flag arrays with a system-scope release store and waits until every rank has announced the same
-// epoch.  A rank reaches this point only after its own per-sample kernel (same stream) has completed, so once the wait
-// is over every rank's gradient buffer of this step is complete and visible over NVLink.  Epochs only grow, so there is
-// nothing to reset; a lost peer traps after ~2 s instead of hanging the device.
-__device__ __forceinline__ void peer_barrier(const Args& A, int tid) {
-    const int e = *reinterpret_cast<volatile int*>(A.sync_epoch) + 1;
-    if (tid < A.n_srcs) {
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(A.sync_flags[tid] + A.rank), "r"(e) : "memory");
-        }
-        const int* mine = A.sync_flags[A.rank] + tid;
-        const long long t0 = clock64();
-        for (;;) {
-            int seen;
-            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-            if (seen >= e) break;
-            if (clock64() - t0 > 4000000000ll) __trap();
-        }
-    }
-    __syncthreads();
-}
-
 template <int NT>
 __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_constant__ Args A) {
     LFGC_PDL_PROLOGUE();
@@ -211,7 +177,6 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
     __shared__ float s_step_size, s_bc2_sqrt;
     __shared__ int s_step;
     const int tid = threadIdx.x;
-    if (A.sync_epoch) peer_barrier(A, tid);
     if (tid == 0) {
         const int step = *reinterpret_cast<volatile int*>(A.step) + 1;
         float step_size, bc2_sqrt;
@@ -352,187 +317,18 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
         const int ticket = atomicAdd(A.step + 1, 1);
         if (ticket == (int)gridDim.x - 1) {
             A.step[1] = 0;
-            if (A.sync_epoch) *A.sync_epoch += 1;
             __threadfence();
             A.step[0] = s_step;
         }
     }
 }
 
-// ---- cluster variant ------------------------------------------------------------------------------------------------------------
-// One CTA per channel executes ~60 k warp instructions (the passes are issue-bound: 29 us measured for the kernel above at
-// C16/G15, no better than the launches it replaces).  Here a thread-block CLUSTER of 8 CTAs (8 SMs) works on each channel:
-// the same passes, the same plans scaled to 8 x 512 workers, but the per-channel buffers live in global memory (L2) and
-// the phases are separated by hardware cluster barriers (barrier.cluster, release / acquire at cluster scope).  With
-// <= 1 position per thread a pass is one L2 round trip plus a barrier instead of ~1600 issue cycles.
-constexpr int kClusterSize = 8;
-constexpr int kClusterThreads = 512;
-
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ unsigned cluster_ctarank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-
-#define LFGC_CL_PASS(fn, plan_)            \
-    LFGC_RUN_PASS(fn, plan_, wid, nworkers) \
-    cluster_sync_all();
-
-template <int NT>
-__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClusterThreads, 1)
-    grid_step_cluster_kernel(const __grid_constant__ Args A) {
-    LFGC_PDL_PROLOGUE();
-    __shared__ float s_step_size, s_bc2_sqrt;
-    __shared__ int s_step;
-    __shared__ float s_red[kClusterThreads];
-    const int tid = threadIdx.x;
-    if (A.sync_epoch) peer_barrier(A, tid);
-    if (tid == 0) {
-        const int step = *reinterpret_cast<volatile int*>(A.step) + 1;
-        float step_size, bc2_sqrt;
-        adam_step_scalars(A.c, step, *A.lr, step_size, bc2_sqrt);
-        s_step = step;
-        s_step_size = step_size;
-        s_bc2_sqrt = bc2_sqrt;
-    }
-    __syncthreads();
-    const int c = blockIdx.x / kClusterSize;
-    const int rank = (int)cluster_ctarank();
-    using PassT = Pass<NT, true>;
-    if (c < A.C) {
-        constexpr int nworkers = kClusterSize * kClusterThreads;
-        const int wid = rank * kClusterThreads + tid;
-        Bufs S;
-        S.L = A.scratch + (size_t)c * ((size_t)A.sL + A.sX + A.sY + A.sC);
-        S.X = S.L + A.sL;
-        S.Y = S.X + A.sX;
-        S.Cg = S.Y + A.sY;
-        float flo[NT], fhi[NT];
-#pragma unroll
-        for (int i = 0; i < NT; ++i) {
-            flo[i] = A.lo[i];
-            fhi[i] = A.hi[i];
-        }
-        const int last = A.n_coeff - 1;
-        const int nvox = last >= 1 ? A.lv[last].t[0] * A.lv[last].t[1] * A.lv[last].t[2] : A.d0[0] * A.d0[1] * A.d0[2];
-        for (int i = wid; i < nvox; i += nworkers) {
-            const long long a = (long long)i * A.Cp + c;
-            float gsum = __ldcv(A.grad_grid[0] + a);
-            for (int r = 1; r < A.n_srcs; ++r) gsum += __ldcv(A.grad_grid[r] + a);
-            S.L[i] = gsum;
-            if (A.zero_grid) A.zero_grid[a] = 0.0f;
-        }
-        if (A.zero_grid && c == A.C - 1) {
-            const int np = A.Cp - A.C;
-            for (int i = wid; i < nvox * np; i += nworkers) A.zero_grid[(long long)(i / np) * A.Cp + A.C + i % np] = 0.0f;
-        }
-        cluster_sync_all();
-        for (int l = last; l >= 1; --l) {
-            const LevelPlan& P = A.lv[l];
-            LFGC_CL_PASS(az, P.az)
-            LFGC_CL_PASS(ay, P.ay)
-            LFGC_CL_PASS(ax, P.ax)
-        }
-        const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-        for (int l = 0; l <= last; ++l) {
-            const int n_l = coeff_elems(A, l);
-            float* slots = l == 0 ? S.L : S.Cg + A.lv[l].cg_off;
-            const long long base = A.coeff_off[l] + (long long)c * n_l;
-            for (int e = wid; e < n_l; e += nworkers) {
-                float pi = A.p[base + e], mi = A.m[base + e], vi = A.v[base + e];
-                const float gi = fmaf(A.w2x2, pi, __ldcg(slots + e));
-                adam_update(pi, gi, mi, vi, A.c, step_size, bc2_sqrt);
-                A.p[base + e] = pi;
-                A.m[base + e] = mi;
-                A.v[base + e] = vi;
-                A.g[base + e] = gi;
-                slots[e] = pi;
-            }
-        }
-        cluster_sync_all();
-        for (int l = 1; l <= last; ++l) {
-            const LevelPlan& P = A.lv[l];
-            LFGC_CL_PASS(sx, P.sx)
-            LFGC_CL_PASS(sy, P.sy)
-            LFGC_CL_PASS(sz, P.sz)
-        }
-        for (int i = wid; i < nvox; i += nworkers) A.grid_cl[(long long)i * A.Cp + c] = __ldcg(S.L + i);
-        if (c == A.C - 1) {
-            const int np = A.Cp - A.C;
-            for (int i = wid; i < nvox * np; i += nworkers) A.grid_cl[(long long)(i / np) * A.Cp + A.C + i % np] = 0.0f;
-        }
-    } else {
-        // MLP block, 64 parameters x 8 slice groups per CTA (see grid_step_kernel)
-        constexpr int PX = 64, SY = kClusterThreads / PX;
-        const int px = tid % PX, sy = tid / PX;
-        const int j = ((c - A.C) * kClusterSize + rank) * PX + px;
-        float acc = 0.0f;
-        if (j <= A.pcount) {
-            for (int r = 0; r < A.n_srcs; ++r) {
-                const float* src = A.mlp_partials[r] + j;
-                for (int b = sy; b < A.nslices; b += 4 * SY) {
-                    float t0 = __ldcv(src + (size_t)b * A.pstride), t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
-                    if (b + SY < A.nslices) t1 = __ldcv(src + (size_t)(b + SY) * A.pstride);
-                    if (b + 2 * SY < A.nslices) t2 = __ldcv(src + (size_t)(b + 2 * SY) * A.pstride);
-                    if (b + 3 * SY < A.nslices) t3 = __ldcv(src + (size_t)(b + 3 * SY) * A.pstride);
-                    acc += (t0 + t1) + (t2 + t3);
-                }
-            }
-        }
-        s_red[sy * PX + px] = acc;
-        __syncthreads();
-        if (sy == 0 && j <= A.pcount) {
-            float t = 0.0f;
-#pragma unroll
-            for (int g = 0; g < SY; ++g) t += s_red[g * PX + px];
-            if (j < A.pcount) {
-                const long long i = A.mlp_off + j;
-                float pi = A.p[i], mi = A.m[i], vi = A.v[i];
-                adam_update(pi, t, mi, vi, A.c, s_step_size, s_bc2_sqrt);
-                A.p[i] = pi;
-                A.m[i] = mi;
-                A.v[i] = vi;
-                A.g[i] = t;
-            } else if (A.loss_out) {
-                A.loss_out[0] = t;
-            }
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const int ticket = atomicAdd(A.step + 1, 1);
-        if (ticket == (int)gridDim.x - 1) {
-            A.step[1] = 0;
-            if (A.sync_epoch) *A.sync_epoch += 1;
-            __threadfence();
-            A.step[0] = s_step;
-        }
-    }
-}
 #endif
 
 }  // namespace gstep
 }  // namespace lfgc
 
 using namespace lfgc;
-
-static gstep::PassPlan make_plan(int ncols, int n, int nworkers) {
-    gstep::PassPlan p;
-    p.ncols = ncols;
-    p.n = n;
-    int g = ncols > 0 ? nworkers / ncols : 1;
-    if (g < 1) g = 1;
-    if (g > n) g = n > 0 ? n : 1;
-    p.groups = g;
-    p.per = (n + g - 1) / g;
-    p.by_ncols = make_fastdiv((unsigned)(ncols > 0 ? ncols : 1));
-    return p;
-}
 
 // Level plans and shared-memory partition sizes; returns the total in floats
 static size_t gstep_layout(gstep::Args& A, const lfgc_wavelet_desc* w, int nworkers = gstep::kThreads) {
@@ -603,31 +399,53 @@ extern "C" size_t lfgc_grid_step_smem_bytes(const lfgc_wavelet_desc* w) {
     return bytes <= (size_t)cap - 64 ? bytes : 0;
 }
 
+// Split path (n_coeff >= 2): the FINEST level runs on the whole GPU with the direct-sum kernels of wavelet.cu -- its adjoint
+// with the Adam update of its detail bands in the epilogue, its synthesis at the end -- and only the coarser levels go
+// through the per-channel shared-memory kernel.  Three dependent launches instead of six, and the one-SM-per-channel part
+// shrinks 8x.  (Measured on B200, C16/G15: the whole pyramid in one CTA per channel takes 29-32 us, issue-bound on 16 of
+// 148 SMs; a variant with a cluster of 8 CTAs per channel and the buffers in L2 took 52 us, every pass paying two L2 round
+// trips; the six separate launches 24 us.)
+namespace lfgc {
+int wavelet_finest_bwd_adam(const lfgc_wavelet_desc* w, const float* grad_grid_cl, int Cp, float* low_grad_out, float* p_l,
+                            float* g_l, float* m_l, float* v_l, const float* lr, const int* step, const AdamCoef& coef,
+                            float w2x2, cudaStream_t st);
+int wavelet_finest_fwd(const lfgc_wavelet_desc* w, const float* low_cl, const float* coeff_l, float* grid_cl, int Cp,
+                       float* also_zero, cudaStream_t st);
+}
+
+static size_t finest_low_elems(const lfgc_wavelet_desc* w) {
+    const int l = w->n_coeff - 1;
+    return (size_t)w->C * w->dims[l][0] * w->dims[l][1] * w->dims[l][2];
+}
+
 extern "C" size_t lfgc_grid_step_scratch_bytes(const lfgc_wavelet_desc* w) {
-    if (gstep_check_desc(w)) return 0;
-    gstep::Args A;
-    return (size_t)w->C * gstep_layout(A, w) * sizeof(float);
+    if (!w || w->n_coeff < 2 || w->n_coeff > LFGC_MAX_LEVELS) return 0;
+    return 2 * finest_low_elems(w) * sizeof(float);
 }
 
-// the cluster variant (8 CTAs per channel, buffers in global memory) runs when the caller provides its scratch;
-// LFGC_GRID_STEP_CLUSTER=0 forces the one-CTA-per-channel kernel
-static bool gstep_use_cluster(const lfgc_wavelet_desc* w, const lfgc_grid_step_args* a) {
-    if (!a->scratch || a->scratch_bytes < lfgc_grid_step_scratch_bytes(w)) return false;
-    const char* e = getenv("LFGC_GRID_STEP_CLUSTER");
-    return !(e && e[0] == '0');
+// 1: lfgc_grid_step can run this pyramid (whole, or split with the scratch above); 0: use the separate kernels
+extern "C" int lfgc_grid_step_supported(const lfgc_wavelet_desc* w) {
+    if (!w) return 0;
+    if (lfgc_grid_step_smem_bytes(w) > 0) return 1;
+    if (w->n_coeff >= 2 && w->n_coeff <= LFGC_MAX_LEVELS) {
+        lfgc_wavelet_desc t = *w;
+        t.n_coeff = w->n_coeff - 1;
+        return lfgc_grid_step_smem_bytes(&t) > 0 ? 1 : 0;
+    }
+    return 0;
 }
 
-static int gstep_fill(gstep::Args& A, const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a, int nworkers) {
+static int gstep_fill(gstep::Args& A, const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a, int nworkers,
+                      bool internal = false) {
     const int rc = gstep_check_desc(w);
     if (rc) return rc;
     if (!a) return fail(LFGC_E_INVALID, "grid_step: null arguments");
-    if (Cp < w->C || (Cp & 3)) return fail(LFGC_E_INVALID, "Cp=%d must be a multiple of 4 and >= C=%d", Cp, w->C);
+    if (!internal && (Cp < w->C || (Cp & 3))) return fail(LFGC_E_INVALID, "Cp=%d must be a multiple of 4 and >= C=%d", Cp, w->C);
     if (a->n_srcs < 1 || a->n_srcs > LFGC_MAX_PEERS) return fail(LFGC_E_UNSUPPORTED, "grid_step: %d gradient sources (1..%d)", a->n_srcs, LFGC_MAX_PEERS);
     if (!a->grid_cl || !a->p || !a->g || !a->m || !a->v || !a->lr || !a->step_count || a->pcount < 0 || a->pstride < a->pcount + 1 || a->nslices < 1)
         return fail(LFGC_E_INVALID, "grid_step: bad buffer arguments");
     gstep_layout(A, w, nworkers);
     A.Cp = Cp;
-    A.scratch = a->scratch;
     A.n_srcs = a->n_srcs;
     for (int r = 0; r < LFGC_MAX_PEERS; ++r) {
         A.grad_grid[r] = r < a->n_srcs ? a->grad_grid[r] : nullptr;
@@ -655,39 +473,58 @@ static int gstep_fill(gstep::Args& A, const lfgc_wavelet_desc* w, int Cp, const 
     A.c = make_adam_coef(a->beta1, a->beta2, a->eps, a->grad_scale);
     A.w2x2 = (float)(2.0 * a->weight_l2);
     A.n_mlp_ctas = a->pcount > 0 ? (a->pcount + 1 + 63) / 64 : 0;   // 64 parameters per CTA (see the kernel)
-    A.rank = a->rank;
-    A.sync_epoch = a->sync_epoch;
-    for (int r = 0; r < LFGC_MAX_PEERS; ++r) {
-        A.sync_flags[r] = (a->sync_epoch && r < a->n_srcs) ? a->sync_flags[r] : nullptr;
-        if (a->sync_epoch && r < a->n_srcs && !A.sync_flags[r]) return fail(LFGC_E_INVALID, "grid_step: flag array of rank %d is null", r);
-    }
-    if (a->sync_epoch && (a->rank < 0 || a->rank >= a->n_srcs)) return fail(LFGC_E_INVALID, "grid_step: bad rank %d", a->rank);
     return LFGC_OK;
 }
 
-extern "C" int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a, void* stream) {
-    gstep::Args A;
-    if (a && w && gstep_check_desc(w) == LFGC_OK && gstep_use_cluster(w, a)) {
-        const int rc = gstep_fill(A, w, Cp, a, gstep::kClusterSize * gstep::kClusterThreads);
-        if (rc) return rc;
-        void (*kc)(const gstep::Args) = gstep::grid_step_cluster_kernel<4>;
-        if (w->n_coeff == 1 || w->n_taps == 2) kc = gstep::grid_step_cluster_kernel<2>;
-        const int mlp_clusters = (A.n_mlp_ctas + gstep::kClusterSize - 1) / gstep::kClusterSize;
-        (void)launch_pdl(kc, dim3((unsigned)((A.C + mlp_clusters) * gstep::kClusterSize)), dim3(gstep::kClusterThreads), (size_t)0,
-                         (cudaStream_t)stream, A);
-        LFGC_LAUNCH_OK();
-        return LFGC_OK;
-    }
-    const int rc = gstep_fill(A, w, Cp, a, gstep::kThreads);
-    if (rc) return rc;
+static int gstep_launch(const gstep::Args& A, const lfgc_wavelet_desc* w, cudaStream_t st) {
     const size_t smem = lfgc_grid_step_smem_bytes(w);
     if (smem == 0) return fail(LFGC_E_UNSUPPORTED, "grid_step: the per-channel wavelet pyramid does not fit in shared memory");
     void (*kern)(const gstep::Args) = gstep::grid_step_kernel<4>;
     if (w->n_coeff == 1 || w->n_taps == 2) kern = gstep::grid_step_kernel<2>;
     LFGC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    (void)launch_pdl(kern, dim3((unsigned)(A.C + A.n_mlp_ctas)), dim3(gstep::kThreads), smem, (cudaStream_t)stream, A);
+    (void)launch_pdl(kern, dim3((unsigned)(A.C + A.n_mlp_ctas)), dim3(gstep::kThreads), smem, st, A);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
+}
+
+extern "C" int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a, void* stream) {
+    gstep::Args A;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = gstep_check_desc(w);
+    if (rc) return rc;
+    if (!a) return fail(LFGC_E_INVALID, "grid_step: null arguments");
+    bool split = w->n_coeff >= 2 && a->n_srcs == 1 && a->scratch && a->scratch_bytes >= lfgc_grid_step_scratch_bytes(w);
+    if (const char* e = getenv("LFGC_GRID_STEP_SPLIT")) split = split && e[0] != '0';
+    if (!split) {
+        rc = gstep_fill(A, w, Cp, a, gstep::kThreads);
+        if (rc) return rc;
+        return gstep_launch(A, w, st);
+    }
+    if (Cp < w->C || (Cp & 3)) return fail(LFGC_E_INVALID, "Cp=%d must be a multiple of 4 and >= C=%d", Cp, w->C);
+    if (!a->grad_grid[0] || !a->grid_cl || !a->p || !a->g || !a->m || !a->v || !a->lr || !a->step_count)
+        return fail(LFGC_E_INVALID, "grid_step: bad buffer arguments");
+    const int last = w->n_coeff - 1;
+    float* low_grad = a->scratch;
+    float* low_val = a->scratch + finest_low_elems(w);
+    const long long off = a->coeff_off[last];
+    // (1) finest adjoint + Adam of the finest detail bands (reads step_count[0]; the kernel of (2) publishes the increment)
+    rc = wavelet_finest_bwd_adam(w, a->grad_grid[0], Cp, low_grad, a->p + off, a->g + off, a->m + off, a->v + off, a->lr,
+                                 a->step_count, make_adam_coef(a->beta1, a->beta2, a->eps, a->grad_scale),
+                                 (float)(2.0 * a->weight_l2), st);
+    if (rc) return rc;
+    // (2) the coarser levels, per channel in shared memory, plus the MLP block; channels-last intermediates of stride C
+    lfgc_wavelet_desc wt = *w;
+    wt.n_coeff = last;
+    lfgc_grid_step_args at = *a;
+    at.grad_grid[0] = low_grad;
+    at.zero_grid = nullptr;
+    at.grid_cl = low_val;
+    rc = gstep_fill(A, &wt, w->C, &at, gstep::kThreads, true);
+    if (rc) return rc;
+    rc = gstep_launch(A, &wt, st);
+    if (rc) return rc;
+    // (3) finest synthesis from the updated low-pass and detail bands; clears the gradient accumulator
+    return wavelet_finest_fwd(w, low_val, a->p + off, a->grid_cl, Cp, a->zero_grid, st);
 }
 
 #ifdef LFGC_GRID_STEP_HOST_TEST

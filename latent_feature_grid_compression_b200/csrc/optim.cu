@@ -44,6 +44,68 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Data-parallel gradient sum WITHOUT a collective: out[i] = sum over the ranks (in rank order, so every rank forms
+// bit-identical sums) of their gradient buffers, read straight over NVLink from peer memory (torch symmetric memory
+// provides the mapping), behind a barrier that lives INSIDE the kernel: every rank's kernel announces its epoch to all
+// ranks' flag arrays with a system-scope release store and waits until every rank has announced the same epoch.  A rank
+// reaches this point only after its own per-sample kernel (same stream) has completed, so once the wait is over every
+// rank's buffer of this step is complete and visible.  Epochs only grow: nothing to reset; a lost peer traps after ~2 s
+// instead of hanging the device.  The caller double-buffers the sources by step parity (a rank may only overwrite a buffer
+// its peers read one epoch later), which is why ONE barrier per step is enough; `zero` (the other parity's local buffer)
+// is cleared here for the next step.  For the 0.23 MB message of the shipped configurations this replaces an NCCL
+// all-reduce whose cost is all latency (+18 us per step at 2 GPUs, +36 us at 8, SCALE_r01).
+struct PeerSumArgs {
+    const float* src[LFGC_MAX_PEERS];
+    int* flags[LFGC_MAX_PEERS];
+    int n_srcs, rank;
+    int* epoch;
+    float* out;
+    float* zero;
+    long long n;
+};
+
+__global__ void __launch_bounds__(512) peer_sum_kernel(const __grid_constant__ PeerSumArgs A) {
+    LFGC_PDL_PROLOGUE();
+    const int tid = threadIdx.x;
+    const int e = *reinterpret_cast<volatile int*>(A.epoch) + 1;
+    if (tid < A.n_srcs) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(A.flags[tid] + A.rank), "r"(e) : "memory");
+        }
+        const int* mine = A.flags[A.rank] + tid;
+        const long long t0 = clock64();
+        for (;;) {
+            int seen;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+            if (seen >= e) break;
+            if (clock64() - t0 > 4000000000ll) __trap();
+        }
+    }
+    __syncthreads();
+    const long long n4 = A.n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 acc = __ldcv(reinterpret_cast<const float4*>(A.src[0]) + i);   // peer data changes every step: never from L1
+        for (int r = 1; r < A.n_srcs; ++r) {
+            const float4 v = __ldcv(reinterpret_cast<const float4*>(A.src[r]) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(A.out)[i] = acc;
+        if (A.zero) reinterpret_cast<float4*>(A.zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // publish the new epoch once every CTA has read the old one (ticket in epoch[1])
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(A.epoch + 1, 1);
+        if (ticket == (int)gridDim.x - 1) {
+            A.epoch[1] = 0;
+            __threadfence();
+            A.epoch[0] = e;
+        }
+    }
+}
+
 __global__ void add_l2_grad_kernel(float* __restrict__ g, const float* __restrict__ p, int64_t n, float w2) {
     LFGC_PDL_PROLOGUE();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,6 +191,30 @@ extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n
     const int64_t blocks = n == 0 ? 1 : (n + 255) / 256;
     (void)launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), st, p, g, m, v, n, lr, step_count,
                      make_adam_coef(beta1, beta2, eps, grad_scale));
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
+
+extern "C" int lfgc_peer_sum(const float* const* srcs, int32_t* const* flags, int n_srcs, int rank, int32_t* epoch, float* out,
+                             float* zero, int64_t n, void* stream) {
+    if (!srcs || !flags || !epoch || !out || n < 0 || (n & 3)) return fail(LFGC_E_INVALID, "peer_sum: bad arguments (n must be a multiple of 4)");
+    if (n_srcs < 1 || n_srcs > LFGC_MAX_PEERS || rank < 0 || rank >= n_srcs) return fail(LFGC_E_UNSUPPORTED, "peer_sum: %d sources, rank %d", n_srcs, rank);
+    PeerSumArgs A = {};
+    for (int r = 0; r < n_srcs; ++r) {
+        if (!srcs[r] || !flags[r]) return fail(LFGC_E_INVALID, "peer_sum: pointer of rank %d is null", r);
+        A.src[r] = srcs[r];
+        A.flags[r] = flags[r];
+    }
+    A.n_srcs = n_srcs;
+    A.rank = rank;
+    A.epoch = epoch;
+    A.out = out;
+    A.zero = zero;
+    A.n = n;
+    int blocks = (int)((n / 4 + 511) / 512);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 2 * sm_count()) blocks = 2 * sm_count();   // all CTAs must be co-resident while they wait on the flags
+    (void)launch_pdl(peer_sum_kernel, dim3((unsigned)blocks), dim3(512), (size_t)0, (cudaStream_t)stream, A);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }

@@ -255,6 +255,15 @@ struct LevelBwdArgs {
     int d[3], t[3], off[3];
     int ntaps;
     float lo[LFGC_MAX_TAPS], hi[LFGC_MAX_TAPS];
+    // optional Adam epilogue on the detail bands of this level (lfgc_grid_step, split path): the thread that has just
+    // formed the gradient of a coefficient updates it, so the gradient never makes a round trip through memory
+    float* ap;             // coefficient tensor l inside the flat parameter buffer (null: no epilogue) ...
+    float* am;             // ... and its Adam moments
+    float* av;
+    const float* lr;
+    const int* step;       // optimiser steps taken so far (read only here; published by the grid-step kernel)
+    AdamCoef coef;
+    float w2x2;            // 2 * weight_l2 (SmallifyLoss weight term)
 };
 
 // One thread per (sub-band k, position b, channel c), channel fastest.  d mult[k][b] = sum_c coeff * g is reduced
@@ -262,6 +271,16 @@ struct LevelBwdArgs {
 template <int NT>
 __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
     LFGC_PDL_PROLOGUE();
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (A.ap) {
+        if (threadIdx.x == 0) {
+            float step_size, bc2_sqrt;
+            adam_step_scalars(A.coef, *reinterpret_cast<const volatile int*>(A.step) + 1, *A.lr, step_size, bc2_sqrt);
+            s_step_size = step_size;
+            s_bc2_sqrt = bc2_sqrt;
+        }
+        __syncthreads();
+    }
     const int64_t dvol = (int64_t)A.d[0] * A.d[1] * A.d[2];
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = idx < 8 * dvol * A.C;
@@ -336,8 +355,18 @@ __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
         } else {
             const int64_t o = ((int64_t)c * 7 + (k - 1)) * dvol + b;
             if (A.gmult_high) { contrib = A.c_high[o] * g; gm = A.gmult_high + (int64_t)(k - 1) * dvol + b; }
-            const float v = A.gm_high ? g * A.gm_high[(int64_t)(k - 1) * dvol + b] : g;
-            A.g_high[o] = A.accumulate ? A.g_high[o] + v : v;
+            float v = A.gm_high ? g * A.gm_high[(int64_t)(k - 1) * dvol + b] : g;
+            if (A.ap) {
+                float pi = A.ap[o], mi = A.am[o], vi = A.av[o];
+                v = fmaf(A.w2x2, pi, v);
+                adam_update(pi, v, mi, vi, A.coef, s_step_size, s_bc2_sqrt);
+                A.ap[o] = pi;
+                A.am[o] = mi;
+                A.av[o] = vi;
+                A.g_high[o] = v;
+            } else {
+                A.g_high[o] = A.accumulate ? A.g_high[o] + v : v;
+            }
         }
     }
     if (A.gmult_low == nullptr && A.gmult_high == nullptr) return;  // uniform across the grid
@@ -459,6 +488,70 @@ static size_t intermediate_elems(const lfgc_wavelet_desc* w) {
         if (e > mx) mx = e;
     }
     return mx;
+}
+
+static void fill_level_geometry(const lfgc_wavelet_desc* w, int l, int (&d)[3], int (&t)[3], int (&off)[3], float (&lo)[LFGC_MAX_TAPS],
+                                float (&hi)[LFGC_MAX_TAPS]) {
+    for (int a = 0; a < 3; ++a) {
+        d[a] = w->dims[l][a];
+        t[a] = w->target[l][a];
+        off[a] = (2 * d[a] + w->n_taps - 2 - t[a]) / 2;  // floor(delta / 2), Torch_Wavelet_Transform.py:71
+    }
+    for (int i = 0; i < LFGC_MAX_TAPS; ++i) {
+        lo[i] = w->rec_lo[i];
+        hi[i] = w->rec_hi[i];
+    }
+}
+
+// Finest-level adjoint with the Adam update of that level's detail bands in its epilogue (mask-free).  grad_grid_cl:
+// (t0,t1,t2,Cp) channels-last; low_grad_out: gradient of the level's low-pass input, channels-last (d0,d1,d2,C).
+int wavelet_finest_bwd_adam(const lfgc_wavelet_desc* w, const float* grad_grid_cl, int Cp, float* low_grad_out, float* p_l,
+                            float* g_l, float* m_l, float* v_l, const float* lr, const int* step, const AdamCoef& coef,
+                            float w2x2, cudaStream_t st) {
+    const int l = w->n_coeff - 1;
+    LevelBwdArgs A = {};
+    A.gout = grad_grid_cl;
+    A.Cs = Cp;
+    A.low_is_coeff = 0;
+    A.c_low = nullptr;
+    A.c_high = p_l;
+    A.g_low = low_grad_out;
+    A.g_high = g_l;
+    A.accumulate = 0;
+    A.C = w->C;
+    A.ntaps = w->n_taps;
+    fill_level_geometry(w, l, A.d, A.t, A.off, A.lo, A.hi);
+    A.ap = p_l;
+    A.am = m_l;
+    A.av = v_l;
+    A.lr = lr;
+    A.step = step;
+    A.coef = coef;
+    A.w2x2 = w2x2;
+    const int64_t total = 8 * (int64_t)A.d[0] * A.d[1] * A.d[2] * A.C;
+    launch_idwt_level_bwd(A, total, st);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
+
+// Finest-level synthesis from a channels-last low-pass input (d0,d1,d2,C) and the level's detail bands.
+int wavelet_finest_fwd(const lfgc_wavelet_desc* w, const float* low_cl, const float* coeff_l, float* grid_cl, int Cp,
+                       float* also_zero, cudaStream_t st) {
+    const int l = w->n_coeff - 1;
+    LevelArgs A = {};
+    A.low = low_cl;
+    A.high = coeff_l;
+    A.out = grid_cl;
+    A.also_zero = also_zero;
+    A.low_cl = 1;
+    A.C = w->C;
+    A.Cs = Cp;
+    A.ntaps = w->n_taps;
+    fill_level_geometry(w, l, A.d, A.t, A.off, A.lo, A.hi);
+    const int64_t total = (int64_t)A.t[0] * A.t[1] * A.t[2] * A.Cs;
+    launch_idwt_level(A, total, st);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
 }
 
 }  // namespace lfgc
@@ -596,7 +689,7 @@ extern "C" int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_gri
     float* buf[2] = {scratch, scratch ? scratch + inter : nullptr};
     const float* gout = grad_grid_cl;
     for (int l = w->n_coeff - 1; l >= 1; --l) {
-        LevelBwdArgs A;
+        LevelBwdArgs A = {};
         A.gout = gout;
         A.Cs = (l == w->n_coeff - 1) ? Cp : w->C;
         A.low_is_coeff = (l == 1) ? 1 : 0;

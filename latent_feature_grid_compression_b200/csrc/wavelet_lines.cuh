@@ -23,6 +23,26 @@ __host__ __device__ __forceinline__ int fdiv(int n, FastDiv f) {
 #endif
 }
 
+// Work distribution of one pass over `nworkers` threads: ncols columns (1-D lines of the pass) x n positions along the
+// filtered dimension; with fewer columns than workers the positions are cut into `groups` ranges of `per`.
+// unit u -> group = u / ncols, column = u % ncols (column fastest: neighbouring threads work on neighbouring lines).
+struct PassPlan {
+    int ncols, n, groups, per;
+    FastDiv by_ncols;
+};
+inline PassPlan make_plan(int ncols, int n, int nworkers) {
+    PassPlan p;
+    p.ncols = ncols;
+    p.n = n;
+    int g = ncols > 0 ? nworkers / ncols : 1;
+    if (g < 1) g = 1;
+    if (g > n) g = n > 0 ? n : 1;
+    p.groups = g;
+    p.per = (n + g - 1) / g;
+    p.by_ncols = make_fastdiv((unsigned)(ncols > 0 ? ncols : 1));
+    return p;
+}
+
 // CG = true: read through L2 only (ld.global.cg) -- for buffers other CTAs wrote earlier in the same kernel
 template <bool CG>
 __host__ __device__ __forceinline__ float ld_f(const float* p) {

@@ -400,24 +400,34 @@ def train_step_partials(geom: Geometry, volume, n: int, seed: int, sample_offset
     return int(ns.value)
 
 
+def peer_sum(src_addrs, flag_addrs, rank: int, epoch, out, zero=None):
+    """out = sum over the ranks' buffers (raw device addresses, peer memory) behind the in-kernel barrier
+    (lfgc_peer_sum); ``epoch``: int32[2] device tensor; ``zero``: buffer cleared in the same pass."""
+    lib = L.load()
+    _req(epoch, 'epoch', torch.int32)
+    _req(out, 'out')
+    L.check(lib.lfgc_peer_sum(L.ptr_array([int(a) for a in src_addrs]), L.ptr_array([int(a) for a in flag_addrs]),
+                              len(src_addrs), int(rank), _p(epoch), _p(out), _p(zero), out.numel(), _stream()),
+            'lfgc_peer_sum')
+
+
 def grid_step_supported(geom: Geometry) -> bool:
-    """True when the per-channel wavelet pyramid of this model fits in shared memory (lfgc_grid_step_smem_bytes)."""
-    return int(L.load().lfgc_grid_step_smem_bytes(ct.byref(geom.wavelet_desc))) > 0
+    """True when lfgc_grid_step covers this model's wavelet pyramid (lfgc_grid_step_supported)."""
+    return int(L.load().lfgc_grid_step_supported(ct.byref(geom.wavelet_desc))) == 1
 
 
 def grid_step_scratch_floats(geom: Geometry) -> int:
-    """Size of the optional global scratch that lets lfgc_grid_step use its 8-CTA-cluster-per-channel variant."""
+    """Size of the scratch that lets lfgc_grid_step run the finest wavelet level on the whole GPU (split path)."""
     return int(L.load().lfgc_grid_step_scratch_bytes(ct.byref(geom.wavelet_desc))) // 4
 
 
 def grid_step(geom: Geometry, grad_grids, mlp_partials, nslices: int, pstride: int, pcount: int, grid_cl, p, g, m, v,
               coeff_offs, mlp_off: int, lr_dev, step_dev, zero_grid=None, loss_out=None, beta1=0.9, beta2=0.999,
-              eps=1e-8, grad_scale=1.0, weight_l2=0.0, sync=None, scratch=None):
+              eps=1e-8, grad_scale=1.0, weight_l2=0.0, scratch=None):
     """Everything of one optimiser step that is not per-sample, one launch (lfgc_grid_step): partial reduction +
     synthesis adjoint + Adam + synthesis of the updated coefficients.  ``grad_grids`` / ``mlp_partials``: lists (one
     entry per gradient source: this rank, or every data-parallel rank in rank order) of tensors or raw device
-    addresses.  ``sync = dict(rank=, flags=[address of every rank's flag array], epoch=<int32 device tensor>)`` turns
-    on the in-kernel peer barrier (sources in peer memory)."""
+    addresses.  ``scratch`` (grid_step_scratch_floats) enables the split path: finest level on the whole GPU."""
     lib = L.load()
     _req(step_dev, 'step', torch.int32)
     a = L.GridStepArgs()
@@ -441,11 +451,6 @@ def grid_step(geom: Geometry, grad_grids, mlp_partials, nslices: int, pstride: i
     if scratch is not None:
         a.scratch = _p(_req(scratch, 'scratch'))
         a.scratch_bytes = scratch.numel() * 4
-    if sync is not None:
-        a.rank = int(sync['rank'])
-        for r, f in enumerate(sync['flags']):
-            a.sync_flags[r] = int(f)
-        a.sync_epoch = _p(_req(sync['epoch'], 'epoch', torch.int32))
     L.check(lib.lfgc_grid_step(ct.byref(geom.wavelet_desc), geom.Cp, ct.byref(a), _stream()), 'lfgc_grid_step')
 
 

@@ -134,8 +134,8 @@ class FastTrainer:
                     and all(s is None for s in model.mask_specs()) and self.weight_l1 == 0.0
                     and ops.grid_step_supported(self.geom))
         if self.world > 1 and mode == 'p2p' and gstep_ok and self.world <= L.MAX_PEERS:
-            # No collective at all: the two parity copies of the buffer live in torch symmetric memory, lfgc_grid_step
-            # reads every rank's copy over NVLink behind its own in-kernel barrier (flags at the end of the allocation).
+            # No collective: the two parity copies of the buffer live in torch symmetric memory, lfgc_peer_sum reads
+            # every rank's copy over NVLink behind its own in-kernel barrier (flags at the end of the allocation).
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
             grp = self.group if self.group is not None else dist.group.WORLD
@@ -147,7 +147,8 @@ class FastTrainer:
             self._p2p = dict(buf=buf, hdl=hdl, rank=int(hdl.rank),
                              peers=[[b + 4 * self._n_red * par for b in bases] for par in (0, 1)],
                              flags=[b + 4 * 2 * self._n_red for b in bases],
-                             epoch=torch.zeros(1, device=self.device, dtype=torch.int32))
+                             epoch=torch.zeros(2, device=self.device, dtype=torch.int32),
+                             summed=torch.zeros(self._n_red, device=self.device, dtype=torch.float32))
             torch.cuda.synchronize()
             dist.barrier(group=grp)          # every rank's flags are zero before anybody's first launch
         else:
@@ -323,14 +324,14 @@ class FastTrainer:
             torch.distributed.all_reduce(self.red, group=self.group)
             ops.grid_step(geom, [self.grad_grid], [self.red_mlp], 1, pcount + 1, pcount, **common)
             return
-        # peer reads inside lfgc_grid_step: this step's buffers of all ranks are the sources; the accumulator cleared is
-        # the OTHER parity's (its last readers finished before they announced this epoch)
+        # lfgc_peer_sum: this step's buffers of all ranks -> one local sum (barrier inside the kernel); the accumulator it
+        # clears is the OTHER parity's (its last readers finished before they announced this epoch)
         P = self._p2p
         par = self._par
         n_grid = self.grid_cl.numel()
-        common['zero_grid'] = self._red2[par ^ 1][:n_grid]
-        ops.grid_step(geom, P['peers'][par], [a + 4 * n_grid for a in P['peers'][par]], 1, pcount + 1, pcount,
-                      sync=dict(rank=P['rank'], flags=P['flags'], epoch=P['epoch']), **common)
+        ops.peer_sum(P['peers'][par], P['flags'], P['rank'], P['epoch'], P['summed'], zero=self._red2[par ^ 1])
+        common['zero_grid'] = None
+        ops.grid_step(geom, [P['summed'][:n_grid]], [P['summed'][n_grid:]], 1, pcount + 1, pcount, **common)
 
     def capture(self, host_fed=False):
         """Warm up eagerly (counts launches), then record the step into a CUDA graph; the optimiser state the

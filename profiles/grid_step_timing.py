@@ -11,7 +11,7 @@ vol = (torch.rand(64, 64, 64, device='cuda') * 2 - 1)
 for C, G in ((16, 15), (8, 9), (32, 15)):
     res = {}
     for flag in ('1', 's', '0'):
-        os.environ['LFGC_GRID_STEP'] = '0' if flag == '0' else '1'; os.environ['LFGC_GRID_STEP_CLUSTER'] = '0' if flag == 's' else '1'
+        os.environ['LFGC_GRID_STEP'] = '0' if flag == '0' else '1'; os.environ['LFGC_GRID_STEP_SPLIT'] = '0' if flag == 's' else '1'
         torch.manual_seed(0)
         m = setup_model(3, 32, 1, 4, 'fourier', 2, '', 0.1, 0.9, 'db2', C, G, '').cuda().train()
         tr = FastTrainer(m, vol, 32768, lr=0.008, seed=1)
@@ -40,7 +40,7 @@ for C, G in ((16, 15), (8, 9), (32, 15)):
         k_us = e0.elapsed_time(e1) * 1e3 / 200
         res[flag] = (step_us, k_us, tr.launches_per_step)
         tr._graphs.clear()
-    print('C%d G%d: grid_step cluster  step %.2f us (per-sample kernel %.2f, rest %.2f) | one CTA/channel  step %.2f us '
+    print('C%d G%d: grid_step split  step %.2f us (per-sample kernel %.2f, rest %.2f) | whole pyramid per CTA  step %.2f us '
           '(rest %.2f) | separate  step %.2f us (kernel+reduce %.2f, rest %.2f, %d launches)' % (
               C, G, res['1'][0], res['1'][1], res['1'][0] - res['1'][1], res['s'][0], res['s'][0] - res['s'][1],
               res['0'][0], res['0'][1], res['0'][0] - res['0'][1], res['0'][2]))

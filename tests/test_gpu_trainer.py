@@ -157,8 +157,8 @@ def test_pipelined_host_fed_step_equals_serial_one():
 
 @pytest.mark.parametrize('wavelet,G,C,w2', [('db2', 15, 16, 0.0), ('haar', 16, 8, 0.0), ('db2', 5, 6, 0.0), ('db2', 15, 8, 1e-4),
                                            ('db2', 17, 5, 0.0)])
-@pytest.mark.parametrize('cluster', ['1', '0'])
-def test_grid_step_path_equals_separate_kernels(wavelet, G, C, w2, cluster, monkeypatch):
+@pytest.mark.parametrize('split', ['1', '0'])
+def test_grid_step_path_equals_separate_kernels(wavelet, G, C, w2, split, monkeypatch):
     """lfgc_grid_step (partial reduction + adjoint + Adam + next synthesis in ONE launch, per-channel CTAs, separable
     levels) against the separate kernels over several optimiser steps, weight-decay term included."""
     from latent_feature_grid_compression_b200 import ops
@@ -174,7 +174,7 @@ def test_grid_step_path_equals_separate_kernels(wavelet, G, C, w2, cluster, monk
     monkeypatch.setenv('LFGC_GRID_STEP', '0')
     ta = FastTrainer(a, vol, 3000, lr=0.008, seed=4, weight_l2=w2)
     monkeypatch.setenv('LFGC_GRID_STEP', '1')
-    monkeypatch.setenv('LFGC_GRID_STEP_CLUSTER', cluster)   # 8-CTA cluster per channel (default) / one CTA per channel
+    monkeypatch.setenv('LFGC_GRID_STEP_SPLIT', split)   # finest level on the whole GPU (default) / whole pyramid per CTA
     tb = FastTrainer(b, vol, 3000, lr=0.008, seed=4, weight_l2=w2)
     assert tb._gstep and not ta._gstep
     for s in range(7):
@@ -184,7 +184,8 @@ def test_grid_step_path_equals_separate_kernels(wavelet, G, C, w2, cluster, monk
             torch.cuda.synchronize()
             ga, gb = ta.flat_g, tb.flat_g
             assert float((ga - gb).abs().max()) <= 2e-6 * float(ga.abs().max())
-    assert int(tb.step_dev[0]) == 7 and int(tb.step_dev[1]) == 0 and tb.launches_per_step == 2
+    assert int(tb.step_dev[0]) == 7 and int(tb.step_dev[1]) == 0
+    assert tb.launches_per_step == (4 if split == '1' and len(tb.coeff_params) > 1 else 2)
     assert abs(ta.last_loss() - tb.last_loss()) <= 1e-5 * abs(ta.last_loss())
     assert float((ta.flat_p - tb.flat_p).abs().max()) <= 1e-5 * float(ta.flat_p.abs().max())
     assert float((ta.flat_m - tb.flat_m).abs().max()) <= 1e-5 * float(ta.flat_m.abs().max())

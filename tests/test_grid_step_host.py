@@ -24,7 +24,8 @@ def hostlib(tmp_path_factory):
     out = str(tmp_path_factory.mktemp('gstep') / 'libgstep_host.so')
     cmd = [nvcc, '-shared', '-Xcompiler', '-fPIC', '-std=c++17', '-O2', '-gencode', 'arch=compute_100a,code=sm_100a',
            '-DLFGC_GRID_STEP_HOST_TEST', '-I', os.path.join(ROOT, 'include'), '-I', CSRC,
-           os.path.join(CSRC, 'grid_step.cu'), os.path.join(CSRC, 'api.cu'), '-o', out]
+           os.path.join(CSRC, 'grid_step.cu'), os.path.join(CSRC, 'wavelet.cu'), os.path.join(CSRC, 'wavelet_sep.cu'),
+           os.path.join(CSRC, 'api.cu'), '-o', out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-2000:]
     return ct.CDLL(out)
@@ -32,7 +33,7 @@ def hostlib(tmp_path_factory):
 
 @pytest.mark.parametrize('C,G,wavelet,n_srcs,w2', [(3, 15, 'db2', 1, 0.0), (2, 16, 'haar', 2, 0.0), (5, 17, 'db2', 1, 1e-3),
                                                  (2, 5, 'db2', 3, 0.0), (6, 12, 'db2', 1, 0.0)])
-@pytest.mark.parametrize('nworkers', [1024, 4096])   # plans of the one-CTA and of the 8-CTA-cluster kernels
+@pytest.mark.parametrize('nworkers', [1024, 352])   # the kernel's plan, and another split of the same work
 def test_grid_step_against_the_oracle(hostlib, C, G, wavelet, n_srcs, w2, nworkers):
     from latent_feature_grid_compression_b200 import _lib as L
     from latent_feature_grid_compression_b200 import ops
