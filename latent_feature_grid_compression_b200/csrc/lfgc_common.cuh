@@ -194,6 +194,64 @@ __device__ __forceinline__ void snake_and_grad_precise(float z, float& h, float&
 }
 #endif
 
+// SnakeAlt VALUE only (forward / reconstruction): 0.5 z + sin^2 z = 0.5 z + 0.5 - 0.5 cos 2z with ONE polynomial.
+// 2z is reduced modulo pi (two-term Cody-Waite, exact products through FMA) to r in [-pi/2, pi/2], where cos r is a
+// degree-5 polynomial in r^2 (least-squares fit on Chebyshev nodes, max abs error 6.2e-8 in fp32 Horner form); the sign
+// (-1)^n goes into the coefficient -0.5 by flipping its sign bit.  15 instructions instead of ~26 for the sin AND cos
+// polynomials plus quadrant selects of sincos_cw, and no select at all.  Valid for |z| < 1e4 like sincos_cw.
+#define LFGC_SNAKE_C2 4.16666343808e-2f
+#define LFGC_SNAKE_C3 -1.38883292675e-3f
+#define LFGC_SNAKE_C4 2.47584812314e-5f
+#define LFGC_SNAKE_C5 -2.60215898606e-7f
+__device__ __forceinline__ float snake_value_fast(float z) {
+    const float w = z + z;
+    const float biased = fmaf(w, 0.318309886f, 12582912.0f);   // rint(2z / pi) by the magic-number trick
+    const float n = biased - 12582912.0f;
+    float r = fmaf(n, -3.14159274f, w);
+    r = fmaf(n, 8.74227766e-08f, r);
+    const float u = r * r;
+    float p = fmaf(u, LFGC_SNAKE_C5, LFGC_SNAKE_C4);
+    p = fmaf(p, u, LFGC_SNAKE_C3);
+    p = fmaf(p, u, LFGC_SNAKE_C2);
+    p = fmaf(p, u, -0.5f);
+    p = fmaf(p, u, 1.0f);                                       // cos r
+    const float sgn = __int_as_float(0xBF000000 ^ (__float_as_int(biased) << 31));   // -0.5 (-1)^n
+    return fmaf(sgn, p, fmaf(0.5f, z, 0.5f));
+}
+
+// The same for two values at once with packed fp32 arithmetic (fma.rn.f32x2, sm_100+: one issue slot per pair).
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void snake_value_fast2(float z0, float z1, float& h0, float& h1) {
+    const unsigned long long z = pack2(z0, z1);
+    const unsigned long long one = pack2(1.0f, 1.0f), half = pack2(0.5f, 0.5f), magic = pack2(12582912.0f, 12582912.0f);
+    const unsigned long long w = fma2(z, one, z);                                        // 2 z
+    const unsigned long long biased = fma2(w, pack2(0.318309886f, 0.318309886f), magic);
+    const unsigned long long n = fma2(biased, one, pack2(-12582912.0f, -12582912.0f));
+    unsigned long long r = fma2(n, pack2(-3.14159274f, -3.14159274f), w);
+    r = fma2(n, pack2(8.74227766e-08f, 8.74227766e-08f), r);
+    const unsigned long long u = fma2(r, r, pack2(0.0f, 0.0f));
+    unsigned long long p = fma2(u, pack2(LFGC_SNAKE_C5, LFGC_SNAKE_C5), pack2(LFGC_SNAKE_C4, LFGC_SNAKE_C4));
+    p = fma2(p, u, pack2(LFGC_SNAKE_C3, LFGC_SNAKE_C3));
+    p = fma2(p, u, pack2(LFGC_SNAKE_C2, LFGC_SNAKE_C2));
+    p = fma2(p, u, pack2(-0.5f, -0.5f));
+    p = fma2(p, u, one);
+    float b0, b1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(biased));
+    const unsigned long long sgn = pack2(__int_as_float(0xBF000000 ^ (__float_as_int(b0) << 31)),
+                                         __int_as_float(0xBF000000 ^ (__float_as_int(b1) << 31)));
+    const unsigned long long h = fma2(sgn, p, fma2(half, z, half));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(h));
+}
+
 // Hidden-layer activation of the fused kernels: ACT 0 = SnakeAlt (the fV-SRN decoder), ACT 1 = ReLU (Variance_Model,
 // model/Variational_Dropout_Layer.py:159-175; gradient 1 where z > 0, as torch's threshold_backward).
 template <int ACT>

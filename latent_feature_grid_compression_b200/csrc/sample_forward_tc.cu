@@ -344,15 +344,20 @@ __global__ void __launch_bounds__(TILE * G, 1) sample_forward_tc_kernel(const __
                 : "r"(tmem_row));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const float* bl_ = bias + l * HP;
+            // SnakeAlt value with the single-polynomial, packed-pair evaluation (snake_value_fast2): this epilogue is what
+            // bounds the kernel (issue-active 75 %, r1 ncu), so its instruction count is the reconstruction rate
             if (l + 1 < L) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bl_ + 4 * c);
+                    float h0, h1, h2, h3;
+                    snake_value_fast2(__uint_as_float(r[4 * c + 0]) + b4.x, __uint_as_float(r[4 * c + 1]) + b4.y, h0, h1);
+                    snake_value_fast2(__uint_as_float(r[4 * c + 2]) + b4.z, __uint_as_float(r[4 * c + 3]) + b4.w, h2, h3);
                     float4 hi, lo;
-                    split_tf32(snake_precise(__uint_as_float(r[4 * c + 0]) + b4.x), hi.x, lo.x);
-                    split_tf32(snake_precise(__uint_as_float(r[4 * c + 1]) + b4.y), hi.y, lo.y);
-                    split_tf32(snake_precise(__uint_as_float(r[4 * c + 2]) + b4.z), hi.z, lo.z);
-                    split_tf32(snake_precise(__uint_as_float(r[4 * c + 3]) + b4.w), hi.w, lo.w);
+                    split_tf32(h0, hi.x, lo.x);
+                    split_tf32(h1, hi.y, lo.y);
+                    split_tf32(h2, hi.z, lo.z);
+                    split_tf32(h3, hi.w, lo.w);
                     *reinterpret_cast<float4*>(Ahi + c * kPanelA + t * 16) = hi;
                     *reinterpret_cast<float4*>(Alo + c * kPanelA + t * 16) = lo;
                 }
@@ -362,10 +367,13 @@ __global__ void __launch_bounds__(TILE * G, 1) sample_forward_tc_kernel(const __
                 for (int c = 0; c < 8; ++c) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bl_ + 4 * c);
                     const float4 w4 = *reinterpret_cast<const float4*>(Wf + 4 * c);
-                    y = fmaf(snake_precise(__uint_as_float(r[4 * c + 0]) + b4.x), w4.x, y);
-                    y = fmaf(snake_precise(__uint_as_float(r[4 * c + 1]) + b4.y), w4.y, y);
-                    y = fmaf(snake_precise(__uint_as_float(r[4 * c + 2]) + b4.z), w4.z, y);
-                    y = fmaf(snake_precise(__uint_as_float(r[4 * c + 3]) + b4.w), w4.w, y);
+                    float h0, h1, h2, h3;
+                    snake_value_fast2(__uint_as_float(r[4 * c + 0]) + b4.x, __uint_as_float(r[4 * c + 1]) + b4.y, h0, h1);
+                    snake_value_fast2(__uint_as_float(r[4 * c + 2]) + b4.z, __uint_as_float(r[4 * c + 3]) + b4.w, h2, h3);
+                    y = fmaf(h0, w4.x, y);
+                    y = fmaf(h1, w4.y, y);
+                    y = fmaf(h2, w4.z, y);
+                    y = fmaf(h3, w4.w, y);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

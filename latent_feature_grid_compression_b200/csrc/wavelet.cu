@@ -294,6 +294,15 @@ __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
     const float* fz = ((k >> 2) & 1) ? A.hi : A.lo;
     const float* fy = ((k >> 1) & 1) ? A.hi : A.lo;
     const float* fx = (k & 1) ? A.hi : A.lo;
+    // Adam epilogue: fetch the parameter and its moments up front, so that their round trip overlaps the gradient loads
+    const bool adam = A.ap != nullptr && live && k > 0;
+    const int64_t oa = ((int64_t)c * 7 + (k - 1)) * dvol + b;
+    float a_p = 0.0f, a_m = 0.0f, a_v = 0.0f;
+    if (adam) {
+        a_p = A.ap[oa];
+        a_m = A.am[oa];
+        a_v = A.av[oa];
+    }
     float g = 0.0f;
     if (live) {
         if (NT > 0) {
@@ -356,8 +365,8 @@ __global__ void idwt_level_bwd_kernel(LevelBwdArgs A) {
             const int64_t o = ((int64_t)c * 7 + (k - 1)) * dvol + b;
             if (A.gmult_high) { contrib = A.c_high[o] * g; gm = A.gmult_high + (int64_t)(k - 1) * dvol + b; }
             float v = A.gm_high ? g * A.gm_high[(int64_t)(k - 1) * dvol + b] : g;
-            if (A.ap) {
-                float pi = A.ap[o], mi = A.am[o], vi = A.av[o];
+            if (adam) {
+                float pi = a_p, mi = a_m, vi = a_v;
                 v = fmaf(A.w2x2, pi, v);
                 adam_update(pi, v, mi, vi, A.coef, s_step_size, s_bc2_sqrt);
                 A.ap[o] = pi;

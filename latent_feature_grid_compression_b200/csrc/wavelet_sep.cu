@@ -26,8 +26,8 @@ namespace wsep {
 struct Level {
     int C, d[3], t[3], off[3], m_lo[3], n_m[3];
     float lo[LFGC_MAX_TAPS], hi[LFGC_MAX_TAPS];
-    FastDiv by_d1, by_t2;
-    PassPlan sx, sy, ay, ax;   // the four shared-memory passes: ~2 units per thread, several positions per unit
+    FastDiv by_d1, by_d2, by_nm2;
+    PassPlan sy, ay;           // the y passes: column (a, ox) fastest (contiguous global stores / conflict-free smem)
 };
 
 // ---- S1: x and y synthesis passes of one (channel, iz) plane ---------------------------------------------------------------
@@ -56,15 +56,18 @@ __global__ void __launch_bounds__(256) synth_xy_kernel(const __grid_constant__ L
     for (int k = 1; k < 8; ++k)
         for (int i = threadIdx.x; i < plane; i += blockDim.x) B[k * plane + i] = __ldg(hsrc + (size_t)(k - 1) * dvol + i);
     __syncthreads();
-    // x pass: unit = (row = (ab, iy), range of pairs): bands (ab, 0 / 1) -> X[ab][iy][:]
-    for (int u = threadIdx.x; u < L.sx.ncols * L.sx.groups; u += blockDim.x) {
-        const int grp = fdiv(u, L.sx.by_ncols);
-        const int row = u - grp * L.sx.ncols;
-        const int ab = fdiv(row, L.by_d1);
-        const int iy = row - ab * d1;
-        const int r0 = grp * L.sx.per, r1 = min(r0 + L.sx.per, L.sx.n);
-        synth_line<NT>(B + (2 * ab) * plane + iy * d2, B + (2 * ab + 1) * plane + iy * d2, 1, d2, X + row * t2, 1, t2,
-                       L.off[2], L.m_lo[2] + r0, L.m_lo[2] + r1, flo, fhi);
+    // x pass: unit = (row = (ab, iy), pair m), m FASTEST: neighbouring threads write neighbouring ox (a row-fastest order
+    // strides the shared-memory stores by t2 floats: 32-way bank conflicts at t2 = 64, measured +110 us per step at C32/G64)
+    {
+        const int n_m = L.n_m[2], nrows = 4 * d1;
+        for (int u = threadIdx.x; u < nrows * n_m; u += blockDim.x) {
+            const int row = fdiv(u, L.by_nm2);
+            const int m = u - row * n_m + L.m_lo[2];
+            const int ab = fdiv(row, L.by_d1);
+            const int iy = row - ab * d1;
+            synth_line<NT>(B + (2 * ab) * plane + iy * d2, B + (2 * ab + 1) * plane + iy * d2, 1, d2, X + row * t2, 1, t2,
+                           L.off[2], m, m + 1, flo, fhi);
+        }
     }
     __syncthreads();
     // y pass: unit = (range of pairs, column = (a, ox)), column fastest so that the global stores are contiguous in ox
@@ -153,20 +156,20 @@ __global__ void __launch_bounds__(256) adj_yx_kernel(const __grid_constant__ Lev
         adj_line<NT>(Ys + a_ * pl + ox, t2, t1, L.off[1], o0, o0 + d1 * t2, t2, r0, r1, flo, fhi);
     }
     __syncthreads();
-    // x^T pass: unit = (row = (ab, iy), range of ix): X[ab][iy][:] -> bands (ab, c = 0 / 1)
+    // x^T pass: unit = (row = (ab, iy), ix), ix fastest (see the x pass): X[ab][iy][:] -> bands (ab, c = 0 / 1)
     {
+        const int nrows = 4 * d1;
         const size_t dvol = (size_t)d0 * d1 * d2;
         float* lowp = g_low + ((size_t)c * d0 + iz) * d1 * d2;
         float* highp = g_high + ((size_t)c * 7 * d0 + iz) * d1 * d2;
-        for (int u = threadIdx.x; u < L.ax.ncols * L.ax.groups; u += blockDim.x) {
-            const int grp = fdiv(u, L.ax.by_ncols);
-            const int row = u - grp * L.ax.ncols;
+        for (int u = threadIdx.x; u < nrows * d2; u += blockDim.x) {
+            const int row = fdiv(u, L.by_d2);
+            const int ix = u - row * d2;
             const int ab = fdiv(row, L.by_d1);
             const int iy = row - ab * d1;
-            const int r0 = grp * L.ax.per, r1 = min(r0 + L.ax.per, L.ax.n);
             float* o0 = (ab == 0 ? lowp : highp + (size_t)(2 * ab - 1) * dvol) + iy * d2;   // band (a, b, 0)
             float* o1 = highp + (size_t)(2 * ab) * dvol + iy * d2;                          // band (a, b, 1)
-            adj_line<NT>(X + row * t2, 1, t2, L.off[2], o0, o1, 1, r0, r1, flo, fhi);
+            adj_line<NT>(X + row * t2, 1, t2, L.off[2], o0, o1, 1, ix, ix + 1, flo, fhi);
         }
     }
 }
@@ -228,12 +231,11 @@ static void fill_level(Level& L, const lfgc_wavelet_desc* w, int l) {
         L.n_m[a] = ((L.off[a] + L.t[a] - 1) >> 1) - L.m_lo[a] + 1;
     }
     L.by_d1 = make_fastdiv((unsigned)L.d[1]);
-    L.by_t2 = make_fastdiv((unsigned)L.t[2]);
-    // 256 threads per CTA, aim at two units per thread: the per-unit index arithmetic is amortised over a run of positions
-    L.sx = make_plan(4 * L.d[1], L.n_m[2], 512);
-    L.sy = make_plan(2 * L.t[2], L.n_m[1], 512);
-    L.ay = make_plan(2 * L.t[2], L.d[1], 512);
-    L.ax = make_plan(4 * L.d[1], L.d[2], 512);
+    L.by_d2 = make_fastdiv((unsigned)L.d[2]);
+    L.by_nm2 = make_fastdiv((unsigned)L.n_m[2]);
+    // one position per unit: these passes are latency-bound, more independent units hide it better
+    L.sy = make_plan(2 * L.t[2], L.n_m[1], 1 << 24);
+    L.ay = make_plan(2 * L.t[2], L.d[1], 1 << 24);
 }
 
 static size_t smem_s1(const Level& L) { return ((size_t)8 * L.d[1] * L.d[2] + (size_t)4 * L.d[1] * L.t[2]) * sizeof(float); }

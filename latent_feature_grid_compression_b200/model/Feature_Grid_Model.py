@@ -53,11 +53,19 @@ class _FeatureGridFunction(torch.autograd.Function):
         out = ops.sample_forward(geom, coords, grid_cl, mlp_flat, clamp=clamp)
         ctx.geom, ctx.specs = geom, specs
         ctx.coords, ctx.grid_cl, ctx.mlp_flat, ctx.coeffs, ctx.auxs = coords, grid_cl, mlp_flat, coeffs, auxs
+        # The backward pass recomputes the forward from live parameter storage (views into the flat buffers), which
+        # bypasses autograd's version-counter check: do that check by hand, as torch would for saved tensors.
+        watched = list(params[:n_coeff]) + [mlp_flat] + [t for s in specs if s is not None for t in (s.p0, s.p1) if t is not None]
+        ctx.versions = [(t, t._version) for t in watched]
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         geom, specs = ctx.geom, ctx.specs
+        for t, v in ctx.versions:
+            if t._version != v:
+                raise RuntimeError('one of the variables needed for gradient computation has been modified by an inplace '
+                                   'operation (a parameter of Feature_Grid_Model changed between forward and backward)')
         gout = grad_out.contiguous().float()
         grad_grid_cl, grad_mlp = ops.sample_backward(geom, ctx.coords, gout, ctx.grid_cl, ctx.mlp_flat)
         want_gmult = [s is not None and len(s.grad_params) > 0 for s in specs]

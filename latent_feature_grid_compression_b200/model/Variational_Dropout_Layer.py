@@ -140,12 +140,16 @@ class _PlainMLPFunction(torch.autograd.Function):
         from .. import ops
         out = ops.plain_mlp_forward(width, n_layers, x, flat)
         ctx.saved = (x, flat, width, n_layers, [tuple(p.shape) for p in params])
+        ctx.flat_version = flat._version      # the backward recomputes from live storage: check it by hand
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         from .. import ops
         x, flat, width, n_layers, shapes = ctx.saved
+        if flat._version != ctx.flat_version:
+            raise RuntimeError('one of the variables needed for gradient computation has been modified by an inplace '
+                               'operation (a Variance_Model parameter changed between forward and backward)')
         g = ops.plain_mlp_backward(width, n_layers, x, grad_out.contiguous().float(), flat)
         grads, off = [], 0
         for shp in shapes:

@@ -8,7 +8,7 @@ from latent_feature_grid_compression_b200.model.model_utils import setup_model
 from latent_feature_grid_compression_b200.training.fast_loop import FastTrainer
 
 vol = (torch.rand(64, 64, 64, device='cuda') * 2 - 1)
-for C, G in ((16, 15), (8, 9), (32, 15)):
+for C, G in ((16, 15), (8, 9), (32, 15), (16, 9), (8, 15), (16, 17), (16, 15)):
     res = {}
     for flag in ('1', 's', '0'):
         os.environ['LFGC_GRID_STEP'] = '0' if flag == '0' else '1'; os.environ['LFGC_GRID_STEP_SPLIT'] = '0' if flag == 's' else '1'

@@ -202,7 +202,7 @@ def test_grid_step_falls_back_when_the_pyramid_does_not_fit_or_masks_are_live():
     from latent_feature_grid_compression_b200.training.fast_loop import FastTrainer
     vol = _volume()
     torch.manual_seed(1)
-    big = setup_model(3, 32, 1, 4, 'fourier', 2, '', 0.1, 0.9, 'db2', 4, 40, '').cuda().train()
+    big = setup_model(3, 32, 1, 4, 'fourier', 2, '', 0.1, 0.9, 'db2', 4, 96, '').cuda().train()   # 49^3 per channel below the finest level
     t = FastTrainer(big, vol, 2000, lr=0.008, seed=1)
     assert not t._gstep
     t.step()
