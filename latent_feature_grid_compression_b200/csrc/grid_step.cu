@@ -493,8 +493,12 @@ extern "C" int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_gri
     int rc = gstep_check_desc(w);
     if (rc) return rc;
     if (!a) return fail(LFGC_E_INVALID, "grid_step: null arguments");
-    bool split = w->n_coeff >= 2 && a->n_srcs == 1 && a->scratch && a->scratch_bytes >= lfgc_grid_step_scratch_bytes(w);
-    if (const char* e = getenv("LFGC_GRID_STEP_SPLIT")) split = split && e[0] != '0';
+    // Measured on B200 (profiles/grid_step_timing.py, 32768 samples per step; split / whole pyramid per CTA / separate
+    // launches, us per step): two wavelet levels C16/G15 70.6 / 79.5 / 73.7, C32/G15 92.7 / 105.6 / 98.9, C8/G15 62.7 /
+    // 65.9 / 67.6, C16/G17 73.7 / 81.7 / 77.8; one level C8/G9 59.4 / 56.0 / 59.3, C16/G9 64.2 / 63.5 / 65.5.
+    const bool can_split = w->n_coeff >= 2 && a->n_srcs == 1 && a->scratch && a->scratch_bytes >= lfgc_grid_step_scratch_bytes(w);
+    bool split = can_split && (w->n_coeff >= 3 || lfgc_grid_step_smem_bytes(w) == 0);
+    if (const char* e = getenv("LFGC_GRID_STEP_SPLIT")) split = can_split && e[0] != '0';   // tuning / test override
     if (!split) {
         rc = gstep_fill(A, w, Cp, a, gstep::kThreads);
         if (rc) return rc;
