@@ -255,6 +255,12 @@ int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const flo
               double beta1, double beta2, double eps, double grad_scale, void* stream);
 
 /* p-gradient of the sample-independent regularisers added in place: g += w_l2 * 2 * p (n_l2 leading elements) */
+/* lfgc_adam with the SmallifyLoss terms (model/Smallify_Dropout.py:22-40) folded into the gradient: + 2 weight_l2 p on
+ * elements [l2_begin, l2_end) (the wavelet coefficients) and + weight_l1 sign(p) on [l1_begin, l1_end) (the mask
+ * parameters); one launch instead of lfgc_add_l2_grad + lfgc_add_l1_grad + lfgc_adam. */
+int lfgc_adam_reg(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+                  double beta1, double beta2, double eps, double grad_scale, int64_t l2_begin, int64_t l2_end,
+                  double weight_l2, int64_t l1_begin, int64_t l1_end, double weight_l1, void* stream);
 int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 

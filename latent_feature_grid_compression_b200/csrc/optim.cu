@@ -7,9 +7,21 @@ namespace lfgc {
 // step_ptr[0] = optimiser steps taken so far, step_ptr[1] = ticket counter (must start at 0).  Every block reads the
 // step before it takes its ticket and the block drawing the last ticket publishes step + 1, so the whole update is
 // one launch and stays correct under CUDA-graph replay.
+// Optional SmallifyLoss terms (model/Smallify_Dropout.py:22-40) folded into the update: + 2 w2 p on [l2_begin, l2_end)
+// (the wavelet coefficients), + w1 sign(p) on [l1_begin, l1_end) (the mask parameters).  Empty ranges: plain Adam.
+struct AdamReg {
+    long long l2_begin, l2_end, l1_begin, l1_end;
+    float w2x2, w1;
+};
+__device__ __forceinline__ float adam_reg_grad(float g, float p, long long i, const AdamReg& r) {
+    if (i >= r.l2_begin && i < r.l2_end) g = fmaf(r.w2x2, p, g);
+    if (i >= r.l1_begin && i < r.l1_end) g += r.w1 * ((p > 0.0f) ? 1.0f : ((p < 0.0f) ? -1.0f : 0.0f));
+    return g;
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, const float* __restrict__ lr_ptr,
-                            int32_t* __restrict__ step_ptr, const AdamCoef c) {
+                            int32_t* __restrict__ step_ptr, const AdamCoef c, const AdamReg reg) {
     LFGC_PDL_PROLOGUE();
     __shared__ float s_step_size, s_bc2_sqrt;
     __shared__ int s_step;
@@ -33,17 +45,17 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         float4 p4 = *reinterpret_cast<const float4*>(p + i4), m4 = *reinterpret_cast<const float4*>(m + i4);
         float4 v4 = *reinterpret_cast<const float4*>(v + i4);
         const float4 g4 = *reinterpret_cast<const float4*>(g + i4);
-        adam_update(p4.x, g4.x, m4.x, v4.x, c, s_step_size, s_bc2_sqrt);
-        adam_update(p4.y, g4.y, m4.y, v4.y, c, s_step_size, s_bc2_sqrt);
-        adam_update(p4.z, g4.z, m4.z, v4.z, c, s_step_size, s_bc2_sqrt);
-        adam_update(p4.w, g4.w, m4.w, v4.w, c, s_step_size, s_bc2_sqrt);
+        adam_update(p4.x, adam_reg_grad(g4.x, p4.x, i4, reg), m4.x, v4.x, c, s_step_size, s_bc2_sqrt);
+        adam_update(p4.y, adam_reg_grad(g4.y, p4.y, i4 + 1, reg), m4.y, v4.y, c, s_step_size, s_bc2_sqrt);
+        adam_update(p4.z, adam_reg_grad(g4.z, p4.z, i4 + 2, reg), m4.z, v4.z, c, s_step_size, s_bc2_sqrt);
+        adam_update(p4.w, adam_reg_grad(g4.w, p4.w, i4 + 3, reg), m4.w, v4.w, c, s_step_size, s_bc2_sqrt);
         *reinterpret_cast<float4*>(p + i4) = p4;
         *reinterpret_cast<float4*>(m + i4) = m4;
         *reinterpret_cast<float4*>(v + i4) = v4;
     } else {
         for (int64_t i = i4; i < n && i < i4 + 4; ++i) {
             float pi = p[i], mi = m[i], vi = v[i];
-            adam_update(pi, g[i], mi, vi, c, s_step_size, s_bc2_sqrt);
+            adam_update(pi, adam_reg_grad(g[i], pi, i, reg), mi, vi, c, s_step_size, s_bc2_sqrt);
             p[i] = pi;
             m[i] = mi;
             v[i] = vi;
@@ -201,15 +213,35 @@ extern "C" int lfgc_variational_dkl_grad(const float* mask_params, float* mask_g
 }
 
 
-extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
-                         double beta1, double beta2, double eps, double grad_scale, void* stream) {
+static int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+                       double beta1, double beta2, double eps, double grad_scale, const AdamReg& reg, void* stream) {
     if (!p || !g || !m || !v || !lr || !step_count || n < 0) return fail(LFGC_E_INVALID, "adam: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t blocks = n == 0 ? 1 : (n + 1023) / 1024;   // 256 threads x 4 parameters
     (void)launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), st, p, g, m, v, n, lr, step_count,
-                     make_adam_coef(beta1, beta2, eps, grad_scale));
+                     make_adam_coef(beta1, beta2, eps, grad_scale), reg);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
+}
+
+extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+                         double beta1, double beta2, double eps, double grad_scale, void* stream) {
+    const AdamReg none = {0, 0, 0, 0, 0.0f, 0.0f};
+    return launch_adam(p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale, none, stream);
+}
+
+extern "C" int lfgc_adam_reg(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+                             double beta1, double beta2, double eps, double grad_scale, int64_t l2_begin, int64_t l2_end,
+                             double weight_l2, int64_t l1_begin, int64_t l1_end, double weight_l1, void* stream) {
+    if (l2_begin < 0 || l2_end > n || l1_begin < 0 || l1_end > n) return fail(LFGC_E_INVALID, "adam_reg: range outside the buffer");
+    AdamReg reg;
+    reg.l2_begin = l2_begin;
+    reg.l2_end = l2_end > l2_begin ? l2_end : l2_begin;
+    reg.l1_begin = l1_begin;
+    reg.l1_end = l1_end > l1_begin ? l1_end : l1_begin;
+    reg.w2x2 = (float)(2.0 * weight_l2);
+    reg.w1 = (float)weight_l1;
+    return launch_adam(p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale, reg, stream);
 }
 
 extern "C" int lfgc_peer_sum(const float* const* srcs, int32_t* const* flags, int n_srcs, int rank, int32_t* epoch, float* out,

@@ -376,6 +376,17 @@ def adam(p, g, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_sc
                           _p(_req(lr_dev, 'lr')), _p(step_dev), beta1, beta2, eps, grad_scale, _stream()), 'lfgc_adam')
 
 
+def adam_reg(p, g, m, v, lr_dev, step_dev, l2_range, weight_l2, l1_range, weight_l1, beta1=0.9, beta2=0.999, eps=1e-8):
+    """Adam with the SmallifyLoss gradient terms folded in (lfgc_adam_reg): + 2 weight_l2 p on ``l2_range`` (begin, end),
+    + weight_l1 sign(p) on ``l1_range``."""
+    lib = L.load()
+    _req(step_dev, 'step', torch.int32)
+    L.check(lib.lfgc_adam_reg(_p(_req(p, 'p')), _p(_req(g, 'g')), _p(_req(m, 'm')), _p(_req(v, 'v')), p.numel(),
+                              _p(_req(lr_dev, 'lr')), _p(step_dev), beta1, beta2, eps, 1.0, int(l2_range[0]),
+                              int(l2_range[1]), float(weight_l2), int(l1_range[0]), int(l1_range[1]), float(weight_l1),
+                              _stream()), 'lfgc_adam_reg')
+
+
 def train_step_partials(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl,
                         mlp_flat, grad_grid_cl, workspace, step_dev=None, step_stride: int = 0, coords=None,
                         targets=None, explicit_idx=None) -> int:

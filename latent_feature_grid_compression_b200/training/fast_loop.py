@@ -168,6 +168,24 @@ class FastTrainer:
         # mask-free models whose per-channel wavelet pyramid fits in shared memory: the whole non-per-sample part of the
         # step (partial reduction + adjoint + Adam + next synthesis) is ONE launch, lfgc_grid_step (LFGC_GRID_STEP=0: off)
         self._gstep = gstep_ok
+        # live Smallify masks on every level (test_impl_test / mhd_p_smallify): the multiplier IS the parameter, so the mask
+        # kernels disappear -- the betas go straight into the synthesis, the adjoint writes d loss / d beta straight into
+        # the flat gradient, the three per-level trackers become ONE launch over flat EMA buffers and the regulariser
+        # gradients ride in the Adam kernel: 8 launches per step instead of 18
+        self._smallify = (self.var_cfg is None and len(model.drop) > 0
+                          and all(isinstance(d, SmallifyDropout) and d.d_mask is None for d in model.drop))
+        if self._smallify:
+            with torch.no_grad():
+                self._ema = torch.cat([d.tracker.EMA.to(self.device).reshape(-1) for d in model.drop]).contiguous()
+                self._emavar = torch.cat([d.tracker.EMAVar.to(self.device).reshape(-1) for d in model.drop]).contiguous()
+                off = 0
+                for d in model.drop:
+                    n = d.betas.numel()
+                    d.tracker.EMA = self._ema[off:off + n].view(d.betas.shape)
+                    d.tracker.EMAVar = self._emavar[off:off + n].view(d.betas.shape)
+                    off += n
+                assert off == self.n_mask_elems
+            self._momentum = float(model.drop[0].tracker.sign_variance_momentum)
         self._gstep_primed = False
         self._gstep_scratch = torch.zeros(max(ops.grid_step_scratch_floats(self.geom), 4), device=self.device) \
             if gstep_ok else None
@@ -223,6 +241,8 @@ class FastTrainer:
             in_coords, in_targets = self._pipe['coords'][host_fed[1]], self._pipe['targets'][host_fed[1]]
         if self._gstep:
             return self._step_body_gstep(host_fed, in_coords, in_targets)
+        if self._smallify:
+            return self._step_body_smallify(host_fed, in_coords, in_targets)
         specs = model.mask_specs()
         mults, auxs = _multipliers(specs)
         coeffs = [p.data for p in self.coeff_params]
@@ -287,6 +307,28 @@ class FastTrainer:
             ops.add_l1_grad(g_red[a:b], self.flat_p[a:b], self.weight_l1)
         ops.adam(self.flat_p, g_red, self.flat_m, self.flat_v, self.lr_dev, self.step_dev, self.betas[0],
                  self.betas[1], self.eps)
+
+    def _step_body_smallify(self, host_fed, in_coords, in_targets):
+        """Live Smallify masks (Smallify_Dropout.py:54-61,103-112; SmallifyLoss :22-40): see __init__."""
+        geom = self.geom
+        n_global = self.batch * self.world
+        a, b = self.mask_off, self.mask_off + self.n_mask_elems
+        ops.smallify_ema(self.flat_p[a:b], self._ema, self._emavar, self._momentum)
+        betas = [d.betas.data for d in self.model.drop]          # views into flat_p: the multipliers themselves
+        coeffs = [p.data for p in self.coeff_params]
+        ops.decode_fwd(geom, coeffs, betas, scratch=self.scratch, out=self.grid_cl, also_zero=self.grad_grid)
+        ops.train_step(geom, self.volume, self.batch, self.seed,
+                       parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
+                       parallel.loss_scale(self.batch, self.world), self.grid_cl,
+                       self.mlp_flat, self.grad_grid, self.flat_g[self.mlp_off:], self.loss_sum, self.workspace,
+                       step_dev=self.step_dev, step_stride=n_global,
+                       coords=in_coords if host_fed else None, targets=in_targets if host_fed else None)
+        ops.decode_bwd(geom, self.grad_grid, coeffs, betas, [True] * len(betas), scratch=self.scratch,
+                       grad_coeffs=[self.grad_of(p) for p in self.coeff_params],
+                       grad_mults=[self.grad_of(d.betas) for d in self.model.drop])
+        g_red = self._allreduce_grads() if self.world > 1 else self.flat_g
+        ops.adam_reg(self.flat_p, g_red, self.flat_m, self.flat_v, self.lr_dev, self.step_dev,
+                     (0, self.n_coeff_elems), self.weight_l2, (a, b), self.weight_l1, self.betas[0], self.betas[1], self.eps)
 
     def _prime_gstep(self):
         """The grid-step path expects the grid of the CURRENT coefficients (and a cleared gradient accumulator) on
