@@ -554,6 +554,36 @@ def measure_config(name, volume, rank, world, dev, pk, opt_steps=300, with_recon
     return out
 
 
+def measure_strong(name, volume, rank, world, dev, opt_steps=300):
+    """The reference's global batch (batch_size * sample_size) split over the ranks: what train_volume(args, world=N)
+    runs.  At the shipped batch sizes a rank keeps only a fraction of a wave of tiles, so this cannot scale; it is
+    reported because weak scaling alone (the headline) trains a different problem."""
+    import torch.distributed as dist
+    from latent_feature_grid_compression_b200.training.fast_loop import make_trainer
+    cfg = CONFIGS[name]
+    a = cfg['args']
+    model = build_model(name, dev)
+    tr = make_trainer(model, volume, cfg['R'] ** 3, a, a['lr'], seed=99, rank=rank, world=world)
+    tr.capture()
+    for _ in range(20):
+        tr.step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(opt_steps):
+        tr.step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    n_global = a['batch_size'] * a['sample_size']
+    tr._graphs.clear()
+    return dict(value=opt_steps * n_global / (ms * 1e-3), unit=UNIT, us_per_optimiser_step=1e3 * ms / opt_steps,
+                global_batch=n_global, per_gpu_batch=n_global // world, scaling='strong')
+
+
 def run_native(args):
     import torch.distributed as dist
     from latent_feature_grid_compression_b200.build import build_library
@@ -697,6 +727,14 @@ def run_native(args):
     del trainer
     torch.cuda.empty_cache()
 
+    # ---- strong scaling (N > 1): the reference's GLOBAL batch split over the ranks -- the same optimisation problem ------
+    strong = None
+    if world > 1 and (a['batch_size'] * a['sample_size']) % world == 0:
+        try:
+            strong = measure_strong(name, volume, rank, world, dev)
+        except Exception as e:   # noqa: BLE001
+            strong = dict(error=repr(e)[:300])
+
     # ---- the other BASELINE configurations and the PSNR of the fast loop (N = 1 ... world) ----------------------------
     extra_cfgs, psnr = {}, None
     if not args.no_extras:
@@ -748,7 +786,8 @@ def run_native(args):
                     extra=dict(us_per_optimiser_step=1e3 * total_ms / (args.steps * steps_per_pass),
                                hot_l2_samples_per_s=steps_per_pass * n * world / (hot_ms * 1e-3),
                                wall_s_timed_region=wall, final_mse=final_loss,
-                               launches_per_optimiser_step=launches, configs=extra_cfgs, psnr=psnr))
+                               launches_per_optimiser_step=launches, strong_scaling=strong, configs=extra_cfgs,
+                               psnr=psnr))
         print(json.dumps(line), flush=True)
     _shutdown(world, dist)
 

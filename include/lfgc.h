@@ -156,8 +156,9 @@ size_t lfgc_backward_workspace_bytes(const lfgc_model_desc* m);
 /* Backward of lfgc_forward for d(loss)/d(out) = grad_out[n] (recomputes the forward; nothing is saved):
  *   grad_grid_cl[z][y][x][Cp] += trilinear scatter of d(features)       (L2 vector atomics)
  *   grad_mlp[P]               (+)= MLP weight/bias gradients             (deterministic two-stage reduction)
- *   grad_coords[n][3]          = d(loss)/d(coords) if non-NULL (the reference computes it, training.py:99, and
- *                                never reads it)
+ *   grad_coords                 must be NULL: the coordinate gradient is NOT produced (the reference's autograd computes
+ *                               one because training.py:99 sets requires_grad, and never reads it); a non-NULL
+ *                               pointer is refused with LFGC_E_UNSUPPORTED rather than silently left unwritten
  * Replaces the autograd backward of grid_sampler_3d, cat, addmm, sin/pow (training/training.py:137). */
 int lfgc_backward(const lfgc_model_desc* m, const float* coords, int64_t n, const float* grad_out,
                   const float* grid_cl, const float* mlp, float* grad_grid_cl, float* grad_mlp,

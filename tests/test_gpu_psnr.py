@@ -44,3 +44,26 @@ def test_fast_loop_reaches_the_same_quality():
     info = train_volume(args, volume=vol, seed=3)
     print('\n[psnr fast loop] reference %.3f dB, fast loop %.3f dB' % (float(g['psnr']), info['psnr']))
     assert info['psnr'] > float(g['psnr']) - 1.5
+
+
+def test_fast_loop_psnr_distribution_matches_the_reference_at_a_baseline_config():
+    """BASELINE config turbulence_basic (150^3, no pruning, the full 50-pass two-phase schedule): the fast loop's final
+    PSNR over three Philox seeds against the reference's own three runs on the same synthetic volume
+    (tests/golden/psnr_configs.json, unmodified training/training.py:184 on CPU).  The sample streams differ by
+    construction, so the gate is distributional: mean within 0.3 dB (the reference's own seed spread is 0.23 dB)."""
+    import json
+    import bench
+    from latent_feature_grid_compression_b200.training.fast_loop import train_volume
+    recs = [r for r in json.load(open(os.path.join(GOLD, 'psnr_configs.json')))
+            if r['config'] == 'turbulence_basic' and r['max_pass'] == r['config_max_pass']]
+    assert len(recs) >= 3
+    vol = bench.synthetic_volume(150, 'cuda').cpu()
+    mine = []
+    for s in range(3):
+        torch.manual_seed(s)
+        info = train_volume(dict(recs[0]['args']), volume=vol, seed=1000 + s)
+        assert info['steps'] == recs[-1]['optimiser_steps']          # same schedule: same number of optimiser steps
+        mine.append(info['psnr'])
+    ref = [r['psnr'] for r in recs]
+    print('\n[psnr @ turbulence_basic] reference %s, fast loop %s' % (['%.2f' % v for v in ref], ['%.2f' % v for v in mine]))
+    assert abs(np.mean(mine) - np.mean(ref)) < 0.3
