@@ -132,7 +132,9 @@ int lfgc_decode_fwd(const lfgc_wavelet_desc* w, const float* const* coeff, const
 
 /* Adjoint of lfgc_decode_fwd (autograd of conv_transpose3d + mul, training/training.py:137).
  * grad_coeff[l] (+)= d(coeff*mult) * gmul[l]  where gmul[l] is the gradient multiplier (aux of the mask; NULL = 1)
- * grad_mult[l]  (+)= sum_c coeff[l][c] * d(coeff*mult)[c]      (NULL entries are skipped) */
+ * grad_mult[l]  (+)= sum_c coeff[l][c] * d(coeff*mult)[c]      (NULL entries are skipped)
+ * accumulate: 0 overwrite (grad_mult is cleared first, one memset per level), 1 add to both, 2 overwrite grad_coeff and
+ * add into grad_mult, which the caller guarantees to be zero (lfgc_adam_reg clears it): no memsets. */
 int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_grid_cl, int Cp, const float* const* coeff,
                     const float* const* gmul, float* scratch, float* const* grad_coeff, float* const* grad_mult,
                     int accumulate, void* stream);
@@ -258,10 +260,14 @@ int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const flo
 /* p-gradient of the sample-independent regularisers added in place: g += w_l2 * 2 * p (n_l2 leading elements) */
 /* lfgc_adam with the SmallifyLoss terms (model/Smallify_Dropout.py:22-40) folded into the gradient: + 2 weight_l2 p on
  * elements [l2_begin, l2_end) (the wavelet coefficients) and + weight_l1 sign(p) on [l1_begin, l1_end) (the mask
- * parameters); one launch instead of lfgc_add_l2_grad + lfgc_add_l1_grad + lfgc_adam. */
-int lfgc_adam_reg(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+ * parameters); one launch instead of lfgc_add_l2_grad + lfgc_add_l1_grad + lfgc_adam.  Optional bookkeeping of the mask
+ * range in the same pass: ema / emavar (nullable pair, l1_end - l1_begin floats) receive the sign-variance tracker update
+ * of lfgc_smallify_ema with the PRE-update parameter (the value this step's forward used); zero_l1_grad != 0 clears the
+ * gradient elements of the range after they were consumed (the adjoint accumulates into them with atomics). */
+int lfgc_adam_reg(float* p, float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
                   double beta1, double beta2, double eps, double grad_scale, int64_t l2_begin, int64_t l2_end,
-                  double weight_l2, int64_t l1_begin, int64_t l1_end, double weight_l1, void* stream);
+                  double weight_l2, int64_t l1_begin, int64_t l1_end, double weight_l1, float* ema, float* emavar,
+                  float momentum, int zero_l1_grad, void* stream);
 int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 

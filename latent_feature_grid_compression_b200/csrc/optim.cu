@@ -12,14 +12,33 @@ namespace lfgc {
 struct AdamReg {
     long long l2_begin, l2_end, l1_begin, l1_end;
     float w2x2, w1;
+    // Smallify bookkeeping of the mask range, riding along (all optional): the sign-variance tracker update
+    // (Smallify_Dropout.py:103-112) with the parameter value this step's forward used (i.e. before the update below),
+    // and clearing the gradient element, which the synthesis adjoint accumulates into with atomics
+    float* ema;
+    float* emavar;
+    float momentum;
+    int zero_l1_grad;
 };
+__device__ __forceinline__ void adam_reg_side(float* g, float p_old, long long i, const AdamReg& r) {
+    if (i < r.l1_begin || i >= r.l1_end) return;
+    if (r.ema) {
+        const long long j = i - r.l1_begin;
+        const float sgn = (p_old > 0.0f) ? 1.0f : ((p_old < 0.0f) ? -1.0f : 0.0f);
+        const float e = r.ema[j];
+        const float phi = __fsub_rn(sgn, e);
+        r.ema[j] = __fadd_rn(e, __fmul_rn(r.momentum, phi));
+        r.emavar[j] = __fmul_rn(__fsub_rn(1.0f, r.momentum), __fadd_rn(r.emavar[j], __fmul_rn(r.momentum, __fmul_rn(phi, phi))));
+    }
+    if (r.zero_l1_grad) g[i] = 0.0f;
+}
 __device__ __forceinline__ float adam_reg_grad(float g, float p, long long i, const AdamReg& r) {
     if (i >= r.l2_begin && i < r.l2_end) g = fmaf(r.w2x2, p, g);
     if (i >= r.l1_begin && i < r.l1_end) g += r.w1 * ((p > 0.0f) ? 1.0f : ((p < 0.0f) ? -1.0f : 0.0f));
     return g;
 }
 
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, const float* __restrict__ lr_ptr,
                             int32_t* __restrict__ step_ptr, const AdamCoef c, const AdamReg reg) {
     LFGC_PDL_PROLOGUE();
@@ -45,6 +64,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         float4 p4 = *reinterpret_cast<const float4*>(p + i4), m4 = *reinterpret_cast<const float4*>(m + i4);
         float4 v4 = *reinterpret_cast<const float4*>(v + i4);
         const float4 g4 = *reinterpret_cast<const float4*>(g + i4);
+        if (reg.l1_end > reg.l1_begin) {
+            adam_reg_side(g, p4.x, i4, reg);
+            adam_reg_side(g, p4.y, i4 + 1, reg);
+            adam_reg_side(g, p4.z, i4 + 2, reg);
+            adam_reg_side(g, p4.w, i4 + 3, reg);
+        }
         adam_update(p4.x, adam_reg_grad(g4.x, p4.x, i4, reg), m4.x, v4.x, c, s_step_size, s_bc2_sqrt);
         adam_update(p4.y, adam_reg_grad(g4.y, p4.y, i4 + 1, reg), m4.y, v4.y, c, s_step_size, s_bc2_sqrt);
         adam_update(p4.z, adam_reg_grad(g4.z, p4.z, i4 + 2, reg), m4.z, v4.z, c, s_step_size, s_bc2_sqrt);
@@ -55,7 +80,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     } else {
         for (int64_t i = i4; i < n && i < i4 + 4; ++i) {
             float pi = p[i], mi = m[i], vi = v[i];
-            adam_update(pi, adam_reg_grad(g[i], pi, i, reg), mi, vi, c, s_step_size, s_bc2_sqrt);
+            const float gi = g[i];
+            adam_reg_side(g, pi, i, reg);
+            adam_update(pi, adam_reg_grad(gi, pi, i, reg), mi, vi, c, s_step_size, s_bc2_sqrt);
             p[i] = pi;
             m[i] = mi;
             v[i] = vi;
@@ -213,7 +240,7 @@ extern "C" int lfgc_variational_dkl_grad(const float* mask_params, float* mask_g
 }
 
 
-static int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+static int launch_adam(float* p, float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
                        double beta1, double beta2, double eps, double grad_scale, const AdamReg& reg, void* stream) {
     if (!p || !g || !m || !v || !lr || !step_count || n < 0) return fail(LFGC_E_INVALID, "adam: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -226,13 +253,15 @@ static int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, 
 
 extern "C" int lfgc_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
                          double beta1, double beta2, double eps, double grad_scale, void* stream) {
-    const AdamReg none = {0, 0, 0, 0, 0.0f, 0.0f};
-    return launch_adam(p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale, none, stream);
+    const AdamReg none = {0, 0, 0, 0, 0.0f, 0.0f, nullptr, nullptr, 0.0f, 0};
+    return launch_adam(p, const_cast<float*>(g), m, v, n, lr, step_count, beta1, beta2, eps, grad_scale, none, stream);
 }
 
-extern "C" int lfgc_adam_reg(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
+extern "C" int lfgc_adam_reg(float* p, float* g, float* m, float* v, int64_t n, const float* lr, int32_t* step_count,
                              double beta1, double beta2, double eps, double grad_scale, int64_t l2_begin, int64_t l2_end,
-                             double weight_l2, int64_t l1_begin, int64_t l1_end, double weight_l1, void* stream) {
+                             double weight_l2, int64_t l1_begin, int64_t l1_end, double weight_l1, float* ema,
+                             float* emavar, float momentum, int zero_l1_grad, void* stream) {
+    if ((ema == nullptr) != (emavar == nullptr)) return fail(LFGC_E_INVALID, "adam_reg: ema and emavar go together");
     if (l2_begin < 0 || l2_end > n || l1_begin < 0 || l1_end > n) return fail(LFGC_E_INVALID, "adam_reg: range outside the buffer");
     AdamReg reg;
     reg.l2_begin = l2_begin;
@@ -241,6 +270,10 @@ extern "C" int lfgc_adam_reg(float* p, const float* g, float* m, float* v, int64
     reg.l1_end = l1_end > l1_begin ? l1_end : l1_begin;
     reg.w2x2 = (float)(2.0 * weight_l2);
     reg.w1 = (float)weight_l1;
+    reg.ema = ema;
+    reg.emavar = emavar;
+    reg.momentum = momentum;
+    reg.zero_l1_grad = zero_l1_grad;
     return launch_adam(p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale, reg, stream);
 }
 

@@ -710,7 +710,7 @@ extern "C" int lfgc_decode_bwd(const lfgc_wavelet_desc* w, const float* grad_gri
         A.g_high = grad_coeff[l];
         A.gmult_low = (l == 1 && grad_mult) ? grad_mult[0] : nullptr;
         A.gmult_high = grad_mult ? grad_mult[l] : nullptr;
-        A.accumulate = accumulate;
+        A.accumulate = accumulate == 1 ? 1 : 0;   // 2: grad_mult pre-cleared by the caller, grad_coeff overwritten
         A.C = w->C;
         A.ntaps = w->n_taps;
         for (int a = 0; a < 3; ++a) {

@@ -166,7 +166,7 @@ def decode_fwd(geom: Geometry, coeffs: Sequence[torch.Tensor], mults: Sequence[O
 
 
 def decode_bwd(geom: Geometry, grad_grid_cl, coeffs, gmuls, want_gmult: Sequence[bool],
-               scratch: Optional[torch.Tensor] = None, grad_coeffs=None, grad_mults=None):
+               scratch: Optional[torch.Tensor] = None, grad_coeffs=None, grad_mults=None, accumulate: int = 0):
     lib = L.load()
     dev = grad_grid_cl.device
     _req(grad_grid_cl, 'grad_grid_cl')
@@ -180,7 +180,7 @@ def decode_bwd(geom: Geometry, grad_grid_cl, coeffs, gmuls, want_gmult: Sequence
     L.check(lib.lfgc_decode_bwd(ct.byref(geom.wavelet_desc), _p(grad_grid_cl), geom.Cp,
                                 L.ptr_array([_p(c) for c in coeffs]), L.ptr_array([_p(m) for m in gmuls]),
                                 _p(scratch), L.ptr_array([_p(g) for g in grad_coeffs]),
-                                L.ptr_array([_p(g) for g in grad_mults]), 0, _stream()), 'lfgc_decode_bwd')
+                                L.ptr_array([_p(g) for g in grad_mults]), int(accumulate), _stream()), 'lfgc_decode_bwd')
     return grad_coeffs, grad_mults
 
 
@@ -376,15 +376,17 @@ def adam(p, g, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_sc
                           _p(_req(lr_dev, 'lr')), _p(step_dev), beta1, beta2, eps, grad_scale, _stream()), 'lfgc_adam')
 
 
-def adam_reg(p, g, m, v, lr_dev, step_dev, l2_range, weight_l2, l1_range, weight_l1, beta1=0.9, beta2=0.999, eps=1e-8):
+def adam_reg(p, g, m, v, lr_dev, step_dev, l2_range, weight_l2, l1_range, weight_l1, beta1=0.9, beta2=0.999, eps=1e-8,
+             ema=None, emavar=None, momentum=0.0, zero_l1_grad=False):
     """Adam with the SmallifyLoss gradient terms folded in (lfgc_adam_reg): + 2 weight_l2 p on ``l2_range`` (begin, end),
-    + weight_l1 sign(p) on ``l1_range``."""
+    + weight_l1 sign(p) on ``l1_range``; optionally the Smallify tracker update (``ema``, ``emavar``) and the clearing of
+    the gradient on ``l1_range`` in the same pass."""
     lib = L.load()
     _req(step_dev, 'step', torch.int32)
     L.check(lib.lfgc_adam_reg(_p(_req(p, 'p')), _p(_req(g, 'g')), _p(_req(m, 'm')), _p(_req(v, 'v')), p.numel(),
                               _p(_req(lr_dev, 'lr')), _p(step_dev), beta1, beta2, eps, 1.0, int(l2_range[0]),
                               int(l2_range[1]), float(weight_l2), int(l1_range[0]), int(l1_range[1]), float(weight_l1),
-                              _stream()), 'lfgc_adam_reg')
+                              _p(ema), _p(emavar), float(momentum), 1 if zero_l1_grad else 0, _stream()), 'lfgc_adam_reg')
 
 
 def train_step_partials(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl,

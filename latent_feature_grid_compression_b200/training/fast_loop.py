@@ -170,8 +170,8 @@ class FastTrainer:
         self._gstep = gstep_ok
         # live Smallify masks on every level (test_impl_test / mhd_p_smallify): the multiplier IS the parameter, so the mask
         # kernels disappear -- the betas go straight into the synthesis, the adjoint writes d loss / d beta straight into
-        # the flat gradient, the three per-level trackers become ONE launch over flat EMA buffers and the regulariser
-        # gradients ride in the Adam kernel: 8 launches per step instead of 18
+        # the flat gradient, the three per-level trackers and the regulariser gradients ride in the Adam
+        # kernel (flat EMA buffers): 7 launches per step instead of 18
         self._smallify = (self.var_cfg is None and len(model.drop) > 0
                           and all(isinstance(d, SmallifyDropout) and d.d_mask is None for d in model.drop))
         if self._smallify:
@@ -313,7 +313,6 @@ class FastTrainer:
         geom = self.geom
         n_global = self.batch * self.world
         a, b = self.mask_off, self.mask_off + self.n_mask_elems
-        ops.smallify_ema(self.flat_p[a:b], self._ema, self._emavar, self._momentum)
         betas = [d.betas.data for d in self.model.drop]          # views into flat_p: the multipliers themselves
         coeffs = [p.data for p in self.coeff_params]
         ops.decode_fwd(geom, coeffs, betas, scratch=self.scratch, out=self.grid_cl, also_zero=self.grad_grid)
@@ -323,12 +322,17 @@ class FastTrainer:
                        self.mlp_flat, self.grad_grid, self.flat_g[self.mlp_off:], self.loss_sum, self.workspace,
                        step_dev=self.step_dev, step_stride=n_global,
                        coords=in_coords if host_fed else None, targets=in_targets if host_fed else None)
+        # d loss / d beta accumulates (atomics) into the mask section of the flat gradient, which the Adam kernel of the
+        # previous step left cleared (accumulate = 2: no memsets)
         ops.decode_bwd(geom, self.grad_grid, coeffs, betas, [True] * len(betas), scratch=self.scratch,
                        grad_coeffs=[self.grad_of(p) for p in self.coeff_params],
-                       grad_mults=[self.grad_of(d.betas) for d in self.model.drop])
+                       grad_mults=[self.grad_of(d.betas) for d in self.model.drop], accumulate=2)
         g_red = self._allreduce_grads() if self.world > 1 else self.flat_g
+        # Adam + SmallifyLoss gradients + the sign-variance tracker (with the betas this step's forward used) + clearing of
+        # the mask gradients, one launch
         ops.adam_reg(self.flat_p, g_red, self.flat_m, self.flat_v, self.lr_dev, self.step_dev,
-                     (0, self.n_coeff_elems), self.weight_l2, (a, b), self.weight_l1, self.betas[0], self.betas[1], self.eps)
+                     (0, self.n_coeff_elems), self.weight_l2, (a, b), self.weight_l1, self.betas[0], self.betas[1], self.eps,
+                     ema=self._ema, emavar=self._emavar, momentum=self._momentum, zero_l1_grad=True)
 
     def _prime_gstep(self):
         """The grid-step path expects the grid of the CURRENT coefficients (and a cleared gradient accumulator) on

@@ -1,6 +1,6 @@
 """Warp-stall samples per source line from an .ncu-rep captured with --import-source on (needs -lineinfo builds).
 
-    python profiles/ncu_hotlines.py gpurun_out/prof_x.ncu-rep [top_n] > profiles/rN_ncu_x_hotlines.txt
+    python profiles/ncu_hotlines.py gpurun_out/prof_x.ncu-rep [top_n [kernel-regex]] > profiles/rN_ncu_x_hotlines.txt
 """
 import collections
 import csv
@@ -9,8 +9,9 @@ import subprocess
 import sys
 
 
-def main(path, top=30):
-    out = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv', '--print-source', 'cuda,sass'],
+def main(path, top=30, kernel=None):
+    out = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv', '--print-source', 'cuda,sass']
+                         + (['--kernel-name-base', 'demangled', '--kernel-name', 'regex:' + kernel] if kernel else []),
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = [r for r in rows if r and r[0] == 'Line No'][0]
@@ -49,4 +50,4 @@ def main(path, top=30):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30, sys.argv[3] if len(sys.argv) > 3 else None)
