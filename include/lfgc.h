@@ -346,6 +346,17 @@ int lfgc_variational_dkl_grad(const float* mask_params, float* mask_grads, int n
                               double* w_dkl, const int32_t* step_count, double ramp, double w_max, float scale,
                               void* stream);
 
+/* All live variational mask layers at once (instead of one lfgc_mask_multiplier / lfgc_mask_param_grad per layer).  The
+ * flat mask section holds, per layer i, [log_thetas_i (n_i) | log_var_i (n_i)] (as for lfgc_variational_dkl_grad);
+ * noise / mult_out / gmult are the layers' masks concatenated (sum n_i floats).
+ *   lfgc_variational_multiplier: mult = exp(log_thetas) + exp(log_var / 2) * noise (Variational_Dropout_Layer.py:104-108);
+ *                                zero_out (nullable, sum n_i floats) is cleared in the same pass
+ *   lfgc_variational_param_grad: mask_grads (flat mask section, overwritten) = autograd of the above for d loss/d mult = gmult */
+int lfgc_variational_multiplier(const float* mask_params, const float* noise, int n_layers, const int64_t* layer_sizes,
+                                float* mult_out, float* zero_out, void* stream);
+int lfgc_variational_param_grad(const float* mask_params, const float* noise, const float* gmult, int n_layers,
+                                const int64_t* layer_sizes, float* mask_grads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

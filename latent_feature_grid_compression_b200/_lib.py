@@ -99,6 +99,8 @@ _SIGNATURES = {
     'lfgc_grid_step_smem_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
     'lfgc_grid_step_scratch_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
     'lfgc_grid_step_supported': (C.c_int, [C.POINTER(WaveletDesc)]),
+    'lfgc_variational_multiplier': (C.c_int, [_f, _f, C.c_int, C.POINTER(C.c_int64), _f, _f, _f]),
+    'lfgc_variational_param_grad': (C.c_int, [_f, _f, _f, C.c_int, C.POINTER(C.c_int64), _f, _f]),
     'lfgc_variational_dkl_grad': (C.c_int, [_f, _f, C.c_int, C.POINTER(C.c_int64), _f, _f, C.c_double, C.c_double,
                                             C.c_float, _f]),
 }

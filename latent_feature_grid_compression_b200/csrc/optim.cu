@@ -264,6 +264,43 @@ __global__ void variational_dkl_grad_kernel(const float* __restrict__ mask_p, fl
     mask_g[lt] -= 2.0f * g;
 }
 
+// All live variational mask layers in ONE launch each way (the per-layer lfgc_mask_multiplier / lfgc_mask_param_grad calls
+// plus their copies were ~20 graph nodes of the variational step).  Position q of the concatenated masks belongs to layer
+// `layer`; its parameters sit in the flat mask section at lt = 2 begin + (q - begin) (log_thetas) and lv = lt + n (log_var).
+__device__ __forceinline__ void dkl_locate(const DklSegments& seg, long long q, long long& lt, long long& lv) {
+    int layer = 0;
+    while (q >= seg.end[layer]) ++layer;
+    const long long begin = layer ? seg.end[layer - 1] : 0;
+    const long long n = seg.end[layer] - begin;
+    lt = 2 * begin + (q - begin);
+    lv = lt + n;
+}
+// mult = exp(log_thetas) + exp(log_var / 2) xi   (Variational_Dropout_Layer.py:104-108); zero_out (nullable) is cleared
+__global__ void variational_multiplier_kernel(const float* __restrict__ mask_p, const float* __restrict__ noise,
+                                              const __grid_constant__ DklSegments seg, float* __restrict__ mult,
+                                              float* __restrict__ zero_out) {
+    LFGC_PDL_PROLOGUE();
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= seg.end[seg.n_layers - 1]) return;
+    long long lt, lv;
+    dkl_locate(seg, q, lt, lv);
+    mult[q] = __fadd_rn(expf(mask_p[lt]), __fmul_rn(expf(mask_p[lv] / 2.0f), noise[q]));
+    if (zero_out) zero_out[q] = 0.0f;
+}
+// d loss / d(log_thetas, log_var) from d loss / d mult (autograd of the line above), written into the flat gradient
+__global__ void variational_param_grad_kernel(const float* __restrict__ mask_p, const float* __restrict__ noise,
+                                              const float* __restrict__ gmult, const __grid_constant__ DklSegments seg,
+                                              float* __restrict__ mask_g) {
+    LFGC_PDL_PROLOGUE();
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= seg.end[seg.n_layers - 1]) return;
+    long long lt, lv;
+    dkl_locate(seg, q, lt, lv);
+    const float gm = gmult[q];
+    mask_g[lt] = gm * expf(mask_p[lt]);
+    mask_g[lv] = gm * (0.5f * expf(mask_p[lv] / 2.0f) * noise[q]);
+}
+
 }  // namespace lfgc
 
 using namespace lfgc;
@@ -296,6 +333,47 @@ static int launch_adam(float* p, float* g, float* m, float* v, int64_t n, const 
     const int64_t blocks = n == 0 ? 1 : (n + 1023) / 1024;   // 256 threads x 4 parameters
     (void)launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), st, p, g, m, v, n, lr, step_count,
                      make_adam_coef(beta1, beta2, eps, grad_scale), reg);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
+
+static int fill_segments(DklSegments& seg, int n_layers, const int64_t* layer_sizes, long long& total) {
+    if (!layer_sizes || n_layers < 1 || n_layers > LFGC_MAX_LEVELS) return fail(LFGC_E_INVALID, "variational masks: bad layer list");
+    seg.n_layers = n_layers;
+    long long acc = 0;
+    for (int i = 0; i < n_layers; ++i) {
+        if (layer_sizes[i] < 0) return fail(LFGC_E_INVALID, "variational masks: negative layer size");
+        acc += layer_sizes[i];
+        seg.end[i] = acc;
+    }
+    total = acc;
+    return LFGC_OK;
+}
+
+extern "C" int lfgc_variational_multiplier(const float* mask_params, const float* noise, int n_layers,
+                                           const int64_t* layer_sizes, float* mult_out, float* zero_out, void* stream) {
+    if (!mask_params || !noise || !mult_out) return fail(LFGC_E_INVALID, "variational_multiplier: null pointer");
+    DklSegments seg;
+    long long total = 0;
+    const int rc = fill_segments(seg, n_layers, layer_sizes, total);
+    if (rc) return rc;
+    if (total == 0) return LFGC_OK;
+    (void)launch_pdl(variational_multiplier_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)stream,
+                     mask_params, noise, seg, mult_out, zero_out);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
+
+extern "C" int lfgc_variational_param_grad(const float* mask_params, const float* noise, const float* gmult, int n_layers,
+                                           const int64_t* layer_sizes, float* mask_grads, void* stream) {
+    if (!mask_params || !noise || !gmult || !mask_grads) return fail(LFGC_E_INVALID, "variational_param_grad: null pointer");
+    DklSegments seg;
+    long long total = 0;
+    const int rc = fill_segments(seg, n_layers, layer_sizes, total);
+    if (rc) return rc;
+    if (total == 0) return LFGC_OK;
+    (void)launch_pdl(variational_param_grad_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)stream,
+                     mask_params, noise, gmult, seg, mask_grads);
     LFGC_LAUNCH_OK();
     return LFGC_OK;
 }

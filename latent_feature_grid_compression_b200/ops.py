@@ -305,6 +305,24 @@ def variational_dkl_grad(mask_params, mask_grads, layer_sizes, w_dkl, step_dev, 
             'lfgc_variational_dkl_grad')
 
 
+def variational_multiplier(mask_params, noise, layer_sizes, mult_out, zero_out=None):
+    """Multipliers of all live variational mask layers in one launch (lfgc_variational_multiplier)."""
+    sizes = (ct.c_int64 * len(layer_sizes))(*[int(v) for v in layer_sizes])
+    L.check(L.load().lfgc_variational_multiplier(_p(_req(mask_params, 'mask_params')), _p(_req(noise, 'noise')),
+                                                 len(layer_sizes), sizes, _p(_req(mult_out, 'mult_out')), _p(zero_out),
+                                                 _stream()), 'lfgc_variational_multiplier')
+
+
+def variational_param_grad(mask_params, noise, gmult, layer_sizes, mask_grads):
+    """d loss / d(log_thetas, log_var) of all live variational mask layers in one launch, written into the flat mask
+    gradient section (lfgc_variational_param_grad)."""
+    sizes = (ct.c_int64 * len(layer_sizes))(*[int(v) for v in layer_sizes])
+    L.check(L.load().lfgc_variational_param_grad(_p(_req(mask_params, 'mask_params')), _p(_req(noise, 'noise')),
+                                                 _p(_req(gmult, 'gmult')), len(layer_sizes), sizes,
+                                                 _p(_req(mask_grads, 'mask_grads')), _stream()),
+            'lfgc_variational_param_grad')
+
+
 def sample(volume_shape, n: int, seed: int = 0, sample_offset: int = 0, volume=None, explicit_idx=None,
            want_raw=True, want_norm=True, want_gt=False, device=None, step_dev=None, step_stride: int = 0, out=None):
     lib = L.load()

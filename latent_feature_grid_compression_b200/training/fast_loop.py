@@ -217,6 +217,16 @@ class FastTrainer:
                 sizes.append(d.log_thetas.numel())
                 off += 2 * d.log_thetas.numel()
             self._var_sizes = sizes
+            # every level carries a live variational mask (the shipped variational configs): multipliers, their gradients
+            # and the noise of ALL levels live in flat buffers, one launch each way (lfgc_variational_multiplier /
+            # _param_grad), no per-layer copies or memsets
+            self._var_fast = (len(self._var_layers) == len(model.drop) and len(model.drop) > 0
+                              and self.n_mask_elems == 2 * sum(sizes))
+            if self._var_fast:
+                npos = sum(sizes)
+                self._vnoise = torch.zeros(npos, device=self.device)
+                self._vmult = torch.zeros(npos, device=self.device)
+                self._vgmult = torch.zeros(npos, device=self.device)
 
     # ------------------------------------------------------------------------------------------------------------
     def _set_red(self, par):
@@ -243,9 +253,25 @@ class FastTrainer:
             return self._step_body_gstep(host_fed, in_coords, in_targets)
         if self._smallify:
             return self._step_body_smallify(host_fed, in_coords, in_targets)
-        specs = model.mask_specs()
-        mults, auxs = _multipliers(specs)
+        var_fast = self.var_cfg is not None and getattr(self, '_var_fast', False)
         coeffs = [p.data for p in self.coeff_params]
+        if var_fast:
+            # fresh xi ~ N(0,1) per mask element and step (Variational_Dropout_Layer.py:105); one draw per level, in level
+            # order, so that the generator is consumed exactly like the module path's randn_like calls
+            off = 0
+            for n_i in self._var_sizes:
+                self._vnoise[off:off + n_i].normal_()
+                off += n_i
+            a_, b_ = self.mask_off, self.mask_off + self.n_mask_elems
+            ops.variational_multiplier(self.flat_p[a_:b_], self._vnoise, self._var_sizes, self._vmult, zero_out=self._vgmult)
+            specs, mults, off = [], [], 0
+            for d, n_i in zip(self.model.drop, self._var_sizes):
+                mults.append(self._vmult[off:off + n_i].view(d.log_thetas.shape))
+                off += n_i
+            auxs = mults
+        else:
+            specs = model.mask_specs()
+            mults, auxs = _multipliers(specs)
         # the synthesis also clears the grid-gradient accumulator; the fused kernel overwrites loss_sum
         ops.decode_fwd(geom, coeffs, mults, scratch=self.scratch, out=self.grid_cl, also_zero=self.grad_grid)
         n_global = self.batch * self.world
@@ -274,9 +300,19 @@ class FastTrainer:
             if vm is not None:
                 ops.plain_mlp_backward(vm.width, vm.n_layers, in_coords, self._dlog_sigma, self.var_flat,
                                        grad_mlp=self.flat_g[self.var_off:], workspace=self._var_ws)
-        want = [s is not None and len(s.grad_params) > 0 for s in specs]
-        _, gmults = ops.decode_bwd(geom, self.grad_grid, coeffs, auxs, want, scratch=self.scratch,
-                                   grad_coeffs=[self.grad_of(p) for p in self.coeff_params])
+        if var_fast:
+            gviews, off = [], 0
+            for d, n_i in zip(self.model.drop, self._var_sizes):
+                gviews.append(self._vgmult[off:off + n_i].view(d.log_thetas.shape))
+                off += n_i
+            ops.decode_bwd(geom, self.grad_grid, coeffs, auxs, [True] * len(gviews), scratch=self.scratch,
+                           grad_coeffs=[self.grad_of(p) for p in self.coeff_params], grad_mults=gviews, accumulate=2)
+            ops.variational_param_grad(self.flat_p[a_:b_], self._vnoise, self._vgmult, self._var_sizes, self.flat_g[a_:b_])
+            gmults = []
+        else:
+            want = [s is not None and len(s.grad_params) > 0 for s in specs]
+            _, gmults = ops.decode_bwd(geom, self.grad_grid, coeffs, auxs, want, scratch=self.scratch,
+                                       grad_coeffs=[self.grad_of(p) for p in self.coeff_params])
         for spec, gm in zip(specs, gmults):
             if spec is None or not spec.grad_params:
                 continue
@@ -297,6 +333,10 @@ class FastTrainer:
                                          1.0 + float(cfg['weight_dkl_multiplier']), float(cfg.get('weight_dkl_max', 30.0)),
                                          self.var_scale)
             ww = float(cfg['weight_weights']) * self.var_scale
+            if var_fast:   # the weight term rides in the Adam kernel
+                ops.adam_reg(self.flat_p, g_red, self.flat_m, self.flat_v, self.lr_dev, self.step_dev,
+                             (0, self.n_coeff_elems), ww, (0, 0), 0.0, self.betas[0], self.betas[1], self.eps)
+                return
             if ww > 0.0 and self.n_coeff_elems:
                 ops.add_l2_grad(g_red[:self.n_coeff_elems], self.flat_p[:self.n_coeff_elems], ww)
         # sample-independent regularisers (SmallifyLoss): added once, after the reduction
