@@ -325,16 +325,12 @@ int lfgc_grid_step_supported(const lfgc_wavelet_desc* w);
  * the sources being every rank's buffer as mapped into THIS process (peer memory, e.g. torch symmetric memory), behind a
  * barrier inside the kernel: this rank stores its epoch (epoch[0] + 1) into slot [rank] of every rank's flag array
  * (flags[r]: int32[n_srcs]) and waits until all n_srcs slots of its own array carry it; the kernel then publishes the new
- * epoch (epoch: device int32[3] = {epochs so far, two ticket scratch words}, all 0 at the start).  Every rank must issue
- * the same sequence of launches.  The caller double-buffers the sources by step parity, so one barrier per step suffices;
- * `zero` (nullable, n floats: the other parity's local buffer) is cleared in the same pass.  n must be a multiple of 4 and
- * the buffers 16-byte aligned.  Optional first phase (partials != NULL): the nslices x pstride partial sums of
- * lfgc_train_step_partials are reduced (fixed order) into local_mlp[pcount + 1] -- a region of THIS rank's source buffer --
- * and loss_out[0] before the rank announces itself, which saves the separate reduction launch.
- * Replaces the NCCL all-reduce of the path when the ranks share a node. */
+ * epoch (epoch: device int32[2] = {epochs so far, ticket scratch}, both 0 at the start).  Every rank must issue the same
+ * sequence of launches.  The caller double-buffers the sources by step parity, so one barrier per step suffices; `zero`
+ * (nullable, n floats: the other parity's local buffer) is cleared in the same pass.  n must be a multiple of 4 and the
+ * buffers 16-byte aligned.  Replaces the NCCL all-reduce of the path when the ranks share a node. */
 int lfgc_peer_sum(const float* const* srcs, int32_t* const* flags, int n_srcs, int rank, int32_t* epoch, float* out,
-                  float* zero, int64_t n, const float* partials, int nslices, int pstride, int pcount, float* local_mlp,
-                  float* loss_out, void* stream);
+                  float* zero, int64_t n, void* stream);
 
 /* Gradient of the KL regulariser of VariationalDropoutLoss (model/Variational_Dropout_Layer.py:54-69,115-122) added
  * in place to the mask-parameter gradients, and the per-step ramp of its weight (:57-58).  mask_params / mask_grads

@@ -88,8 +88,7 @@ _SIGNATURES = {
     'lfgc_adam': (C.c_int, [_f, _f, _f, _f, _i64, _f, _f, C.c_double, C.c_double, C.c_double, C.c_double, _f]),
     'lfgc_adam_reg': (C.c_int, [_f, _f, _f, _f, _i64, _f, _f, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _i64,
                                 C.c_double, _i64, _i64, C.c_double, _f, _f, C.c_float, C.c_int, _f]),
-    'lfgc_peer_sum': (C.c_int, [C.POINTER(_f), C.POINTER(_f), C.c_int, C.c_int, _f, _f, _f, _i64, _f, C.c_int, C.c_int,
-                                C.c_int, _f, _f, _f]),
+    'lfgc_peer_sum': (C.c_int, [C.POINTER(_f), C.POINTER(_f), C.c_int, C.c_int, _f, _f, _f, _i64, _f]),
     'lfgc_add_l2_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_add_l1_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_train_step_partials': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f,

@@ -114,67 +114,18 @@ struct PeerSumArgs {
     const float* src[LFGC_MAX_PEERS];
     int* flags[LFGC_MAX_PEERS];
     int n_srcs, rank;
-    int* epoch;            // [0] epochs so far, [1] ticket of the epoch publication, [2] ticket of the local reduction
+    int* epoch;
     float* out;
     float* zero;
     long long n;
-    // optional first phase: this rank's MLP-gradient partial sums (lfgc_train_step_partials) are reduced into its own
-    // source buffer before it is announced, which saves the separate reduction launch
-    const float* partials;
-    int nslices, pstride, pcount;
-    float* local_mlp;      // pcount + 1 floats inside src[rank]: MLP gradient, then the loss slot
-    float* loss_out;
 };
 
 __global__ void __launch_bounds__(512) peer_sum_kernel(const __grid_constant__ PeerSumArgs A) {
     LFGC_PDL_PROLOGUE();
-    __shared__ float s_red[512];
-    __shared__ int s_last;
     const int tid = threadIdx.x;
     const int e = *reinterpret_cast<volatile int*>(A.epoch) + 1;
-    bool announce = blockIdx.x == 0;
-    if (A.partials) {
-        // 64 parameters x 8 slice groups per chunk, fixed summation order (deterministic)
-        constexpr int PX = 64, SY = 512 / PX;
-        const int px = tid % PX, sy = tid / PX;
-        const int nchunks = (A.pcount + 1 + PX - 1) / PX;
-        for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-            const int j = ch * PX + px;
-            float acc = 0.0f;
-            if (j <= A.pcount) {
-                const float* src = A.partials + j;
-                for (int b = sy; b < A.nslices; b += 4 * SY) {
-                    float t0 = __ldcg(src + (size_t)b * A.pstride), t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
-                    if (b + SY < A.nslices) t1 = __ldcg(src + (size_t)(b + SY) * A.pstride);
-                    if (b + 2 * SY < A.nslices) t2 = __ldcg(src + (size_t)(b + 2 * SY) * A.pstride);
-                    if (b + 3 * SY < A.nslices) t3 = __ldcg(src + (size_t)(b + 3 * SY) * A.pstride);
-                    acc += (t0 + t1) + (t2 + t3);
-                }
-            }
-            s_red[sy * PX + px] = acc;
-            __syncthreads();
-            if (sy == 0 && j <= A.pcount) {
-                float t = 0.0f;
-#pragma unroll
-                for (int g = 0; g < SY; ++g) t += s_red[g * PX + px];
-                A.local_mlp[j] = t;
-                if (j == A.pcount && A.loss_out) A.loss_out[0] = t;
-            }
-            __syncthreads();
-        }
-        // the CTA that finishes last announces this rank (all CTAs' writes are fenced to system scope first)
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            const int ticket = atomicAdd(A.epoch + 2, 1);
-            s_last = ticket == (int)gridDim.x - 1;
-            if (s_last) A.epoch[2] = 0;
-        }
-        __syncthreads();
-        announce = s_last != 0;
-    }
     if (tid < A.n_srcs) {
-        if (announce) {
+        if (blockIdx.x == 0) {
             __threadfence_system();
             asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(A.flags[tid] + A.rank), "r"(e) : "memory");
         }
@@ -405,11 +356,9 @@ extern "C" int lfgc_adam_reg(float* p, float* g, float* m, float* v, int64_t n, 
 }
 
 extern "C" int lfgc_peer_sum(const float* const* srcs, int32_t* const* flags, int n_srcs, int rank, int32_t* epoch, float* out,
-                             float* zero, int64_t n, const float* partials, int nslices, int pstride, int pcount,
-                             float* local_mlp, float* loss_out, void* stream) {
+                             float* zero, int64_t n, void* stream) {
     if (!srcs || !flags || !epoch || !out || n < 0 || (n & 3)) return fail(LFGC_E_INVALID, "peer_sum: bad arguments (n must be a multiple of 4)");
     if (n_srcs < 1 || n_srcs > LFGC_MAX_PEERS || rank < 0 || rank >= n_srcs) return fail(LFGC_E_UNSUPPORTED, "peer_sum: %d sources, rank %d", n_srcs, rank);
-    if (partials && (!local_mlp || nslices < 1 || pcount < 0 || pstride < pcount + 1)) return fail(LFGC_E_INVALID, "peer_sum: bad partial-sum arguments");
     PeerSumArgs A = {};
     for (int r = 0; r < n_srcs; ++r) {
         if (!srcs[r] || !flags[r]) return fail(LFGC_E_INVALID, "peer_sum: pointer of rank %d is null", r);
@@ -422,19 +371,9 @@ extern "C" int lfgc_peer_sum(const float* const* srcs, int32_t* const* flags, in
     A.out = out;
     A.zero = zero;
     A.n = n;
-    A.partials = partials;
-    A.nslices = nslices;
-    A.pstride = pstride;
-    A.pcount = pcount;
-    A.local_mlp = local_mlp;
-    A.loss_out = loss_out;
     int blocks = (int)((n / 4 + 511) / 512);
-    if (partials) {
-        const int nchunks = (pcount + 1 + 63) / 64;
-        if (nchunks > blocks) blocks = nchunks;
-    }
     if (blocks < 1) blocks = 1;
-    if (blocks > sm_count()) blocks = sm_count();   // all CTAs must be co-resident while they wait on the flags
+    if (blocks > 2 * sm_count()) blocks = 2 * sm_count();   // all CTAs must be co-resident while they wait on the flags
     (void)launch_pdl(peer_sum_kernel, dim3((unsigned)blocks), dim3(512), (size_t)0, (cudaStream_t)stream, A);
     LFGC_LAUNCH_OK();
     return LFGC_OK;

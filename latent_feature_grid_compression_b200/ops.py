@@ -431,17 +431,14 @@ def train_step_partials(geom: Geometry, volume, n: int, seed: int, sample_offset
     return int(ns.value)
 
 
-def peer_sum(src_addrs, flag_addrs, rank: int, epoch, out, zero=None, partials=None, nslices=0, pstride=0, pcount=0,
-             local_mlp=None, loss_out=None):
+def peer_sum(src_addrs, flag_addrs, rank: int, epoch, out, zero=None):
     """out = sum over the ranks' buffers (raw device addresses, peer memory) behind the in-kernel barrier
-    (lfgc_peer_sum); ``epoch``: int32[3] device tensor; ``zero``: buffer cleared in the same pass; ``partials``: this
-    rank's deferred MLP-gradient partial sums, reduced into ``local_mlp`` (inside its source buffer) first."""
+    (lfgc_peer_sum); ``epoch``: int32[2] device tensor; ``zero``: buffer cleared in the same pass."""
     lib = L.load()
     _req(epoch, 'epoch', torch.int32)
     _req(out, 'out')
     L.check(lib.lfgc_peer_sum(L.ptr_array([int(a) for a in src_addrs]), L.ptr_array([int(a) for a in flag_addrs]),
-                              len(src_addrs), int(rank), _p(epoch), _p(out), _p(zero), out.numel(), _p(partials),
-                              int(nslices), int(pstride), int(pcount), _p(local_mlp), _p(loss_out), _stream()),
+                              len(src_addrs), int(rank), _p(epoch), _p(out), _p(zero), out.numel(), _stream()),
             'lfgc_peer_sum')
 
 

@@ -147,7 +147,7 @@ class FastTrainer:
             self._p2p = dict(buf=buf, hdl=hdl, rank=int(hdl.rank),
                              peers=[[b + 4 * self._n_red * par for b in bases] for par in (0, 1)],
                              flags=[b + 4 * 2 * self._n_red for b in bases],
-                             epoch=torch.zeros(3, device=self.device, dtype=torch.int32),
+                             epoch=torch.zeros(2, device=self.device, dtype=torch.int32),
                              summed=torch.zeros(self._n_red, device=self.device, dtype=torch.float32))
             torch.cuda.synchronize()
             dist.barrier(group=grp)          # every rank's flags are zero before anybody's first launch
@@ -404,23 +404,18 @@ class FastTrainer:
             ops.grid_step(geom, [self.grad_grid], [self.workspace], ns, pcount + 1, pcount, loss_out=self.loss_sum,
                           **common)
             return
+        ops.train_step(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl, self.mlp_flat,
+                       self.grad_grid, self.red_mlp[:pcount], self.loss_sum, self.workspace, **kw)
         if self._p2p is None:
-            ops.train_step(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl, self.mlp_flat,
-                           self.grad_grid, self.red_mlp[:pcount], self.loss_sum, self.workspace, **kw)
             torch.distributed.all_reduce(self.red, group=self.group)
             ops.grid_step(geom, [self.grad_grid], [self.red_mlp], 1, pcount + 1, pcount, **common)
             return
-        # lfgc_peer_sum: reduces this rank's partial sums into its buffer, then this step's buffers of all ranks -> one
-        # local sum (barrier inside the kernel); the accumulator it clears is the OTHER parity's (its last readers finished
-        # before they announced this epoch)
+        # lfgc_peer_sum: this step's buffers of all ranks -> one local sum (barrier inside the kernel); the accumulator it
+        # clears is the OTHER parity's (its last readers finished before they announced this epoch)
         P = self._p2p
         par = self._par
         n_grid = self.grid_cl.numel()
-        ns = ops.train_step_partials(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl,
-                                     self.mlp_flat, self.grad_grid, self.workspace, **kw)
-        ops.peer_sum(P['peers'][par], P['flags'], P['rank'], P['epoch'], P['summed'], zero=self._red2[par ^ 1],
-                     partials=self.workspace, nslices=ns, pstride=pcount + 1, pcount=pcount, local_mlp=self.red_mlp,
-                     loss_out=self.loss_sum)
+        ops.peer_sum(P['peers'][par], P['flags'], P['rank'], P['epoch'], P['summed'], zero=self._red2[par ^ 1])
         common['zero_grid'] = None
         ops.grid_step(geom, [P['summed'][:n_grid]], [P['summed'][n_grid:]], 1, pcount + 1, pcount, **common)
 
