@@ -527,8 +527,10 @@ def measure_config(name, volume, rank, world, dev, pk, opt_steps=300, with_recon
             trainer.grad_grid.zero_()
             if i >= 5:
                 ke[i - 5][0].record()
-            ops.train_step(geom, volume, n, 1234, 0, 1.0 / n, trainer.grid_cl, trainer.mlp_flat, trainer.grad_grid, gm,
-                           trainer.loss_sum, trainer.workspace, step_dev=trainer.step_dev, step_stride=n)
+            # the fused per-sample kernel ALONE (its MLP-gradient partial sums stay in the workspace; their reduction is a
+            # separate launch / part of lfgc_grid_step)
+            ops.train_step_partials(geom, volume, n, 1234, 0, 1.0 / n, trainer.grid_cl, trainer.mlp_flat,
+                                    trainer.grad_grid, trainer.workspace, step_dev=trainer.step_dev, step_stride=n)
             if i >= 5:
                 ke[i - 5][1].record()
         torch.cuda.synchronize()
@@ -684,8 +686,10 @@ def run_native(args):
             trainer.grad_grid.zero_()
             if i >= 5:
                 ke[i - 5][0].record()
-            ops.train_step(geom, volume, n, 1234, 0, 1.0 / n, trainer.grid_cl, trainer.mlp_flat, trainer.grad_grid, gm,
-                           trainer.loss_sum, trainer.workspace, step_dev=trainer.step_dev, step_stride=n)
+            # the fused per-sample kernel ALONE (its MLP-gradient partial sums stay in the workspace; their reduction is a
+            # separate launch / part of lfgc_grid_step)
+            ops.train_step_partials(geom, volume, n, 1234, 0, 1.0 / n, trainer.grid_cl, trainer.mlp_flat,
+                                    trainer.grad_grid, trainer.workspace, step_dev=trainer.step_dev, step_stride=n)
             if i >= 5:
                 ke[i - 5][1].record()
         torch.cuda.synchronize()
@@ -705,7 +709,7 @@ def run_native(args):
                              'the contractions run on tcgen05 (see roofline_tensor), the kernel time is the per-sample fp32 '
                              'work left on the SM (gather, Fourier, SnakeAlt, hi/lo splits, scatter) and its latency '
                              'chain, so the CUDA-core FFMA2 peak stays the yardstick (it is what the FFMA2 kernel is '
-                             'bounded by).  Timed as lfgc_train_step = kernel + partial reduction' % (fwd + bwd))
+                             'bounded by).  Timed as lfgc_train_step_partials = this kernel alone' % (fwd + bwd))
         tf32_peak = pk.get('bf16_tflops', 1654.2) / 2.0
         roofline_tensor = dict(bound='tensor', achieved=ach_tflops, peak=tf32_peak, unit='TFLOP/s',
                                frac=ach_tflops / tf32_peak, executed_over_algorithmic=2.6,
