@@ -14,7 +14,8 @@
 //               A2  one CTA per (channel, iz): y^T pass -> x^T pass in shared memory -> the 8 band gradients
 //
 // All intermediates are CHANNEL-FIRST (the reference's coefficient layout), so every global access is a contiguous run;
-// the channels-last grid the sample kernels read (and its gradient) is converted by a tiled transpose at the finest level.
+// the z passes of the finest level turn 32 x 32 (position, channel) tiles in shared memory to read / write the
+// channels-last grid the sample kernels use.
 // HBM traffic per level ~ 4 x the level's output size instead of 64 L2 loads per vertex.
 #include "wavelet_lines.cuh"
 
@@ -174,46 +175,110 @@ __global__ void __launch_bounds__(256) adj_yx_kernel(const __grid_constant__ Lev
     }
 }
 
-// ---- layout conversion at the finest level: channel-first [C][n] <-> channels-last [n][Cp], 32 x 32 tiles ------------------
-__global__ void __launch_bounds__(1024) to_channels_last_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                                                float* __restrict__ also_zero, int C, int Cp, long long n) {
+// ---- finest level: the z passes read / write the CHANNELS-LAST grid directly ----------------------------------------------------
+// A separate transpose of the 33.5 MB grid (and of its gradient) cost 39 + 33 us per step at C32/G64; here the 32 x 32
+// (position, channel) tile is turned inside the z-pass kernels: compute with lane = position (contiguous Y accesses),
+// touch the grid with lane = channel (contiguous channels-last accesses).
+template <int NT>
+__global__ void __launch_bounds__(1024) synth_z_cl_kernel(const __grid_constant__ Level L, const float* __restrict__ Y,
+                                                          float* __restrict__ grid_cl, float* __restrict__ also_zero, int Cp) {
     LFGC_PDL_PROLOGUE();
-    __shared__ float tile[32][33];
-    const long long p0 = (long long)blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
+    __shared__ float tile[2][32][33];
+    const int d0 = L.d[0], t0 = L.t[0], pl = L.t[1] * L.t[2];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    {
-        const int c = c0 + ty;
-        const long long p = p0 + tx;
-        tile[ty][tx] = (c < C && p < n) ? __ldg(src + (size_t)c * n + p) : 0.0f;
+    const int pos = blockIdx.x * 32 + tx, c = blockIdx.y * 32 + ty;       // compute role: lane = position
+    const int wpos = blockIdx.x * 32 + ty, wc = blockIdx.y * 32 + tx;      // write role:   lane = channel
+    const bool live = pos < pl && c < L.C;
+    float flo[NT], fhi[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        flo[i] = L.lo[i];
+        fhi[i] = L.hi[i];
     }
-    __syncthreads();
-    {
-        const int c = c0 + tx;
-        const long long p = p0 + ty;
-        if (c < Cp && p < n) {
-            dst[(size_t)p * Cp + c] = tile[tx][ty];
-            if (also_zero) also_zero[(size_t)p * Cp + c] = 0.0f;
+    const float* y0 = Y + (size_t)(live ? c : 0) * 2 * d0 * pl + (live ? pos : 0);
+    const float* y1 = y0 + (size_t)d0 * pl;
+    for (int m = L.m_lo[0]; m < L.m_lo[0] + L.n_m[0]; ++m) {
+        float ev = 0.0f, od = 0.0f;
+        if (live) {
+#pragma unroll
+            for (int a = 0; a < NT / 2; ++a) {
+                const int i = m - a;
+                if ((unsigned)i < (unsigned)d0) {
+                    const float l = __ldg(y0 + (size_t)i * pl), h = __ldg(y1 + (size_t)i * pl);
+                    ev = fmaf(l, flo[2 * a], ev);
+                    ev = fmaf(h, fhi[2 * a], ev);
+                    od = fmaf(l, flo[2 * a + 1], od);
+                    od = fmaf(h, fhi[2 * a + 1], od);
+                }
+            }
         }
+        tile[0][ty][tx] = ev;      // [channel][position]
+        tile[1][ty][tx] = od;
+        __syncthreads();
+        const int oe = 2 * m - L.off[0];
+        if (wpos < pl && wc < Cp) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int oz = oe + k;
+                if ((unsigned)oz < (unsigned)t0) {
+                    const size_t o = ((size_t)oz * pl + wpos) * Cp + wc;
+                    grid_cl[o] = tile[k][tx][ty];
+                    if (also_zero) also_zero[o] = 0.0f;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
-__global__ void __launch_bounds__(1024) from_channels_last_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                                                  int C, int Cp, long long n) {
+
+template <int NT>
+__global__ void __launch_bounds__(1024) adj_z_cl_kernel(const __grid_constant__ Level L, const float* __restrict__ g_cl, int Cp,
+                                                        float* __restrict__ Y) {
     LFGC_PDL_PROLOGUE();
-    __shared__ float tile[32][33];
-    const long long p0 = (long long)blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
+    __shared__ float tile[2][32][33];
+    const int d0 = L.d[0], t0 = L.t[0], pl = L.t[1] * L.t[2];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    {
-        const int c = c0 + tx;
-        const long long p = p0 + ty;
-        tile[ty][tx] = (c < C && p < n) ? __ldg(src + (size_t)p * Cp + c) : 0.0f;
+    const int pos = blockIdx.x * 32 + tx, c = blockIdx.y * 32 + ty;       // compute role: lane = position
+    const int rpos = blockIdx.x * 32 + ty, rc = blockIdx.y * 32 + tx;      // read role:    lane = channel
+    const bool live = pos < pl && c < L.C;
+    const bool rlive = rpos < pl && rc < L.C;
+    float flo[NT], fhi[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        flo[i] = L.lo[i];
+        fhi[i] = L.hi[i];
     }
-    __syncthreads();
-    {
-        const int c = c0 + ty;
-        const long long p = p0 + tx;
-        if (c < C && p < n) dst[(size_t)c * n + p] = tile[tx][ty];
+    // window of the NT output planes q0 .. q0 + NT - 1 (q0 = 2 i - off) this thread's input position i sees; it slides by two
+    float w[NT];
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt) w[tt] = 0.0f;
+    float* y0 = Y + (size_t)(live ? c : 0) * 2 * d0 * pl + (live ? pos : 0);
+    float* y1 = y0 + (size_t)d0 * pl;
+    // planes below the first window position that are still inside it: load NT - 2 planes up front (q = -off .. -off + NT - 3)
+    for (int i = -((NT - 2) / 2); i < d0; ++i) {
+        // the two planes entering the window of input position i: q = 2 i + NT - 2 - off and the next one
+        const int qa = 2 * i + NT - 2 - L.off[0];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int q = qa + k;
+            tile[k][ty][tx] = (rlive && (unsigned)q < (unsigned)t0) ? __ldg(g_cl + ((size_t)q * pl + rpos) * Cp + rc) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tt = 0; tt + 2 < NT; ++tt) w[tt] = w[tt + 2];
+        w[NT - 2] = tile[0][tx][ty];      // [position][channel] as stored by the read role
+        w[NT - 1] = tile[1][tx][ty];
+        __syncthreads();
+        if (i >= 0 && live) {
+            float lo = 0.0f, hi = 0.0f;
+#pragma unroll
+            for (int tt = 0; tt < NT; ++tt) {
+                lo = fmaf(w[tt], flo[tt], lo);
+                hi = fmaf(w[tt], fhi[tt], hi);
+            }
+            y0[(size_t)i * pl] = lo;
+            y1[(size_t)i * pl] = hi;
+        }
     }
 }
 
@@ -298,18 +363,19 @@ static int sep_fwd(const lfgc_wavelet_desc* w, const float* const* coeff, float*
         LFGC_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
         (void)launch_pdl(k1, dim3((unsigned)L.d[0], (unsigned)L.C), dim3(256), sm1, st, L, low, coeff[l], Y);
         LFGC_LAUNCH_OK();
-        float* out = buf[l & 1];
         const int pl = L.t[1] * L.t[2];
+        if (l == w->n_coeff - 1) {   // finest level: straight into the channels-last grid
+            (void)launch_pdl(synth_z_cl_kernel<NT>, dim3((unsigned)((pl + 31) / 32), (unsigned)((Cp + 31) / 32)), dim3(1024), (size_t)0,
+                             st, L, (const float*)Y, grid_cl, also_zero, Cp);
+            LFGC_LAUNCH_OK();
+            break;
+        }
+        float* out = buf[l & 1];
         (void)launch_pdl(synth_z_kernel<NT>, dim3((unsigned)((pl + 255) / 256), (unsigned)L.C), dim3(256), (size_t)0, st, L,
                          (const float*)Y, out);
         LFGC_LAUNCH_OK();
         low = out;
     }
-    const int last = w->n_coeff - 1;
-    const long long n = (long long)w->target[last][0] * w->target[last][1] * w->target[last][2];
-    (void)launch_pdl(to_channels_last_kernel, dim3((unsigned)((n + 31) / 32), (unsigned)((Cp + 31) / 32)), dim3(1024), (size_t)0,
-                     st, low, grid_cl, also_zero, w->C, Cp, n);
-    LFGC_LAUNCH_OK();
     return LFGC_OK;
 }
 
@@ -327,17 +393,17 @@ static int sep_bwd(const lfgc_wavelet_desc* w, const float* grad_grid_cl, int Cp
     float* Y = scratch;
     float* buf[2] = {scratch + ybuf, scratch + ybuf + inter};
     const int last = w->n_coeff - 1;
-    const long long n = (long long)w->target[last][0] * w->target[last][1] * w->target[last][2];
-    float* g = buf[last & 1];
-    (void)launch_pdl(from_channels_last_kernel, dim3((unsigned)((n + 31) / 32), (unsigned)((w->C + 31) / 32)), dim3(1024),
-                     (size_t)0, st, grad_grid_cl, g, w->C, Cp, n);
-    LFGC_LAUNCH_OK();
+    const float* g = nullptr;
     for (int l = last; l >= 1; --l) {
         Level L;
         fill_level(L, w, l);
         const int pl = L.t[1] * L.t[2];
-        (void)launch_pdl(adj_z_kernel<NT>, dim3((unsigned)((pl + 255) / 256), (unsigned)L.C), dim3(256), (size_t)0, st, L,
-                         (const float*)g, Y);
+        if (l == last) {   // finest level: straight from the channels-last gradient
+            (void)launch_pdl(adj_z_cl_kernel<NT>, dim3((unsigned)((pl + 31) / 32), (unsigned)((L.C + 31) / 32)), dim3(1024), (size_t)0,
+                             st, L, grad_grid_cl, Cp, Y);
+        } else {
+            (void)launch_pdl(adj_z_kernel<NT>, dim3((unsigned)((pl + 255) / 256), (unsigned)L.C), dim3(256), (size_t)0, st, L, g, Y);
+        }
         LFGC_LAUNCH_OK();
         float* g_low = l == 1 ? grad_coeff[0] : buf[(l - 1) & 1];
         auto k2 = adj_yx_kernel<NT>;
