@@ -305,6 +305,60 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     const int nfix = 3 + 6 * P.F;
     const int Cp = P.Cp;
 
+    // ---- sample position and layer-0 gathers -------------------------------------------------------------------------------
+    uint64_t sample_base = A.sample_offset;
+    if (FUSED && A.step_dev) sample_base += (uint64_t)(*A.step_dev) * A.step_stride;
+    const bool small_volume = A.n_voxels <= 0xFFFFFFFFull;   // 32-bit index arithmetic (every shipped volume)
+    auto load_position = [&](int64_t sg, bool valid, float& cx, float& cy, float& cz, float& aux) {
+        cx = cy = cz = aux = 0.0f;
+        if (!valid) return;
+        if (FUSED && !A.coords) {
+            const unsigned long long v = A.explicit_idx ? (unsigned long long)A.explicit_idx[sg]
+                                                        : philox_voxel(A.seed, sample_base + (uint64_t)sg, A.n_voxels);
+            int i, j, k;
+            if (small_volume) {
+                const unsigned v32 = (unsigned)v, r2 = (unsigned)A.R[2], r12 = (unsigned)A.R[1] * r2;
+                const unsigned ii = v32 / r12, rem = v32 - ii * r12, jj = rem / r2;
+                i = (int)ii;
+                j = (int)jj;
+                k = (int)(rem - jj * r2);
+            } else {
+                const unsigned long long r12 = (unsigned long long)A.R[1] * A.R[2];
+                i = (int)(v / r12);
+                j = (int)((v / A.R[2]) % A.R[1]);
+                k = (int)(v % A.R[2]);
+            }
+            cx = normalized_coord((float)i, A.max_idx[0], A.scales[0]);
+            cy = normalized_coord((float)j, A.max_idx[1], A.scales[1]);
+            cz = normalized_coord((float)k, A.max_idx[2], A.scales[2]);
+            aux = __ldg(A.volume + v);
+        } else {  // caller-supplied positions; aux = target value (fused) or d(loss)/d(out)
+            cx = __ldg(A.coords + 3 * sg);
+            cy = __ldg(A.coords + 3 * sg + 1);
+            cz = __ldg(A.coords + 3 * sg + 2);
+            aux = __ldg(A.grad_out + sg);
+        }
+    };
+    float cx, cy, cz, aux;
+    Corners Kc;
+    float4 gv[8], gu[8];   // the first two feature chunks of this thread (c = q and q + TPS), gathered at the 8 corners
+    auto issue_gather = [&]() {
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) gv[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * q);
+        if (4 * (q + TPS) < Cp) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) gu[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * (q + TPS));
+        }
+    };
+    // The first tile's loads go out before the one-time setup below: the Philox draw, the volume read and the 16 gathers are
+    // three dependent memory round trips that now overlap the ~7 k cycles of parameter staging.
+    if ((int64_t)blockIdx.x * TILE < A.n) {
+        const int64_t sg0 = (int64_t)blockIdx.x * TILE + s;
+        load_position(sg0, sg0 < A.n, cx, cy, cz, aux);
+        make_corners(P, cx, cy, cz, Kc);
+        issue_gather();
+    }
+
     // ---- one-time setup ------------------------------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barA), "r"(1));
@@ -336,6 +390,7 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         }
     }
     __syncthreads();
+    BT_MARK(12)  // setup: zero fill, parameter staging, TMEM allocation
     {
         const float* stage = reinterpret_cast<const float*>(DmHi);
         // ones column (column 31 of group 1 of the hi block): bias gradient row of every dW accumulator
@@ -346,21 +401,30 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             const int fbase = (l == 0 ? 0 : (K0p + (l - 1) * HP) / 4) * kPanelW;
             const int bbase = l == 0 ? 0 : Lo.wb0 + (l - 1) * (HP / 4) * kPanelW;
             const int brows = l == 0 ? Lo.Np0 : HP;
-            // warp = output row j, lane = input column r: no per-element division (it used to cost ~5 us per launch)
-            for (int j = warp; j < H; j += NT / 32) {
-                for (int r = lane; r < K; r += 32) {
-                    int k = r;
-                    if (l == 0) k = r < nfix ? Cp + r : r - nfix;  // permuted layer-0 columns
+            // warp = output row j (stride NT/32), lane = input column r; everything that depends on the column only is
+            // hoisted, so an element costs a load, the split and four stores with constant strides
+            constexpr int JS = NT / 32;   // a multiple of 4: (j & 3) is the same for every j of a warp
+            for (int r = lane; r < K; r += 32) {
+                int k = r;
+                if (l == 0) k = r < nfix ? Cp + r : r - nfix;  // permuted layer-0 columns
+                const bool back = l > 0 || k < Cp;             // backward operand: only the feature columns of layer 0
+                const float* src = W + warp * K + r;
+                unsigned char* fh = WfHi + fbase + (k >> 2) * kPanelW + (k & 3) * 4 + warp * 16;            // forward: B[n = j][K = k]
+                unsigned char* bh = WbHi + bbase + k * 16 + (warp & 3) * 4 + (warp >> 2) * brows * 16;      // backward: B[n = k][K = j]
+                const int fstep = JS * 16, bstep = (JS >> 2) * brows * 16;
+                const ptrdiff_t flo = WfLo - WfHi, blo = WbLo - WbHi;
+                for (int j = warp; j < H; j += JS) {
                     float hi, lo;
-                    split_tf32(W[j * K + r], hi, lo);
-                    const int fo = fbase + (k >> 2) * kPanelW + j * 16 + (k & 3) * 4;          // forward: B[n = j][K = k]
-                    *reinterpret_cast<float*>(WfHi + fo) = hi;
-                    *reinterpret_cast<float*>(WfLo + fo) = lo;
-                    if (l > 0 || k < Cp) {                                                     // backward: B[n = k][K = j]
-                        const int bo = bbase + (j >> 2) * brows * 16 + k * 16 + (j & 3) * 4;
-                        *reinterpret_cast<float*>(WbHi + bo) = hi;
-                        *reinterpret_cast<float*>(WbLo + bo) = lo;
+                    split_tf32(*src, hi, lo);
+                    *reinterpret_cast<float*>(fh) = hi;
+                    *reinterpret_cast<float*>(fh + flo) = lo;
+                    if (back) {
+                        *reinterpret_cast<float*>(bh) = hi;
+                        *reinterpret_cast<float*>(bh + blo) = lo;
                     }
+                    src += JS * K;
+                    fh += fstep;
+                    bh += bstep;
                 }
             }
             const float* b = stage + mlp_b_off(l, in0, H);
@@ -370,6 +434,7 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         for (int j = threadIdx.x; j < HP; j += NT) wfs[j] = j < H ? wf[j] : 0.0f;
         if (threadIdx.x == 0) wfs[HP] = wf[H];
     }
+    BT_MARK(13)  // setup: weight panels
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -388,9 +453,6 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     for (int i = 0; i < CW; ++i) accWf[i] = 0.0f;
     float accbf = 0.0f, loss_part = 0.0f;
 
-    uint64_t sample_base = A.sample_offset;
-    if (FUSED && A.step_dev) sample_base += (uint64_t)(*A.step_dev) * A.step_stride;
-
     // this thread's 4 columns [j0, j0+4) of an MN-major block pair
     auto put_mn = [&](unsigned char* hi_base, unsigned char* lo_base, int j0, const float4& hi, const float4& lo) {
         const int off = mn_off(s, j0);
@@ -404,28 +466,11 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         // ---- input stage: the TPS threads of a sample take the K chunks c = q, q + TPS, ... ----------------------------
         const int64_t sg = tile * TILE + s;
         const bool valid = sg < A.n;
-        float cx = 0.f, cy = 0.f, cz = 0.f, aux = 0.f;
-        if (valid) {
-            if (FUSED && !A.coords) {
-                unsigned long long v = A.explicit_idx ? (unsigned long long)A.explicit_idx[sg]
-                                                      : philox_voxel(A.seed, sample_base + (uint64_t)sg, A.n_voxels);
-                const unsigned long long r12 = (unsigned long long)A.R[1] * A.R[2];
-                const int i = (int)(v / r12);
-                const int j = (int)((v / A.R[2]) % A.R[1]);
-                const int k = (int)(v % A.R[2]);
-                cx = normalized_coord((float)i, A.max_idx[0], A.scales[0]);
-                cy = normalized_coord((float)j, A.max_idx[1], A.scales[1]);
-                cz = normalized_coord((float)k, A.max_idx[2], A.scales[2]);
-                aux = __ldg(A.volume + v);
-            } else {  // caller-supplied positions; aux = target value (fused) or d(loss)/d(out)
-                cx = __ldg(A.coords + 3 * sg);
-                cy = __ldg(A.coords + 3 * sg + 1);
-                cz = __ldg(A.coords + 3 * sg + 2);
-                aux = __ldg(A.grad_out + sg);
-            }
+        if (!first_tile) {   // the first tile's position and gathers were issued ahead of the one-time setup
+            load_position(sg, valid, cx, cy, cz, aux);
+            make_corners(P, cx, cy, cz, Kc);
+            issue_gather();
         }
-        Corners Kc;
-        make_corners(P, cx, cy, cz, Kc);
         // one K chunk (4 columns) of the layer-0 input: tf32 hi / lo operand columns and the fp32 copy
         auto emit = [&](int c, const float (&v4)[4]) {
             float hi[4], lo[4];
@@ -435,37 +480,7 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             tmem_st<4>(trow + colA_lo(0) + 4 * c, lo);
             X0s[c * TILE + s] = make_float4(v4[0], v4[1], v4[2], v4[3]);
         };
-        // feature chunks two at a time: 16 independent 128-bit gathers in flight per thread
-        for (int c = q; 4 * c < Cp; c += 2 * TPS) {
-            const int c2 = c + TPS;
-            const bool two = 4 * c2 < Cp;
-            float4 v[8], u[8];
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) v[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c);
-            if (two) {
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) u[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c2);
-            }
-            float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
-                a[0] = fmaf(v[cc].x, Kc.w[cc], a[0]);
-                a[1] = fmaf(v[cc].y, Kc.w[cc], a[1]);
-                a[2] = fmaf(v[cc].z, Kc.w[cc], a[2]);
-                a[3] = fmaf(v[cc].w, Kc.w[cc], a[3]);
-            }
-            emit(c, a);
-            if (two) {
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    b[0] = fmaf(u[cc].x, Kc.w[cc], b[0]);
-                    b[1] = fmaf(u[cc].y, Kc.w[cc], b[1]);
-                    b[2] = fmaf(u[cc].z, Kc.w[cc], b[2]);
-                    b[3] = fmaf(u[cc].w, Kc.w[cc], b[3]);
-                }
-                emit(c2, b);
-            }
-        }
+        // positional columns first: their sincos work runs while the gathers are in flight
         for (int c = (Cp >> 2) + q; c < K0p / 4; c += TPS) {
             float v4[4];
 #pragma unroll
@@ -485,6 +500,38 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
                 v4[i] = val;
             }
             emit(c, v4);
+        }
+        // feature chunks two at a time: 16 independent 128-bit gathers in flight per thread; the first pair was issued above
+        for (int c = q; 4 * c < Cp; c += 2 * TPS) {
+            const int c2 = c + TPS;
+            const bool two = 4 * c2 < Cp;
+            if (c != q) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) gv[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c);
+                if (two) {
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) gu[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c2);
+                }
+            }
+            float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                a[0] = fmaf(gv[cc].x, Kc.w[cc], a[0]);
+                a[1] = fmaf(gv[cc].y, Kc.w[cc], a[1]);
+                a[2] = fmaf(gv[cc].z, Kc.w[cc], a[2]);
+                a[3] = fmaf(gv[cc].w, Kc.w[cc], a[3]);
+            }
+            emit(c, a);
+            if (two) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    b[0] = fmaf(gu[cc].x, Kc.w[cc], b[0]);
+                    b[1] = fmaf(gu[cc].y, Kc.w[cc], b[1]);
+                    b[2] = fmaf(gu[cc].z, Kc.w[cc], b[2]);
+                    b[3] = fmaf(gu[cc].w, Kc.w[cc], b[3]);
+                }
+                emit(c2, b);
+            }
         }
         tmem_st_wait();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -522,10 +569,15 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
                 tmem_ld<CW>(trow + cAcc + col0, z);
                 const float* bl_ = bias + l * HP + col0;
 #pragma unroll
-                for (int i = 0; i < CW; ++i) {
-                    float g;
-                    snake_and_grad_precise(z[i] + bl_[i], hs[i], g);
-                    if (l + 1 < L) { if (l + 1 < LMAX) gs[l < LMAX - 1 ? l : 0][i] = g; } else glast[i] = g;
+                for (int i = 0; i < CW; i += 2) {
+                    float g0, g1;
+                    snake_and_grad_fast2(z[i] + bl_[i], z[i + 1] + bl_[i + 1], hs[i], hs[i + 1], g0, g1);
+                    if (l + 1 < L) {
+                        if (l + 1 < LMAX) { gs[l < LMAX - 1 ? l : 0][i] = g0; gs[l < LMAX - 1 ? l : 0][i + 1] = g1; }
+                    } else {
+                        glast[i] = g0;
+                        glast[i + 1] = g1;
+                    }
                 }
                 if (l + 1 < L) {
                     float hi[CW], lo[CW];
@@ -698,68 +750,49 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* dst = A.partial + (size_t)blockIdx.x * A.pstride;
-    float* xch = reinterpret_cast<float*>(DmHi);   // [layer][row 0..63][32]: the lo * dz halves (accumulator rows 64..127)
-    if ((warp & 3) >= 2) {
-        const int row = (((warp & 3) - 2) << 5) | lane;
-        for (int l = q; l < L; l += TPS) {
-            float r[32], r2[32];
-            tmem_ld<32>(trow + cW + l * kWAcc, r);
-            tmem_ld<32>(trow + cW + l * kWAcc + HP, r2);
+    // Every accumulator row (TMEM lane) passes through shared memory once: S[layer][row 0..127][33 floats].  With a row
+    // stride of 33 both the lane-per-row stores and the row-fastest reads are bank-conflict free, and the global stores
+    // become one compact loop over the packed parameter order in which all warps take part (the former register-to-global
+    // flush was ~850 instructions of straight-line code run by half of the warps: 8.6 k cycles, mostly instruction fetch).
+    constexpr int kSRow = 33;
+    float* S = reinterpret_cast<float*>(Hm);                 // Hm and Dm are contiguous: 96 KB
+    float* red = S + LMAX * TILE * kSRow;                    // [128][36]: 32 Wf partials | bf | loss
+    for (int l = q; l < L; l += TPS) {
+        float r[32], r2[32];
+        tmem_ld<32>(trow + cW + l * kWAcc, r);               // columns: dz hi
+        tmem_ld<32>(trow + cW + l * kWAcc + HP, r2);         //          dz lo
+        float* row = S + (l * TILE + s) * kSRow;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(xch + (l * 64 + row) * 32 + j) =
-                    make_float4(r[j] + r2[j], r[j + 1] + r2[j + 1], r[j + 2] + r2[j + 2], r[j + 3] + r2[j + 3]);
-        }
+        for (int j = 0; j < 32; ++j) row[j] = r[j] + r2[j];
+    }
+#pragma unroll
+    for (int i = 0; i < CW; ++i) red[s * 36 + col0 + i] = accWf[i];
+    if (q == 0) {
+        red[s * 36 + 32] = accbf;
+        red[s * 36 + 33] = FUSED ? loss_part : 0.0f;
     }
     __syncthreads();
-    if ((warp & 3) < 2) {   // accumulator rows 0..63 live in lane quarters 0 and 1
-        const int row = ((warp & 3) << 5) | lane;
-        for (int l = q; l < L; l += TPS) {
-            float r[32];
-            {
-                float r2[32];
-                tmem_ld<32>(trow + cW + l * kWAcc, r);
-                tmem_ld<32>(trow + cW + l * kWAcc + HP, r2);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] += r2[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 o = *reinterpret_cast<const float4*>(xch + (l * 64 + row) * 32 + j);
-                r[j] += o.x; r[j + 1] += o.y; r[j + 2] += o.z; r[j + 3] += o.w;
-            }
-            const int Kin = l == 0 ? in0 : H;
-            const int woff = mlp_w_off(l, in0, H);
-            int orig = -1;   // column of W_l this accumulator row belongs to
-            if (l > 0) {
-                if (row < H) orig = row;
-            } else if (row < Cp) {
-                if (row < P.C) orig = nfix + row;
-            } else if (row < Cp + nfix) {
-                orig = row - Cp;
-            }
-            if (orig >= 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < H) dst[woff + j * Kin + orig] = r[j];
-            }
-            if (row == kOnesRow) {
-                const int boff = mlp_b_off(l, in0, H);
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < H) dst[boff + j] = r[j];
+    BT_MARK(14)  // flush: accumulators to shared memory
+    for (int l = 0; l < L; ++l) {
+        const int Kin = l == 0 ? in0 : H;
+        const int woff = mlp_w_off(l, in0, H), boff = mlp_b_off(l, in0, H);
+        const float* Sl = S + l * TILE * kSRow;
+        // warp = output row j, lane = input column k: coalesced stores, conflict-free reads, pointer increments only
+        for (int k = lane; k < Kin; k += 32) {
+            const int row = l > 0 ? k : (k < nfix ? Cp + k : k - nfix);   // layer 0: permuted columns
+            const float* src = Sl + row * kSRow + warp;                  // rows 0..63 hold hi * dz, rows 64..127 lo * dz
+            float* d = dst + woff + warp * Kin + k;
+            for (int j = warp; j < H; j += NT / 32) {
+                *d = src[0] + src[64 * kSRow];
+                src += NT / 32;
+                d += (NT / 32) * Kin;
             }
         }
+        if (warp == (l & 3) && lane < H)   // bias: the ones row
+            dst[boff + lane] = Sl[kOnesRow * kSRow + lane] + Sl[(kOnesRow + 64) * kSRow + lane];
     }
+    BT_MARK(15)  // flush: dW to the partial slice
     {
-        float* red = reinterpret_cast<float*>(Hm);   // [128][36]: 32 Wf partials | bf | loss
-#pragma unroll
-        for (int i = 0; i < CW; ++i) red[s * 36 + col0 + i] = accWf[i];
-        if (q == 0) {
-            red[s * 36 + 32] = accbf;
-            red[s * 36 + 33] = FUSED ? loss_part : 0.0f;
-        }
-        __syncthreads();
         // column sums over the 128 samples: 7 row groups x 36 columns in parallel, then 7 partials per column
         float* red2 = red + TILE * 36;
         {

@@ -12,8 +12,8 @@ mlp = m.mlp_flat()
 vol = torch.rand(255, 255, 255, device='cuda') * 2 - 1
 ws = torch.empty(geom.backward_workspace_bytes // 4, device='cuda')
 os.environ['LFGC_BACKWARD_TC'] = '1'
-names = ['setup', 'input', 'barrier', 'mma issue', 'mma wait', 'fwd epilogue', 'output+loss', 'bwd staging', 'dz', 'scatter', 'flush', 'dW wait']
-for tps in ('2', '4'):
+names = ['setup', 'input', 'barrier', 'mma issue', 'mma wait', 'fwd epilogue', 'output+loss', 'bwd staging', 'dz', 'scatter', 'flush (reduction)', 'dW wait', 'setup: fill+stage', 'setup: panels', 'flush: lo halves', 'flush: dW rows']
+for tps in ('2',):
     os.environ['LFGC_TC_TPS'] = tps
     for n in (32768, 262144):
         gg = torch.zeros((*geom.G, geom.Cp), device='cuda'); gm = torch.empty(geom.mlp_param_count, device='cuda'); ls = torch.zeros(1, device='cuda')
@@ -23,6 +23,6 @@ for tps in ('2', '4'):
         for _ in range(reps): ops.train_step(geom, vol, n, 7, 0, 1.0 / n, grid, mlp, gg, gm, ls, ws)
         buf = (ctypes.c_ulonglong * 16)(); lib.lfgc_btc_timing(buf, 1)
         ctas = min(148, (n + 127) // 128)
-        tot = sum(buf[:12])
+        tot = sum(buf[:16])
         print('tps=%s n=%d: cycles per CTA (thread 0) per launch: %.0f  (tiles per CTA %.2f)' % (tps, n, tot / reps / ctas, n / 128 / ctas))
         for i, nm in enumerate(names): print('  %-14s %9.0f %5.1f%%' % (nm, buf[i] / reps / ctas, 100.0 * buf[i] / tot))
