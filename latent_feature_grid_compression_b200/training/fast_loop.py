@@ -638,16 +638,23 @@ def _regulariser_weights(args):
 def epoch_schedule(n_voxels: int, batch_size: int, sample_size: int, max_pass: float):
     """The reference's pass accounting as a generator of (step index, prior_passes, volume_passes, last) tuples
     (training/training.py:76-114,178): the ``while int(volume_passes) + 1 < max_pass`` test is evaluated only at
-    DataLoader-epoch boundaries (one epoch = ceil(n_voxels / batch_size) batches = ``sample_size`` volume passes);
-    inside an epoch the loop leaves only through ``int(volume_passes) >= max_pass``.  The caller may stop early
-    (plateau strategy) by closing the generator."""
-    per_step = float(batch_size * sample_size)
-    steps_per_epoch = -(-int(n_voxels) // int(batch_size))
+    DataLoader-epoch boundaries (one epoch = ceil(n_voxels / batch_size) batches = exactly ``sample_size`` volume passes,
+    because the LAST batch of an epoch is the partial one the DataLoader yields with drop_last=False and the reference
+    counts the samples it actually saw, :108); inside an epoch the loop leaves only through
+    ``int(volume_passes) >= max_pass``.  The caller may stop early (plateau strategy) by closing the generator.
+
+    The fast loop's batch is fixed (the step is a captured graph), so the one partial step per epoch trains on a full
+    batch here (mhd_p: 32768 instead of 12272 samples once every 8097 steps); the ACCOUNTING follows the reference, which
+    is what fixes the number of optimiser steps and the learning-rate decay points (30365 steps for the 60-pass mhd_p
+    run, tests/golden/psnr_configs.json)."""
+    n_voxels, batch_size = int(n_voxels), int(batch_size)
+    steps_per_epoch = -(-n_voxels // batch_size)
+    last_items = n_voxels - (steps_per_epoch - 1) * batch_size
     seen, passes, step = 0.0, 0.0, 0
     while int(passes) + 1 < max_pass:
-        for _ in range(steps_per_epoch):
+        for i in range(steps_per_epoch):
             prior = int(seen / n_voxels)
-            seen += per_step
+            seen += float((last_items if i == steps_per_epoch - 1 else batch_size) * sample_size)
             passes = seen / n_voxels
             step += 1
             done = int(passes) >= max_pass

@@ -25,7 +25,9 @@ def reference_steps(n_voxels, batch_size, sample_size, max_pass):
     while int(volume_passes) + 1 < max_pass:
         for idx in range(loader_len):
             steps += 1
-            voxel_seen += batch_size * sample_size
+            # the last batch of an epoch is partial (drop_last=False) and :108 counts the samples actually seen;
+            # pinned by the 60-pass reference run of tests/golden/psnr_configs.json (30365 steps, not 30362)
+            voxel_seen += min(batch_size, n_voxels - idx * batch_size) * sample_size
             volume_passes = voxel_seen / n_voxels
             if int(volume_passes) >= max_pass:
                 break
@@ -45,7 +47,7 @@ def test_epoch_schedule_counts_match_the_reference_loop(n_voxels, batch_size, sa
             assert got[-1][2] == want_passes
             assert [g[0] for g in got] == list(range(1, want + 1))
             # prior / current pass numbers are what the decay strategies are fed with
-            assert all(p == int((i * batch_size * sample_size) / n_voxels) for i, (_, p, _, _) in enumerate(got))
+            assert all(got[i][1] == int(got[i - 1][2]) for i in range(1, len(got))) and got[0][1] == 0
 
 
 def test_advisor_counter_examples():
