@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LFGC_ABI_VERSION 3 /* 3: lfgc_grid_step / lfgc_train_step_partials replace lfgc_step_glue */
+#define LFGC_ABI_VERSION 4 /* 4: + lfgc_train_step_accumulate; 3: lfgc_grid_step / lfgc_train_step_partials replace lfgc_step_glue */
 #define LFGC_MAX_LEVELS 12 /* coefficient tensors per model (1 low-pass + up to 11 detail levels) */
 #define LFGC_MAX_TAPS 16   /* longest supported 1-D reconstruction filter */
 #define LFGC_MAX_LAYERS 8  /* hidden layers of the decoder MLP */
@@ -270,6 +270,17 @@ int lfgc_adam_reg(float* p, float* g, float* m, float* v, int64_t n, const float
                   float momentum, int zero_l1_grad, void* stream);
 int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* stream);
+
+/* lfgc_train_step that ADDS its MLP-gradient sums and its loss sum to grad_mlp_loss[0 .. lfgc_mlp_param_count] (the last
+ * float is the loss): the buffer is a running sum the caller cleared (or carries over).  The tensor-core kernel adds with
+ * atomics from its own epilogue, so there is no reduction launch and no use of the workspace slices; the summation order is
+ * then not fixed (like the grid gradient's, which always accumulates with atomics).  This is the per-sample launch of the
+ * data-parallel step: the buffer is the MLP section of the [grid gradient | MLP gradient | loss] message lfgc_peer_sum reads. */
+int lfgc_train_step_accumulate(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n, uint64_t seed,
+                               uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
+                               const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
+                               float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl,
+                               float* grad_mlp_loss, void* workspace, size_t workspace_bytes, void* stream);
 
 /* lfgc_train_step that LEAVES the MLP-gradient partial sums in the workspace instead of reducing them: *nslices_out (host
  * int, written at call time) rows of (lfgc_mlp_param_count + 1) floats, the last float of a row being that slice's

@@ -18,7 +18,7 @@ MAX_PEERS = 16
 
 MASK_IDENTITY, MASK_DIRECT, MASK_VARIATIONAL, MASK_STE_SIGMOID, MASK_BERNOULLI = range(5)
 F_CLAMP = 1
-ABI_VERSION = 3   # include/lfgc.h LFGC_ABI_VERSION this binding was written against
+ABI_VERSION = 4   # include/lfgc.h LFGC_ABI_VERSION this binding was written against
 
 _ERRORS = {-1: 'LFGC_E_INVALID', -2: 'LFGC_E_UNSUPPORTED', -3: 'LFGC_E_CUDA', -4: 'LFGC_E_WORKSPACE'}
 
@@ -94,6 +94,8 @@ _SIGNATURES = {
     'lfgc_train_step_partials': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f,
                                            C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, C.c_size_t,
                                            C.POINTER(C.c_int32), _f]),
+    'lfgc_train_step_accumulate': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64,
+                                             _f, C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, _f, C.c_size_t, _f]),
     'lfgc_grid_step': (C.c_int, [C.POINTER(WaveletDesc), C.c_int, C.POINTER(GridStepArgs), _f]),
     'lfgc_grid_step_smem_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
     'lfgc_grid_step_scratch_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),

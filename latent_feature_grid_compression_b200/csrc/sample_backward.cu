@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
 #pragma unroll
         for (int r = 0; r < 32; ++r) t += red[r][px];
         if (i < pcount) grad[i] = accumulate ? grad[i] + t : t;
-        else if (loss_out) loss_out[0] = t;
+        else if (loss_out) loss_out[0] = accumulate == 2 ? loss_out[0] + t : t;
     }
 }
 
@@ -503,15 +503,21 @@ static int train_step_impl(const lfgc_model_desc* m, const float* volume, const 
                            const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
                            float loss_scale, const float* log_sigma, float* dlog_sigma, const float* grid_cl,
                            const float* mlp, float* grad_grid_cl, float* grad_mlp, float* loss_sum, int accumulate_mlp,
-                           void* workspace, size_t workspace_bytes, void* stream, int32_t* nslices_out = nullptr) {
+                           void* workspace, size_t workspace_bytes, void* stream, int32_t* nslices_out = nullptr,
+                           float* atomic_out = nullptr) {
     BwdArgs A;
     A.defer_reduce = nslices_out ? 1 : 0;
     A.nslices = 0;
+    A.atomic_out = atomic_out;
     int rc = fill_sample_params(m, 0, A.P);
     if (rc) return rc;
     if (nslices_out) {
         *nslices_out = 0;
         grad_mlp = reinterpret_cast<float*>(workspace);   // unused in deferred mode; keeps the common checks uniform
+    }
+    if (atomic_out) {
+        grad_mlp = atomic_out;
+        accumulate_mlp = 1;
     }
     rc = common_checks(m, n, grid_cl, mlp, grad_grid_cl, grad_mlp, workspace);
     if (rc) return rc;
@@ -578,6 +584,18 @@ extern "C" int lfgc_train_step_partials(const lfgc_model_desc* m, const float* v
     return train_step_impl(m, volume, R, n, seed, sample_offset, step_dev, step_stride, explicit_idx, explicit_coords,
                            explicit_gt, loss_scale, nullptr, nullptr, grid_cl, mlp, grad_grid_cl, nullptr, nullptr, 0,
                            workspace, workspace_bytes, stream, nslices_out);
+}
+
+extern "C" int lfgc_train_step_accumulate(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
+                                          uint64_t seed, uint64_t sample_offset, const int32_t* step_dev,
+                                          uint64_t step_stride, const int64_t* explicit_idx, const float* explicit_coords,
+                                          const float* explicit_gt, float loss_scale, const float* grid_cl,
+                                          const float* mlp, float* grad_grid_cl, float* grad_mlp_loss, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+    if (!grad_mlp_loss) return fail(LFGC_E_INVALID, "train_step_accumulate: grad_mlp_loss is null");
+    return train_step_impl(m, volume, R, n, seed, sample_offset, step_dev, step_stride, explicit_idx, explicit_coords,
+                           explicit_gt, loss_scale, nullptr, nullptr, grid_cl, mlp, grad_grid_cl, nullptr, nullptr, 1,
+                           workspace, workspace_bytes, stream, nullptr, grad_mlp_loss);
 }
 
 extern "C" int lfgc_train_step_weighted(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,

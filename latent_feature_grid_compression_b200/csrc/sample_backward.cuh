@@ -29,6 +29,9 @@ struct BwdArgs {
     int pstride;                // floats per workspace slice: pcount + 1 (the last entry carries the loss partial)
     int defer_reduce;           // 1: leave the partial sums in the workspace (lfgc_train_step_partials); the reduction
     int nslices;                //    is folded into lfgc_grid_step, which is told how many slices there are (out)
+    float* atomic_out = nullptr;  // lfgc_train_step_accumulate: [pcount + 1] running sums (MLP gradient | loss) the kernel
+                                  // ADDS to; the tensor-core kernel does it with atomics from its flush (no workspace
+                                  // slices, no reduction launch), the other kernels through the reduction kernel
 };
 
 // Tries the wide kernel (v2: 8-12 warps per CTA, S'(z) in registers, packed FFMA2).  Returns LFGC_OK after
@@ -41,12 +44,17 @@ size_t backward_v2_workspace_floats(int pcount, int sms);
 int launch_backward_tc(BwdArgs& A, int fused, float* grad_mlp, int accumulate, void* workspace, size_t workspace_bytes,
                        cudaStream_t st);
 
-// grad[i] (+)= sum_b partial[b][i] for i < pcount; loss_out[0] = sum_b partial[b][pcount] (fixed order: deterministic)
+// grad[i] (+)= sum_b partial[b][i] for i < pcount; loss_out[0] (+)= sum_b partial[b][pcount] (fixed order: deterministic);
+// accumulate: 0 overwrite, 1 add to grad, 2 add to grad and to loss_out
 void launch_reduce_partials(const float* partial, int nslices, int pstride, int pcount, float* grad, int accumulate,
                             float* loss_out, cudaStream_t st);
 // what every launcher calls after its kernel: reduce now, or (A.defer_reduce) only record the slice count
 inline void finish_partials(BwdArgs& A, int nslices, float* grad, int accumulate, float* loss_out, cudaStream_t st) {
     A.nslices = nslices;
+    if (A.atomic_out) {   // accumulate == 2: the loss is added as well
+        launch_reduce_partials(A.partial, nslices, A.pstride, A.pcount, A.atomic_out, 2, A.atomic_out + A.pcount, st);
+        return;
+    }
     if (!A.defer_reduce) launch_reduce_partials(A.partial, nslices, A.pstride, A.pcount, grad, accumulate, loss_out, st);
 }
 

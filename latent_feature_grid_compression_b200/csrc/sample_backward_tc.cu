@@ -749,7 +749,15 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* dst = A.partial + (size_t)blockIdx.x * A.pstride;
+    // destination: this CTA's workspace slice (reduced later, fixed order), or -- lfgc_train_step_accumulate -- the running
+    // sums themselves, added to with atomics (148 CTAs x 3.4 k reductions at the very end of the kernel cost less than the
+    // reduction launch they replace in the data-parallel step)
+    float* const aout = A.atomic_out;
+    float* dst = aout ? aout : A.partial + (size_t)blockIdx.x * A.pstride;
+    auto put = [&](int idx, float v) {
+        if (aout) atomicAdd(dst + idx, v);
+        else dst[idx] = v;
+    };
     // Every accumulator row (TMEM lane) passes through shared memory once: S[layer][row 0..127][33 floats].  With a row
     // stride of 33 both the lane-per-row stores and the row-fastest reads are bank-conflict free, and the global stores
     // become one compact loop over the packed parameter order in which all warps take part (the former register-to-global
@@ -781,15 +789,15 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         for (int k = lane; k < Kin; k += 32) {
             const int row = l > 0 ? k : (k < nfix ? Cp + k : k - nfix);   // layer 0: permuted columns
             const float* src = Sl + row * kSRow + warp;                  // rows 0..63 hold hi * dz, rows 64..127 lo * dz
-            float* d = dst + woff + warp * Kin + k;
+            int o = woff + warp * Kin + k;
             for (int j = warp; j < H; j += NT / 32) {
-                *d = src[0] + src[64 * kSRow];
+                put(o, src[0] + src[64 * kSRow]);
                 src += NT / 32;
-                d += (NT / 32) * Kin;
+                o += (NT / 32) * Kin;
             }
         }
         if (warp == (l & 3) && lane < H)   // bias: the ones row
-            dst[boff + lane] = Sl[kOnesRow * kSRow + lane] + Sl[(kOnesRow + 64) * kSRow + lane];
+            put(boff + lane, Sl[kOnesRow * kSRow + lane] + Sl[(kOnesRow + 64) * kSRow + lane]);
     }
     BT_MARK(15)  // flush: dW to the partial slice
     {
@@ -810,11 +818,11 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             for (int g = 0; g < 7; ++g) t += red2[g * 36 + threadIdx.x];
             const int wfo = mlp_wf_off(L, in0, H);
             if (threadIdx.x < 32) {
-                if ((int)threadIdx.x < H) dst[wfo + threadIdx.x] = t;
+                if ((int)threadIdx.x < H) put(wfo + threadIdx.x, t);
             } else if (threadIdx.x == 32) {
-                dst[wfo + H] = t;
+                put(wfo + H, t);
             } else {
-                dst[A.pcount] = t;
+                put(A.pcount, t);
             }
         }
     }
@@ -841,6 +849,10 @@ static int launch_tps(BwdArgs& A, int K0p, float* grad_mlp, int accumulate, void
     A.partial = reinterpret_cast<float*>(workspace);
     (void)launch_pdl(kern, dim3((unsigned)grid), dim3(TILE * TPS), (size_t)(Lo.total), st, A, K0p);
     LFGC_LAUNCH_OK();
+    if (A.atomic_out) {   // the kernel added its sums itself
+        A.nslices = 0;
+        return LFGC_OK;
+    }
     finish_partials(A, (int)grid, grad_mlp, accumulate, FUSED ? A.loss_sum : nullptr, st);
     if (!A.defer_reduce) LFGC_LAUNCH_OK();
     return LFGC_OK;

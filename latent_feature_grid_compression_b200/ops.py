@@ -431,6 +431,32 @@ def train_step_partials(geom: Geometry, volume, n: int, seed: int, sample_offset
     return int(ns.value)
 
 
+def train_step_accumulate(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl,
+                          mlp_flat, grad_grid_cl, grad_mlp_loss, workspace, step_dev=None, step_stride: int = 0,
+                          coords=None, targets=None, explicit_idx=None):
+    """``train_step`` that ADDS its MLP-gradient sums and loss sum to ``grad_mlp_loss`` (mlp_param_count + 1 floats, a
+    running sum the caller cleared) -- atomics from the tensor-core kernel's epilogue, no reduction launch
+    (lfgc_train_step_accumulate)."""
+    lib = L.load()
+    if volume is not None:
+        _req(volume, 'volume')
+    if coords is not None:
+        _req(coords, 'coords')
+        _req(targets, 'targets')
+    if explicit_idx is not None:
+        _req(explicit_idx, 'explicit_idx', torch.int64)
+    if grad_mlp_loss.numel() < geom.mlp_param_count + 1:
+        raise L.LfgcError('train_step_accumulate: grad_mlp_loss holds %d floats, %d needed'
+                          % (grad_mlp_loss.numel(), geom.mlp_param_count + 1))
+    shape3 = L.int3(volume.shape) if volume is not None else None
+    L.check(lib.lfgc_train_step_accumulate(ct.byref(geom.model_desc), _p(volume), shape3, int(n), int(seed),
+                                           int(sample_offset), _p(step_dev), int(step_stride), _p(explicit_idx),
+                                           _p(coords), _p(targets), float(loss_scale), _p(_req(grid_cl, 'grid_cl')),
+                                           _p(_req(mlp_flat, 'mlp')), _p(_req(grad_grid_cl, 'grad_grid_cl')),
+                                           _p(_req(grad_mlp_loss, 'grad_mlp_loss')), _p(_req(workspace, 'workspace')),
+                                           workspace.numel() * 4, _stream()), 'lfgc_train_step_accumulate')
+
+
 def peer_sum(src_addrs, flag_addrs, rank: int, epoch, out, zero=None):
     """out = sum over the ranks' buffers (raw device addresses, peer memory) behind the in-kernel barrier
     (lfgc_peer_sum); ``epoch``: int32[2] device tensor; ``zero``: buffer cleared in the same pass."""

@@ -404,12 +404,16 @@ class FastTrainer:
             ops.grid_step(geom, [self.grad_grid], [self.workspace], ns, pcount + 1, pcount, loss_out=self.loss_sum,
                           **common)
             return
-        ops.train_step(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl, self.mlp_flat,
-                       self.grad_grid, self.red_mlp[:pcount], self.loss_sum, self.workspace, **kw)
         if self._p2p is None:
+            ops.train_step(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl, self.mlp_flat,
+                           self.grad_grid, self.red_mlp[:pcount], self.loss_sum, self.workspace, **kw)
             torch.distributed.all_reduce(self.red, group=self.group)
             ops.grid_step(geom, [self.grad_grid], [self.red_mlp], 1, pcount + 1, pcount, **common)
             return
+        # the per-sample kernel adds its MLP-gradient and loss sums straight into the message buffer (cleared one step
+        # earlier, like the grid-gradient section): no reduction launch between it and the peer sum
+        ops.train_step_accumulate(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl, self.mlp_flat,
+                                  self.grad_grid, self.red_mlp, self.workspace, **kw)
         # lfgc_peer_sum: this step's buffers of all ranks -> one local sum (barrier inside the kernel); the accumulator it
         # clears is the OTHER parity's (its last readers finished before they announced this epoch)
         P = self._p2p
@@ -547,7 +551,10 @@ class FastTrainer:
         self.lr_dev.fill_(float(lr))
 
     def last_loss(self) -> float:
-        """Mean squared error of the last step's local batch (device -> host read)."""
+        """Mean squared error of the last step's batch (device -> host read): the local batch, or -- peer-sum data
+        parallelism, where the loss travels in the summed message -- the global one."""
+        if self._p2p is not None:
+            return float(self._p2p['summed'][self.grid_cl.numel() + self.n_mlp_elems].item()) / (self.batch * self.world)
         return float(self.loss_sum.item()) / self.batch
 
     def complete_loss(self) -> float:
@@ -558,8 +565,11 @@ class FastTrainer:
         if self.var_cfg is not None:
             raise L.LfgcError('complete_loss() is defined for the MSE (+ SmallifyLoss) objective only')
         with torch.no_grad():
-            t = self.loss_sum.double() / float(self.batch * self.world)
-            if self.world > 1:
+            if self._p2p is not None:   # already summed over the ranks (identical on every rank)
+                t = self._p2p['summed'][self.grid_cl.numel() + self.n_mlp_elems].double() / float(self.batch * self.world)
+            else:
+                t = self.loss_sum.double() / float(self.batch * self.world)
+            if self.world > 1 and self._p2p is None:
                 t = t.clone()
                 torch.distributed.all_reduce(t, group=self.group)
             if self.weight_l1 > 0.0 and self.n_mask_elems:

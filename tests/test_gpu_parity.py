@@ -283,6 +283,36 @@ def test_fused_train_step_matches_separate_path_and_oracle():
         off += k
 
 
+@pytest.mark.parametrize('n', [1000, 32768])
+@pytest.mark.parametrize('tc', ['1', '0'])
+def test_train_step_accumulate_adds_the_same_sums(n, tc, monkeypatch):
+    """lfgc_train_step_accumulate (atomics from the tensor-core kernel's epilogue / the reduction kernel in add mode for the
+    FFMA2 kernels) adds exactly what lfgc_train_step writes: MLP gradient, loss (last float), grid gradient."""
+    from latent_feature_grid_compression_b200 import ops
+    monkeypatch.setenv('LFGC_BACKWARD_TC', tc)
+    model, g, cfg = build_model('basic_db2_c16_g15')
+    geom = model.geometry()
+    gen = torch.Generator().manual_seed(11)
+    vol = (torch.rand(31, 29, 37, generator=gen) * 2 - 1).cuda()
+    idx = torch.randint(0, vol.numel(), (n,), generator=gen).cuda()
+    coeffs = [f.detach().contiguous() for f in model.feature_grid]
+    grid_cl = ops.decode_fwd(geom, coeffs, [None] * len(coeffs))
+    mlp = model.mlp_flat()
+    ws = torch.empty(geom.backward_workspace_bytes // 4, device='cuda')
+    gg = torch.zeros_like(grid_cl)
+    gm = torch.empty(geom.mlp_param_count, device='cuda')
+    loss = torch.zeros(1, device='cuda')
+    ops.train_step(geom, vol, n, 0, 0, 1.0 / n, grid_cl, mlp, gg, gm, loss, ws, explicit_idx=idx)
+    gg2 = torch.zeros_like(grid_cl)
+    acc = torch.zeros(geom.mlp_param_count + 1, device='cuda')
+    for rep in (1, 2):     # a running sum: the second call doubles it
+        ops.train_step_accumulate(geom, vol, n, 0, 0, 1.0 / n, grid_cl, mlp, gg2, acc, ws, explicit_idx=idx)
+        torch.cuda.synchronize()
+        assert float((acc[:-1] - rep * gm).abs().max()) <= 3e-6 * rep * float(gm.abs().max())
+        assert abs(float(acc[-1]) - rep * float(loss)) <= 1e-5 * rep * float(loss)
+        assert float((gg2 - rep * gg).abs().max()) <= 3e-6 * rep * float(gg.abs().max())
+
+
 def test_flat_adam_matches_torch_adam():
     from latent_feature_grid_compression_b200 import ops
     gen = torch.Generator().manual_seed(5)
