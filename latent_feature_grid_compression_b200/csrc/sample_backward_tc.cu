@@ -18,8 +18,8 @@
 //                  slot carries dz_l (hi | lo) (h_3 is read out for its weight-gradient operand first)
 //       [224,480)  dW_l^T accumulators, one 64-column block per layer ([A dz_hi | A dz_lo]), kept across the whole
 //                  persistent loop
-//   The fp32 copy of the layer-0 input (re-split for dW_0 in the backward) lives in shared memory, written and read by
-//   the same threads.
+//   The fp32 copy of the layer-0 input (re-split for dW_0 in the backward) lives in shared memory (written in the input
+//   stage, read after the forward pass: block barriers in between).
 //   Forward, layer l:      z_l = h_l W_l^T          A = h_l (TMEM),            B = W_l   K-major panels (smem)
 //   Backward, layer l:     dh_l = dz_l W_l          A = dz_l (TMEM),           B = W_l^T K-major panels (smem)
 //                          dW_l^T += [h_l | 1]^T dz_l   A = h_l MN-major (smem), B = dz_l MN-major (smem), K = samples
@@ -341,15 +341,29 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     };
     float cx, cy, cz, aux;
     Corners Kc;
-    float4 gv[8], gu[8];   // the first two feature chunks of this thread (c = q and q + TPS), gathered at the 8 corners
-    auto issue_gather = [&]() {
+    float4 gv[8], gu[8];   // two adjacent feature chunks (8 channels) of this thread, gathered at the 8 corners
+    // Feature chunks are taken in adjacent pairs (2p, 2p + 1), p = q, q + TPS, ...: 32 contiguous bytes per corner, fetched
+    // with ONE 256-bit load (LDG.E.256, sm_100+) where the rows allow it -- half the load instructions and L1 wavefronts of
+    // the divergent gather, which is what bounds the input stage.
+    const bool wide_rows = (Cp & 7) == 0 && (reinterpret_cast<uintptr_t>(A.grid) & 31) == 0;
+    auto gather_pair = [&](int p) {
+        if (wide_rows) {
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) gv[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * q);
-        if (4 * (q + TPS) < Cp) {
+            for (int cc = 0; cc < 8; ++cc)
+                asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=f"(gv[cc].x), "=f"(gv[cc].y), "=f"(gv[cc].z), "=f"(gv[cc].w), "=f"(gu[cc].x), "=f"(gu[cc].y),
+                               "=f"(gu[cc].z), "=f"(gu[cc].w)
+                             : "l"(A.grid + Kc.off[cc] + 8 * p));
+        } else {
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) gu[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * (q + TPS));
+            for (int cc = 0; cc < 8; ++cc) gv[cc] = ldg_f4(A.grid + Kc.off[cc] + 8 * p);
+            if (4 * (2 * p + 1) < Cp) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) gu[cc] = ldg_f4(A.grid + Kc.off[cc] + 8 * p + 4);
+            }
         }
     };
+    auto issue_gather = [&]() { gather_pair(q); };
     // The first tile's loads go out before the one-time setup below: the Philox draw, the volume read and the 16 gathers are
     // three dependent memory round trips that now overlap the ~7 k cycles of parameter staging.
     if ((int64_t)blockIdx.x * TILE < A.n) {
@@ -501,18 +515,11 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             }
             emit(c, v4);
         }
-        // feature chunks two at a time: 16 independent 128-bit gathers in flight per thread; the first pair was issued above
-        for (int c = q; 4 * c < Cp; c += 2 * TPS) {
-            const int c2 = c + TPS;
+        // feature chunks in adjacent pairs; the first pair was issued above
+        for (int p = q; 8 * p < Cp; p += TPS) {
+            const int c = 2 * p, c2 = c + 1;
             const bool two = 4 * c2 < Cp;
-            if (c != q) {
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) gv[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c);
-                if (two) {
-#pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) gu[cc] = ldg_f4(A.grid + Kc.off[cc] + 4 * c2);
-                }
-            }
+            if (p != q) gather_pair(p);
             float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(TILE * G, 1) sample_forward_tc_kernel(const __
             }
             Corners K;
             make_corners(P, cx, cy, cz, K);
+            const bool wide_rows = (P.Cp & 7) == 0 && (reinterpret_cast<uintptr_t>(A.grid) & 31) == 0;
             // two channel chunks per batch: 16 independent 128-bit loads in flight per thread (the gather's L2 round
             // trips are the largest stall of this kernel; ncu source view)
             auto emit = [&](const float4& a, int chunk) {
@@ -252,11 +253,20 @@ __global__ void __launch_bounds__(TILE * G, 1) sample_forward_tc_kernel(const __
             for (int c4 = 0; c4 < P.Cp; c4 += 8) {
                 const bool two = c4 + 4 < P.Cp;
                 float4 v[8], u[8];
+                if (wide_rows) {   // both chunks with one 256-bit load per corner (LDG.E.256, sm_100+)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = ldg_f4(A.grid + K.off[c] + c4);
-                if (two) {
+                    for (int c = 0; c < 8; ++c)
+                        asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w), "=f"(u[c].x), "=f"(u[c].y),
+                                       "=f"(u[c].z), "=f"(u[c].w)
+                                     : "l"(A.grid + K.off[c] + c4));
+                } else {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) u[c] = ldg_f4(A.grid + K.off[c] + c4 + 4);
+                    for (int c = 0; c < 8; ++c) v[c] = ldg_f4(A.grid + K.off[c] + c4);
+                    if (two) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) u[c] = ldg_f4(A.grid + K.off[c] + c4 + 4);
+                    }
                 }
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
