@@ -291,6 +291,37 @@ __device__ __forceinline__ void snake_and_grad_fast2(float z0, float z1, float& 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(g0), "=f"(g1) : "l"(g));
 }
 
+// sin and cos of TWO arguments at once (the Fourier features of the tensor-core kernels): the reduction modulo pi and the
+// two polynomials of snake_and_grad_fast2 applied to x itself; the sign (-1)^n goes onto both results with one XOR each.
+// Max abs error 1.1e-7 (sin) / 6.2e-8 (cos) for |x| < 1e4; ~27 issue slots per pair against 2 x 28 for sincos_cw.
+__device__ __forceinline__ void sincos_fast2(float x0, float x1, float& s0, float& c0, float& s1, float& c1) {
+    const unsigned long long w = pack2(x0, x1);
+    const unsigned long long one = pack2(1.0f, 1.0f), magic = pack2(12582912.0f, 12582912.0f), zero = pack2(0.0f, 0.0f);
+    const unsigned long long biased = fma2(w, pack2(0.318309886f, 0.318309886f), magic);
+    const unsigned long long n = fma2(biased, one, pack2(-12582912.0f, -12582912.0f));
+    unsigned long long r = fma2(n, pack2(-3.14159274f, -3.14159274f), w);
+    r = fma2(n, pack2(8.74227766e-08f, 8.74227766e-08f), r);
+    const unsigned long long u = fma2(r, r, zero);
+    unsigned long long p = fma2(u, pack2(LFGC_SNAKE_C5, LFGC_SNAKE_C5), pack2(LFGC_SNAKE_C4, LFGC_SNAKE_C4));
+    p = fma2(p, u, pack2(LFGC_SNAKE_C3, LFGC_SNAKE_C3));
+    p = fma2(p, u, pack2(LFGC_SNAKE_C2, LFGC_SNAKE_C2));
+    p = fma2(p, u, pack2(-0.5f, -0.5f));
+    p = fma2(p, u, one);                                                                 // cos r
+    unsigned long long t = fma2(u, pack2(LFGC_SNAKE_S4, LFGC_SNAKE_S4), pack2(LFGC_SNAKE_S3, LFGC_SNAKE_S3));
+    t = fma2(t, u, pack2(LFGC_SNAKE_S2, LFGC_SNAKE_S2));
+    t = fma2(t, u, pack2(LFGC_SNAKE_S1, LFGC_SNAKE_S1));
+    t = fma2(t, fma2(r, u, zero), r);                                                    // sin r
+    float b0, b1, pc0, pc1, ps0, ps1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(biased));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(pc0), "=f"(pc1) : "l"(p));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(ps0), "=f"(ps1) : "l"(t));
+    const int g0 = __float_as_int(b0) << 31, g1 = __float_as_int(b1) << 31;              // parity of n -> sign bit
+    s0 = __int_as_float(__float_as_int(ps0) ^ g0);
+    c0 = __int_as_float(__float_as_int(pc0) ^ g0);
+    s1 = __int_as_float(__float_as_int(ps1) ^ g1);
+    c1 = __int_as_float(__float_as_int(pc1) ^ g1);
+}
+
 // Hidden-layer activation of the fused kernels: ACT 0 = SnakeAlt (the fV-SRN decoder), ACT 1 = ReLU (Variance_Model,
 // model/Variational_Dropout_Layer.py:159-175; gradient 1 where z > 0, as torch's threshold_backward).
 template <int ACT>

@@ -494,25 +494,32 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             tmem_st<4>(trow + colA_lo(0) + 4 * c, lo);
             X0s[c * TILE + s] = make_float4(v4[0], v4[1], v4[2], v4[3]);
         };
-        // positional columns first: their sincos work runs while the gathers are in flight
+        // positional columns first: their sincos work runs while the gathers are in flight.  A chunk's four columns take
+        // two packed evaluations (sincos_fast2: two arguments each, sin or cos picked per column)
         for (int c = (Cp >> 2) + q; c < K0p / 4; c += TPS) {
-            float v4[4];
+            float arg[4], v4[4];
+            int kind[4];   // 0: the argument itself (xyz), 1: sin, 2: cos, 3: zero pad
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = 4 * c + i - Cp;   // 0..2 xyz, then per frequency [sin x y z | cos x y z]
-                float val = 0.0f;
+                arg[i] = 0.0f;
+                kind[i] = 3;
                 if (r < 3) {
-                    val = r == 0 ? cx : (r == 1 ? cy : cz);
+                    arg[i] = r == 0 ? cx : (r == 1 ? cy : cz);
+                    kind[i] = 0;
                 } else if (r < nfix) {
                     const int f = (r - 3) / 6, m = (r - 3) - 6 * f;
                     const int ax = m >= 3 ? m - 3 : m;
                     const float coord = ax == 0 ? cx : (ax == 1 ? cy : cz);
-                    float sn, cs;
-                    sincos_cw(__fmul_rn(coord, P.omega[f]), sn, cs);  // argument rounded to fp32 first
-                    val = m >= 3 ? cs : sn;
+                    arg[i] = __fmul_rn(coord, P.omega[f]);   // argument rounded to fp32 first
+                    kind[i] = m >= 3 ? 2 : 1;
                 }
-                v4[i] = val;
             }
+            float sn[4], cs[4];
+            sincos_fast2(arg[0], arg[1], sn[0], cs[0], sn[1], cs[1]);
+            sincos_fast2(arg[2], arg[3], sn[2], cs[2], sn[3], cs[3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v4[i] = kind[i] == 0 ? arg[i] : (kind[i] == 1 ? sn[i] : (kind[i] == 2 ? cs[i] : 0.0f));
             emit(c, v4);
         }
         // feature chunks in adjacent pairs; the first pair was issued above

@@ -299,14 +299,21 @@ __global__ void __launch_bounds__(TILE * G, 1) sample_forward_tc_kernel(const __
             put(k++, cx);
             put(k++, cy);
             put(k++, cz);
-            for (int f = 0; f < P.F; ++f) {
+            // Fourier features two arguments at a time (sincos_fast2); frequencies in pairs so that no lane is wasted
+            for (int f = 0; f < P.F; f += 2) {
                 const float om = P.omega[f];
-                float sx, cxx, sy, cyy, sz, czz;
-                sincos_cw(__fmul_rn(cx, om), sx, cxx);
-                sincos_cw(__fmul_rn(cy, om), sy, cyy);
-                sincos_cw(__fmul_rn(cz, om), sz, czz);
+                const bool pair = f + 1 < P.F;
+                const float om2 = pair ? P.omega[f + 1] : om;
+                float sx, cxx, sy, cyy, sz, czz, sx2, cx2, sy2, cy2, sz2, cz2;
+                sincos_fast2(__fmul_rn(cx, om), __fmul_rn(cy, om), sx, cxx, sy, cyy);   // arguments rounded to fp32 first
+                sincos_fast2(__fmul_rn(cz, om), __fmul_rn(cx, om2), sz, czz, sx2, cx2);
                 put(k++, sx); put(k++, sy); put(k++, sz);
                 put(k++, cxx); put(k++, cyy); put(k++, czz);
+                if (pair) {
+                    sincos_fast2(__fmul_rn(cy, om2), __fmul_rn(cz, om2), sy2, cy2, sz2, cz2);
+                    put(k++, sx2); put(k++, sy2); put(k++, sz2);
+                    put(k++, cx2); put(k++, cy2); put(k++, cz2);
+                }
             }
             for (; k < K0p; ++k) put(k, 0.0f);
         }
