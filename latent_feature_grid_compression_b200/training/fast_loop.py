@@ -153,6 +153,7 @@ class FastTrainer:
             dist.barrier(group=grp)          # every rank's flags are zero before anybody's first launch
         else:
             self._red2 = [torch.zeros(self._n_red, device=self.device, dtype=torch.float32)]
+        self._side = None
         self._par = 0                        # parity of the next step (only the p2p path has two buffers)
         self._set_red(0)
         self.scratch = torch.empty(max(self.geom.decode_scratch_bytes // 4, 4), device=self.device)
@@ -244,6 +245,21 @@ class FastTrainer:
         torch.distributed.all_reduce(self.flat_g, group=self.group)
         return self.flat_g
 
+    def _fork(self):
+        """Side stream for work that is independent of the main chain (the Variance_Model passes of the variational step);
+        inside a graph capture the event edges become graph dependencies, so the branches run concurrently on replay."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._side.wait_event(ev)
+        return torch.cuda.stream(self._side)
+
+    def _join(self):
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        torch.cuda.current_stream().wait_event(ev)
+
     def _step_body(self, host_fed=False):
         model, geom = self.model, self.geom
         in_coords, in_targets = self._in_coords, self._in_targets
@@ -272,9 +288,23 @@ class FastTrainer:
         else:
             specs = model.mask_specs()
             mults, auxs = _multipliers(specs)
+        n_global = self.batch * self.world
+        vm = self.var_model if self.var_cfg is not None else None
+        if self.var_cfg is not None:
+            # variational likelihood: the samples are materialised so that the Variance_Model sees the positions; drawing
+            # them and the Variance_Model forward do not depend on the synthesis: side branch
+            if not host_fed:
+                in_coords, in_targets = self._s_coords, self._s_gt
+            with self._fork():
+                if not host_fed:
+                    ops.sample(self.volume.shape, self.batch, seed=self.seed,
+                               sample_offset=parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
+                               volume=self.volume, step_dev=self.step_dev, step_stride=n_global,
+                               out=(None, in_coords, in_targets))
+                if vm is not None:
+                    ops.plain_mlp_forward(vm.width, vm.n_layers, in_coords, self.var_flat, out=self._log_sigma)
         # the synthesis also clears the grid-gradient accumulator; the fused kernel overwrites loss_sum
         ops.decode_fwd(geom, coeffs, mults, scratch=self.scratch, out=self.grid_cl, also_zero=self.grad_grid)
-        n_global = self.batch * self.world
         if self.var_cfg is None:
             ops.train_step(geom, self.volume, self.batch, self.seed,
                            parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
@@ -283,23 +313,15 @@ class FastTrainer:
                            step_dev=self.step_dev, step_stride=n_global,
                            coords=in_coords if host_fed else None, targets=in_targets if host_fed else None)
         else:
-            # variational likelihood: the samples are materialised so that the Variance_Model sees the positions
-            if not host_fed:
-                in_coords, in_targets = self._s_coords, self._s_gt
-                ops.sample(self.volume.shape, self.batch, seed=self.seed,
-                           sample_offset=parallel.sample_stream_offset(0, self.rank, self.batch, self.world),
-                           volume=self.volume, step_dev=self.step_dev, step_stride=n_global,
-                           out=(None, in_coords, in_targets))
-            vm = self.var_model
-            if vm is not None:
-                ops.plain_mlp_forward(vm.width, vm.n_layers, in_coords, self.var_flat, out=self._log_sigma)
+            self._join()
             ops.train_step(geom, None, self.batch, self.seed, 0, 0.5 * self.var_scale, self.grid_cl, self.mlp_flat,
                            self.grad_grid, self.flat_g[self.mlp_off:self.mlp_off + self.n_mlp_elems], self.loss_sum,
                            self.workspace, coords=in_coords, targets=in_targets, log_sigma=self._log_sigma,
                            dlog_sigma=self._dlog_sigma if vm is not None else None)
-            if vm is not None:
-                ops.plain_mlp_backward(vm.width, vm.n_layers, in_coords, self._dlog_sigma, self.var_flat,
-                                       grad_mlp=self.flat_g[self.var_off:], workspace=self._var_ws)
+            if vm is not None:   # the Variance_Model backward runs beside the synthesis adjoint
+                with self._fork():
+                    ops.plain_mlp_backward(vm.width, vm.n_layers, in_coords, self._dlog_sigma, self.var_flat,
+                                           grad_mlp=self.flat_g[self.var_off:], workspace=self._var_ws)
         if var_fast:
             gviews, off = [], 0
             for d, n_i in zip(self.model.drop, self._var_sizes):
@@ -321,6 +343,8 @@ class FastTrainer:
             self.grad_of(spec.grad_params[0]).copy_(g0)
             if len(spec.grad_params) == 2:
                 self.grad_of(spec.grad_params[1]).copy_(g1)
+        if vm is not None:
+            self._join()
         g_red = self._allreduce_grads() if self.world > 1 else self.flat_g
         if self.var_cfg is not None:
             # sample-independent terms of VariationalDropoutLoss, added once after the reduction: KL of the live masks
