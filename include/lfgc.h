@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LFGC_ABI_VERSION 4 /* 4: + lfgc_train_step_accumulate; 3: lfgc_grid_step / lfgc_train_step_partials replace lfgc_step_glue */
+#define LFGC_ABI_VERSION 5 /* 5: lfgc_peer_announce; 4: + lfgc_train_step_accumulate; 3: lfgc_grid_step / lfgc_train_step_partials replace lfgc_step_glue */
 #define LFGC_MAX_LEVELS 12 /* coefficient tensors per model (1 low-pass + up to 11 detail levels) */
 #define LFGC_MAX_TAPS 16   /* longest supported 1-D reconstruction filter */
 #define LFGC_MAX_LAYERS 8  /* hidden layers of the decoder MLP */
@@ -276,11 +276,24 @@ int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* st
  * atomics from its own epilogue, so there is no reduction launch and no use of the workspace slices; the summation order is
  * then not fixed (like the grid gradient's, which always accumulates with atomics).  This is the per-sample launch of the
  * data-parallel step: the buffer is the MLP section of the [grid gradient | MLP gradient | loss] message lfgc_peer_sum reads. */
+/* Optional early announcement for lfgc_peer_sum: once the LAST CTA of the per-sample kernel has added its sums (all of this
+ * rank's contribution to the step is then complete), it stores epoch[0] + 1 into slot [rank] of every rank's flag array --
+ * what lfgc_peer_sum would otherwise do at its start -- so that the flags travel over NVLink while the next launch is still
+ * being set up.  Pass the same flags / rank / epoch as to lfgc_peer_sum (and announced = 1 there); ticket: device int32,
+ * 0 at the start, reset by the kernel. */
+typedef struct lfgc_peer_announce {
+    int32_t n_peers, rank;
+    int32_t* flags[LFGC_MAX_PEERS];
+    const int32_t* epoch;
+    int32_t* ticket;
+} lfgc_peer_announce;
+
 int lfgc_train_step_accumulate(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n, uint64_t seed,
                                uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
                                const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
                                float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl,
-                               float* grad_mlp_loss, void* workspace, size_t workspace_bytes, void* stream);
+                               float* grad_mlp_loss, const lfgc_peer_announce* announce /* nullable */, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /* lfgc_train_step that LEAVES the MLP-gradient partial sums in the workspace instead of reducing them: *nslices_out (host
  * int, written at call time) rows of (lfgc_mlp_param_count + 1) floats, the last float of a row being that slice's
@@ -341,7 +354,8 @@ int lfgc_grid_step_supported(const lfgc_wavelet_desc* w);
  * (nullable, n floats: the other parity's local buffer) is cleared in the same pass.  n must be a multiple of 4 and the
  * buffers 16-byte aligned.  Replaces the NCCL all-reduce of the path when the ranks share a node. */
 int lfgc_peer_sum(const float* const* srcs, int32_t* const* flags, int n_srcs, int rank, int32_t* epoch, float* out,
-                  float* zero, int64_t n, void* stream);
+                  float* zero, int64_t n, int announced /* 1: lfgc_train_step_accumulate already stored this epoch's flags */,
+                  void* stream);
 
 /* Gradient of the KL regulariser of VariationalDropoutLoss (model/Variational_Dropout_Layer.py:54-69,115-122) added
  * in place to the mask-parameter gradients, and the per-step ramp of its weight (:57-58).  mask_params / mask_grads

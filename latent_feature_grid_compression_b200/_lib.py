@@ -18,7 +18,7 @@ MAX_PEERS = 16
 
 MASK_IDENTITY, MASK_DIRECT, MASK_VARIATIONAL, MASK_STE_SIGMOID, MASK_BERNOULLI = range(5)
 F_CLAMP = 1
-ABI_VERSION = 4   # include/lfgc.h LFGC_ABI_VERSION this binding was written against
+ABI_VERSION = 5   # include/lfgc.h LFGC_ABI_VERSION this binding was written against
 
 _ERRORS = {-1: 'LFGC_E_INVALID', -2: 'LFGC_E_UNSUPPORTED', -3: 'LFGC_E_CUDA', -4: 'LFGC_E_WORKSPACE'}
 
@@ -50,6 +50,11 @@ class GridStepArgs(C.Structure):
                 ('mlp_off', _i64), ('loss_out', _f), ('lr', _f), ('step_count', _f), ('beta1', C.c_double),
                 ('beta2', C.c_double), ('eps', C.c_double), ('grad_scale', C.c_double), ('weight_l2', C.c_double),
                 ('scratch', _f), ('scratch_bytes', C.c_size_t)]
+
+
+class PeerAnnounce(C.Structure):
+    """lfgc_peer_announce (include/lfgc.h)."""
+    _fields_ = [('n_peers', C.c_int32), ('rank', C.c_int32), ('flags', _f * MAX_PEERS), ('epoch', _f), ('ticket', _f)]
 
 
 _SIGNATURES = {
@@ -88,14 +93,15 @@ _SIGNATURES = {
     'lfgc_adam': (C.c_int, [_f, _f, _f, _f, _i64, _f, _f, C.c_double, C.c_double, C.c_double, C.c_double, _f]),
     'lfgc_adam_reg': (C.c_int, [_f, _f, _f, _f, _i64, _f, _f, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _i64,
                                 C.c_double, _i64, _i64, C.c_double, _f, _f, C.c_float, C.c_int, _f]),
-    'lfgc_peer_sum': (C.c_int, [C.POINTER(_f), C.POINTER(_f), C.c_int, C.c_int, _f, _f, _f, _i64, _f]),
+    'lfgc_peer_sum': (C.c_int, [C.POINTER(_f), C.POINTER(_f), C.c_int, C.c_int, _f, _f, _f, _i64, C.c_int, _f]),
     'lfgc_add_l2_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_add_l1_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_train_step_partials': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f,
                                            C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, C.c_size_t,
                                            C.POINTER(C.c_int32), _f]),
     'lfgc_train_step_accumulate': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64,
-                                             _f, C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, _f, C.c_size_t, _f]),
+                                             _f, C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, C.POINTER(PeerAnnounce),
+                                             _f, C.c_size_t, _f]),
     'lfgc_grid_step': (C.c_int, [C.POINTER(WaveletDesc), C.c_int, C.POINTER(GridStepArgs), _f]),
     'lfgc_grid_step_smem_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
     'lfgc_grid_step_scratch_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),

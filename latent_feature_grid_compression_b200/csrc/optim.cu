@@ -146,15 +146,28 @@ struct PeerSumArgs {
     float* out;
     float* zero;
     long long n;
+    int announced;   // this epoch's flags were already stored by the per-sample kernel (lfgc_peer_announce)
 };
 
+#ifdef LFGC_PHASE_TIMING
+__device__ unsigned long long g_peer_ns[8];   // [0] barrier wait, [1] remote reads + sum, [2] launches, [3] entry skew vs the train kernel
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
 __global__ void __launch_bounds__(512) peer_sum_kernel(const __grid_constant__ PeerSumArgs A) {
     LFGC_PDL_PROLOGUE();
     const int tid = threadIdx.x;
+#ifdef LFGC_PHASE_TIMING
+    const unsigned long long t_in = gtimer();
+#endif
     const int e = *reinterpret_cast<volatile int*>(A.epoch) + 1;
     if (tid < A.n_srcs) {
-        if (blockIdx.x == 0) {
-            __threadfence_system();
+        if (blockIdx.x == 0 && !A.announced) {
+            // everything this rank contributes was written by EARLIER kernels of this stream (complete and visible at
+            // device scope, i.e. in this GPU's L2, which is where peers read it): the release store alone orders it
             asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(A.flags[tid] + A.rank), "r"(e) : "memory");
         }
         const int* mine = A.flags[A.rank] + tid;
@@ -167,6 +180,9 @@ __global__ void __launch_bounds__(512) peer_sum_kernel(const __grid_constant__ P
         }
     }
     __syncthreads();
+#ifdef LFGC_PHASE_TIMING
+    const unsigned long long t_bar = gtimer();
+#endif
     const long long n4 = A.n >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 acc = __ldcv(reinterpret_cast<const float4*>(A.src[0]) + i);   // peer data changes every step: never from L1
@@ -179,6 +195,14 @@ __global__ void __launch_bounds__(512) peer_sum_kernel(const __grid_constant__ P
     }
     // publish the new epoch once every CTA has read the old one (ticket in epoch[1])
     __syncthreads();
+#ifdef LFGC_PHASE_TIMING
+    if (tid == 0 && blockIdx.x == 0) {
+        const unsigned long long t_end = gtimer();
+        atomicAdd(&g_peer_ns[0], t_bar - t_in);
+        atomicAdd(&g_peer_ns[1], t_end - t_bar);
+        atomicAdd(&g_peer_ns[2], 1ull);
+    }
+#endif
     if (tid == 0) {
         __threadfence();
         const int ticket = atomicAdd(A.epoch + 1, 1);
@@ -385,8 +409,20 @@ extern "C" int lfgc_adam_reg(float* p, float* g, float* m, float* v, int64_t n, 
     return launch_adam(p, g, m, v, n, lr, step_count, beta1, beta2, eps, grad_scale, reg, stream);
 }
 
+#ifdef LFGC_PHASE_TIMING
+extern "C" int lfgc_peer_timing(unsigned long long* out8, int reset) {
+    cudaDeviceSynchronize();
+    if (out8) cudaMemcpyFromSymbol(out8, g_peer_ns, sizeof(unsigned long long) * 8);
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_peer_ns, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
+
 extern "C" int lfgc_peer_sum(const float* const* srcs, int32_t* const* flags, int n_srcs, int rank, int32_t* epoch, float* out,
-                             float* zero, int64_t n, void* stream) {
+                             float* zero, int64_t n, int announced, void* stream) {
     if (!srcs || !flags || !epoch || !out || n < 0 || (n & 3)) return fail(LFGC_E_INVALID, "peer_sum: bad arguments (n must be a multiple of 4)");
     if (n_srcs < 1 || n_srcs > LFGC_MAX_PEERS || rank < 0 || rank >= n_srcs) return fail(LFGC_E_UNSUPPORTED, "peer_sum: %d sources, rank %d", n_srcs, rank);
     PeerSumArgs A = {};
@@ -401,6 +437,7 @@ extern "C" int lfgc_peer_sum(const float* const* srcs, int32_t* const* flags, in
     A.out = out;
     A.zero = zero;
     A.n = n;
+    A.announced = announced ? 1 : 0;
     int blocks = (int)((n / 4 + 511) / 512);
     if (blocks < 1) blocks = 1;
     if (blocks > 2 * sm_count()) blocks = 2 * sm_count();   // all CTAs must be co-resident while they wait on the flags

@@ -32,7 +32,21 @@ struct BwdArgs {
     float* atomic_out = nullptr;  // lfgc_train_step_accumulate: [pcount + 1] running sums (MLP gradient | loss) the kernel
                                   // ADDS to; the tensor-core kernel does it with atomics from its flush (no workspace
                                   // slices, no reduction launch), the other kernels through the reduction kernel
+    // early announcement for lfgc_peer_sum (lfgc_peer_announce): the last CTA to finish stores *ann_epoch + 1 into slot
+    // [ann_rank] of every rank's flag array
+    int ann_n = 0, ann_rank = 0;
+    int* ann_flags[LFGC_MAX_PEERS] = {};
+    const int* ann_epoch = nullptr;
+    int* ann_ticket = nullptr;
 };
+
+// stores the announcement of BwdArgs (one thread); used by the tensor-core kernel's last CTA and by announce_kernel
+__device__ __forceinline__ void announce_epoch(const BwdArgs& A) {
+    const int e = *reinterpret_cast<const volatile int*>(A.ann_epoch) + 1;
+    for (int r = 0; r < A.ann_n; ++r)
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(A.ann_flags[r] + A.ann_rank), "r"(e) : "memory");
+}
+void launch_announce(const BwdArgs& A, cudaStream_t st);
 
 // Tries the wide kernel (v2: 8-12 warps per CTA, S'(z) in registers, packed FFMA2).  Returns LFGC_OK after
 // launching, or 1 when the configuration is not covered (the caller then uses the generic kernel), or an error.
@@ -53,6 +67,7 @@ inline void finish_partials(BwdArgs& A, int nslices, float* grad, int accumulate
     A.nslices = nslices;
     if (A.atomic_out) {   // accumulate == 2: the loss is added as well
         launch_reduce_partials(A.partial, nslices, A.pstride, A.pcount, A.atomic_out, 2, A.atomic_out + A.pcount, st);
+        if (A.ann_n > 0) launch_announce(A, st);
         return;
     }
     if (!A.defer_reduce) launch_reduce_partials(A.partial, nslices, A.pstride, A.pcount, grad, accumulate, loss_out, st);

@@ -840,6 +840,20 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             }
         }
     }
+    if (aout && A.ann_n > 0) {
+        // early announcement (lfgc_peer_announce): every thread's reductions are performed device-wide before the CTA takes
+        // its ticket; the CTA that draws the last one knows all of this rank's sums are complete and tells the peers
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int ticket = atomicAdd(A.ann_ticket, 1);
+            if (ticket == (int)gridDim.x - 1) {
+                *A.ann_ticket = 0;
+                __threadfence();
+                announce_epoch(A);
+            }
+        }
+    }
     BT_MARK(10)  // flush
     BT_FLUSH()
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

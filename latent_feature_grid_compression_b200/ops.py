@@ -433,10 +433,11 @@ def train_step_partials(geom: Geometry, volume, n: int, seed: int, sample_offset
 
 def train_step_accumulate(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl,
                           mlp_flat, grad_grid_cl, grad_mlp_loss, workspace, step_dev=None, step_stride: int = 0,
-                          coords=None, targets=None, explicit_idx=None):
+                          coords=None, targets=None, explicit_idx=None, announce=None):
     """``train_step`` that ADDS its MLP-gradient sums and loss sum to ``grad_mlp_loss`` (mlp_param_count + 1 floats, a
     running sum the caller cleared) -- atomics from the tensor-core kernel's epilogue, no reduction launch
-    (lfgc_train_step_accumulate)."""
+    (lfgc_train_step_accumulate).  ``announce``: a ``peer_announce(...)`` block; the kernel's last CTA then stores this
+    rank's epoch flags for ``peer_sum(..., announced=True)``."""
     lib = L.load()
     if volume is not None:
         _req(volume, 'volume')
@@ -453,18 +454,36 @@ def train_step_accumulate(geom: Geometry, volume, n: int, seed: int, sample_offs
                                            int(sample_offset), _p(step_dev), int(step_stride), _p(explicit_idx),
                                            _p(coords), _p(targets), float(loss_scale), _p(_req(grid_cl, 'grid_cl')),
                                            _p(_req(mlp_flat, 'mlp')), _p(_req(grad_grid_cl, 'grad_grid_cl')),
-                                           _p(_req(grad_mlp_loss, 'grad_mlp_loss')), _p(_req(workspace, 'workspace')),
-                                           workspace.numel() * 4, _stream()), 'lfgc_train_step_accumulate')
+                                           _p(_req(grad_mlp_loss, 'grad_mlp_loss')),
+                                           ct.byref(announce) if announce is not None else None,
+                                           _p(_req(workspace, 'workspace')), workspace.numel() * 4, _stream()),
+            'lfgc_train_step_accumulate')
 
 
-def peer_sum(src_addrs, flag_addrs, rank: int, epoch, out, zero=None):
+def peer_announce(flag_addrs, rank: int, epoch, ticket):
+    """lfgc_peer_announce block: the flag arrays of all ranks (raw device addresses), this rank, the epoch counter peer_sum
+    maintains and a zeroed int32 ticket.  Keep the tensors alive as long as the block is in use."""
+    _req(epoch, 'epoch', torch.int32)
+    _req(ticket, 'ticket', torch.int32)
+    a = L.PeerAnnounce()
+    a.n_peers = len(flag_addrs)
+    a.rank = int(rank)
+    for i, addr in enumerate(flag_addrs):
+        a.flags[i] = int(addr)
+    a.epoch = epoch.data_ptr()
+    a.ticket = ticket.data_ptr()
+    return a
+
+
+def peer_sum(src_addrs, flag_addrs, rank: int, epoch, out, zero=None, announced=False):
     """out = sum over the ranks' buffers (raw device addresses, peer memory) behind the in-kernel barrier
     (lfgc_peer_sum); ``epoch``: int32[2] device tensor; ``zero``: buffer cleared in the same pass."""
     lib = L.load()
     _req(epoch, 'epoch', torch.int32)
     _req(out, 'out')
     L.check(lib.lfgc_peer_sum(L.ptr_array([int(a) for a in src_addrs]), L.ptr_array([int(a) for a in flag_addrs]),
-                              len(src_addrs), int(rank), _p(epoch), _p(out), _p(zero), out.numel(), _stream()),
+                              len(src_addrs), int(rank), _p(epoch), _p(out), _p(zero), out.numel(),
+                              1 if announced else 0, _stream()),
             'lfgc_peer_sum')
 
 

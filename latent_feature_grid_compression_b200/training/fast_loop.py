@@ -148,7 +148,10 @@ class FastTrainer:
                              peers=[[b + 4 * self._n_red * par for b in bases] for par in (0, 1)],
                              flags=[b + 4 * 2 * self._n_red for b in bases],
                              epoch=torch.zeros(2, device=self.device, dtype=torch.int32),
-                             summed=torch.zeros(self._n_red, device=self.device, dtype=torch.float32))
+                             summed=torch.zeros(self._n_red, device=self.device, dtype=torch.float32),
+                             ticket=torch.zeros(1, device=self.device, dtype=torch.int32))
+            self._p2p['announce'] = ops.peer_announce(self._p2p['flags'], self._p2p['rank'], self._p2p['epoch'],
+                                                      self._p2p['ticket'])
             torch.cuda.synchronize()
             dist.barrier(group=grp)          # every rank's flags are zero before anybody's first launch
         else:
@@ -436,14 +439,16 @@ class FastTrainer:
             return
         # the per-sample kernel adds its MLP-gradient and loss sums straight into the message buffer (cleared one step
         # earlier, like the grid-gradient section): no reduction launch between it and the peer sum
+        # ... and its last CTA stores this rank's epoch flags, so they cross NVLink during the launch gap
         ops.train_step_accumulate(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl, self.mlp_flat,
-                                  self.grad_grid, self.red_mlp, self.workspace, **kw)
+                                  self.grad_grid, self.red_mlp, self.workspace, announce=self._p2p['announce'], **kw)
         # lfgc_peer_sum: this step's buffers of all ranks -> one local sum (barrier inside the kernel); the accumulator it
         # clears is the OTHER parity's (its last readers finished before they announced this epoch)
         P = self._p2p
         par = self._par
         n_grid = self.grid_cl.numel()
-        ops.peer_sum(P['peers'][par], P['flags'], P['rank'], P['epoch'], P['summed'], zero=self._red2[par ^ 1])
+        ops.peer_sum(P['peers'][par], P['flags'], P['rank'], P['epoch'], P['summed'], zero=self._red2[par ^ 1],
+                     announced=True)
         common['zero_grid'] = None
         ops.grid_step(geom, [P['summed'][:n_grid]], [P['summed'][n_grid:]], 1, pcount + 1, pcount, **common)
 
