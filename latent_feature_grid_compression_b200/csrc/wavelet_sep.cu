@@ -27,7 +27,7 @@ namespace wsep {
 struct Level {
     int C, d[3], t[3], off[3], m_lo[3], n_m[3];
     float lo[LFGC_MAX_TAPS], hi[LFGC_MAX_TAPS];
-    FastDiv by_d1, by_d2, by_nm2;
+    FastDiv by_d1, by_d2, by_nm2, by_plane;
     PassPlan sy, ay;           // the y passes: column (a, ox) fastest (contiguous global stores / conflict-free smem)
 };
 
@@ -53,9 +53,29 @@ __global__ void __launch_bounds__(256) synth_xy_kernel(const __grid_constant__ L
     const size_t dvol = (size_t)d0 * plane;
     const float* lsrc = low + ((size_t)c * d0 + iz) * plane;
     const float* hsrc = high + ((size_t)c * 7 * d0 + iz) * plane;
-    for (int i = threadIdx.x; i < plane; i += blockDim.x) B[i] = __ldg(lsrc + i);
-    for (int k = 1; k < 8; ++k)
-        for (int i = threadIdx.x; i < plane; i += blockDim.x) B[k * plane + i] = __ldg(hsrc + (size_t)(k - 1) * dvol + i);
+    // B = [low plane | 7 high planes], one flat index space; eight independent loads in flight per thread (the plain
+    // per-plane loops kept ~1 load in flight: the load phase was a chain of L2 round trips, long-scoreboard + barrier stalls)
+    {
+        const int total = 8 * plane;
+        for (int base = threadIdx.x; base < total; base += 8 * blockDim.x) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * blockDim.x;
+                v[u] = 0.0f;
+                if (idx < total) {
+                    const int k = fdiv(idx, L.by_plane);
+                    const int i = idx - k * plane;
+                    v[u] = __ldg(k == 0 ? lsrc + i : hsrc + (size_t)(k - 1) * dvol + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * blockDim.x;
+                if (idx < total) B[idx] = v[u];
+            }
+        }
+    }
     __syncthreads();
     // x pass: unit = (row = (ab, iy), pair m), m FASTEST: neighbouring threads write neighbouring ox (a row-fastest order
     // strides the shared-memory stores by t2 floats: 32-way bank conflicts at t2 = 64, measured +110 us per step at C32/G64)
@@ -143,7 +163,27 @@ __global__ void __launch_bounds__(256) adj_yx_kernel(const __grid_constant__ Lev
     const int pl = t1 * t2;
     for (int a_ = 0; a_ < 2; ++a_) {
         const float* src = Y + ((size_t)(c * 2 + a_) * d0 + iz) * pl;
-        for (int i = threadIdx.x; i < pl; i += blockDim.x) Ys[a_ * pl + i] = __ldg(src + i);
+        if ((pl & 3) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {   // 128-bit loads, four in flight per thread
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(Ys + a_ * pl);
+            const int n4 = pl >> 2;
+            for (int base = threadIdx.x; base < n4; base += 4 * blockDim.x) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * blockDim.x;
+                    if (i < n4) v[u] = __ldg(s4 + i);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * blockDim.x;
+                    if (i < n4) d4[i] = v[u];
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int i = threadIdx.x; i < pl; i += blockDim.x) Ys[a_ * pl + i] = __ldg(src + i);
+        }
     }
     __syncthreads();
     // y^T pass: unit = (range of iy, column = (a, ox)): Ys[a][:][ox] -> X[(a, b = 0 / 1)][iy][ox]
@@ -197,21 +237,41 @@ __global__ void __launch_bounds__(1024) synth_z_cl_kernel(const __grid_constant_
     }
     const float* y0 = Y + (size_t)(live ? c : 0) * 2 * d0 * pl + (live ? pos : 0);
     const float* y1 = y0 + (size_t)d0 * pl;
-    for (int m = L.m_lo[0]; m < L.m_lo[0] + L.n_m[0]; ++m) {
-        float ev = 0.0f, od = 0.0f;
-        if (live) {
-#pragma unroll
-            for (int a = 0; a < NT / 2; ++a) {
-                const int i = m - a;
-                if ((unsigned)i < (unsigned)d0) {
-                    const float l = __ldg(y0 + (size_t)i * pl), h = __ldg(y1 + (size_t)i * pl);
-                    ev = fmaf(l, flo[2 * a], ev);
-                    ev = fmaf(h, fhi[2 * a], ev);
-                    od = fmaf(l, flo[2 * a + 1], od);
-                    od = fmaf(h, fhi[2 * a + 1], od);
-                }
-            }
+    // Sliding window over the input planes (each is used by NT / 2 consecutive m) with the NEXT plane's two loads issued
+    // before this iteration's barriers and stores: the loop used to expose one global round trip per m (33 of them per CTA).
+    constexpr int NW = NT / 2;
+    float wl[NW], wh[NW];   // wl[a] = low input plane m - a
+    // blockIdx.z splits the m range: 128 CTAs of 33 dependent iterations each left SMs idle and the chain long
+    const int m_per = (L.n_m[0] + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int m_begin = L.m_lo[0] + (int)blockIdx.z * m_per;
+    const int m_end = min(m_begin + m_per, L.m_lo[0] + L.n_m[0]);
+    auto load_plane = [&](int i, float& l, float& h) {
+        l = h = 0.0f;
+        if (live && (unsigned)i < (unsigned)d0) {
+            l = __ldg(y0 + (size_t)i * pl);
+            h = __ldg(y1 + (size_t)i * pl);
         }
+    };
+#pragma unroll
+    for (int a = 0; a < NW; ++a) load_plane(m_begin - a, wl[a], wh[a]);
+    for (int m = m_begin; m < m_end; ++m) {
+        float ln, hn;
+        load_plane(m + 1 < m_end ? m + 1 : -1, ln, hn);
+        float ev = 0.0f, od = 0.0f;
+#pragma unroll
+        for (int a = 0; a < NW; ++a) {
+            ev = fmaf(wl[a], flo[2 * a], ev);
+            ev = fmaf(wh[a], fhi[2 * a], ev);
+            od = fmaf(wl[a], flo[2 * a + 1], od);
+            od = fmaf(wh[a], fhi[2 * a + 1], od);
+        }
+#pragma unroll
+        for (int a = NW - 1; a > 0; --a) {
+            wl[a] = wl[a - 1];
+            wh[a] = wh[a - 1];
+        }
+        wl[0] = ln;
+        wh[0] = hn;
         tile[0][ty][tx] = ev;      // [channel][position]
         tile[1][ty][tx] = od;
         __syncthreads();
@@ -255,21 +315,31 @@ __global__ void __launch_bounds__(1024) adj_z_cl_kernel(const __grid_constant__ 
     float* y0 = Y + (size_t)(live ? c : 0) * 2 * d0 * pl + (live ? pos : 0);
     float* y1 = y0 + (size_t)d0 * pl;
     // planes below the first window position that are still inside it: load NT - 2 planes up front (q = -off .. -off + NT - 3)
-    for (int i = -((NT - 2) / 2); i < d0; ++i) {
+    auto load_pair = [&](int i, float& a0, float& a1) {
         // the two planes entering the window of input position i: q = 2 i + NT - 2 - off and the next one
         const int qa = 2 * i + NT - 2 - L.off[0];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int q = qa + k;
-            tile[k][ty][tx] = (rlive && (unsigned)q < (unsigned)t0) ? __ldg(g_cl + ((size_t)q * pl + rpos) * Cp + rc) : 0.0f;
-        }
+        a0 = (rlive && (unsigned)qa < (unsigned)t0) ? __ldg(g_cl + ((size_t)qa * pl + rpos) * Cp + rc) : 0.0f;
+        a1 = (rlive && (unsigned)(qa + 1) < (unsigned)t0) ? __ldg(g_cl + ((size_t)(qa + 1) * pl + rpos) * Cp + rc) : 0.0f;
+    };
+    // blockIdx.z splits the input positions; every chunk first fills its window (NT - 2 planes)
+    const int i_per = (d0 + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int i_begin = (int)blockIdx.z * i_per, i_end = min(i_begin + i_per, d0);
+    float c0, c1;
+    load_pair(i_begin - (NT - 2) / 2, c0, c1);
+    for (int i = i_begin - (NT - 2) / 2; i < i_end; ++i) {
+        float n0 = 0.0f, n1 = 0.0f;
+        if (i + 1 < i_end) load_pair(i + 1, n0, n1);   // next iteration's planes: in flight across the barriers below
+        tile[0][ty][tx] = c0;
+        tile[1][ty][tx] = c1;
+        c0 = n0;
+        c1 = n1;
         __syncthreads();
 #pragma unroll
         for (int tt = 0; tt + 2 < NT; ++tt) w[tt] = w[tt + 2];
         w[NT - 2] = tile[0][tx][ty];      // [position][channel] as stored by the read role
         w[NT - 1] = tile[1][tx][ty];
         __syncthreads();
-        if (i >= 0 && live) {
+        if (i >= i_begin && live) {
             float lo = 0.0f, hi = 0.0f;
 #pragma unroll
             for (int tt = 0; tt < NT; ++tt) {
@@ -298,6 +368,7 @@ static void fill_level(Level& L, const lfgc_wavelet_desc* w, int l) {
     L.by_d1 = make_fastdiv((unsigned)L.d[1]);
     L.by_d2 = make_fastdiv((unsigned)L.d[2]);
     L.by_nm2 = make_fastdiv((unsigned)L.n_m[2]);
+    L.by_plane = make_fastdiv((unsigned)(L.d[1] * L.d[2]));
     // one position per unit: these passes are latency-bound, more independent units hide it better
     L.sy = make_plan(2 * L.t[2], L.n_m[1], 1 << 24);
     L.ay = make_plan(2 * L.t[2], L.d[1], 1 << 24);
@@ -365,7 +436,7 @@ static int sep_fwd(const lfgc_wavelet_desc* w, const float* const* coeff, float*
         LFGC_LAUNCH_OK();
         const int pl = L.t[1] * L.t[2];
         if (l == w->n_coeff - 1) {   // finest level: straight into the channels-last grid
-            (void)launch_pdl(synth_z_cl_kernel<NT>, dim3((unsigned)((pl + 31) / 32), (unsigned)((Cp + 31) / 32)), dim3(1024), (size_t)0,
+            (void)launch_pdl(synth_z_cl_kernel<NT>, dim3((unsigned)((pl + 31) / 32), (unsigned)((Cp + 31) / 32), 2u), dim3(1024), (size_t)0,
                              st, L, (const float*)Y, grid_cl, also_zero, Cp);
             LFGC_LAUNCH_OK();
             break;
@@ -399,7 +470,7 @@ static int sep_bwd(const lfgc_wavelet_desc* w, const float* grad_grid_cl, int Cp
         fill_level(L, w, l);
         const int pl = L.t[1] * L.t[2];
         if (l == last) {   // finest level: straight from the channels-last gradient
-            (void)launch_pdl(adj_z_cl_kernel<NT>, dim3((unsigned)((pl + 31) / 32), (unsigned)((L.C + 31) / 32)), dim3(1024), (size_t)0,
+            (void)launch_pdl(adj_z_cl_kernel<NT>, dim3((unsigned)((pl + 31) / 32), (unsigned)((L.C + 31) / 32), 2u), dim3(1024), (size_t)0,
                              st, L, grad_grid_cl, Cp, Y);
         } else {
             (void)launch_pdl(adj_z_kernel<NT>, dim3((unsigned)((pl + 255) / 256), (unsigned)L.C), dim3(256), (size_t)0, st, L, g, Y);
