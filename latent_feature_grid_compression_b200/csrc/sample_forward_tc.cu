@@ -228,9 +228,18 @@ __global__ void __launch_bounds__(TILE * G, 1) sample_forward_tc_kernel(const __
                     cz = __ldg(A.coords + 3 * s + 2);
                 } else {
                     const int64_t v = A.first + s;
-                    const int k = (int)(v % A.R2);
-                    const int j = (int)((v / A.R2) % A.R1);
-                    const int i = (int)(v / ((int64_t)A.R2 * A.R1));
+                    int i, j, k;
+                    if (v < 0x100000000ll && (int64_t)A.R2 * A.R1 < 0x100000000ll) {   // 32-bit index arithmetic (every shipped volume): two divisions instead of
+                        const unsigned v32 = (unsigned)v, r2 = (unsigned)A.R2, r12 = r2 * (unsigned)A.R1;   // three 64-bit ones
+                        const unsigned ii = v32 / r12, rem = v32 - ii * r12, jj = rem / r2;
+                        i = (int)ii;
+                        j = (int)jj;
+                        k = (int)(rem - jj * r2);
+                    } else {
+                        k = (int)(v % A.R2);
+                        j = (int)((v / A.R2) % A.R1);
+                        i = (int)(v / ((int64_t)A.R2 * A.R1));
+                    }
                     cx = __ldg(A.axis[0] + i);
                     cy = __ldg(A.axis[1] + j);
                     cz = __ldg(A.axis[2] + k);
