@@ -271,8 +271,11 @@ int lfgc_adam_reg(float* p, float* g, float* m, float* v, int64_t n, const float
 int lfgc_add_l2_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 int lfgc_add_l1_grad(float* g, const float* p, int64_t n, float weight, void* stream);
 
-/* lfgc_train_step that ADDS its MLP-gradient sums and its loss sum to grad_mlp_loss[0 .. lfgc_mlp_param_count] (the last
- * float is the loss): the buffer is a running sum the caller cleared (or carries over).  The tensor-core kernel adds with
+/* lfgc_train_step that ADDS its MLP-gradient sums and its loss sum to grad_mlp_loss: n_slices rows of
+ * lfgc_mlp_param_count + 1 floats (the last float of a row is the loss); the buffer is a running sum the caller cleared (or
+ * carries over) and the result is the SUM OF THE ROWS (lfgc_grid_step's nslices / pstride take exactly this).  The CTAs are
+ * spread over the rows because same-address reductions of 148 CTAs arriving together serialise in L2 (one row: +3.5 us);
+ * kernels other than the tensor-core one add everything to row 0.  The tensor-core kernel adds with
  * atomics from its own epilogue, so there is no reduction launch and no use of the workspace slices; the summation order is
  * then not fixed (like the grid gradient's, which always accumulates with atomics).  This is the per-sample launch of the
  * data-parallel step: the buffer is the MLP section of the [grid gradient | MLP gradient | loss] message lfgc_peer_sum reads. */
@@ -292,8 +295,8 @@ int lfgc_train_step_accumulate(const lfgc_model_desc* m, const float* volume, co
                                uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
                                const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
                                float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl,
-                               float* grad_mlp_loss, const lfgc_peer_announce* announce /* nullable */, void* workspace,
-                               size_t workspace_bytes, void* stream);
+                               float* grad_mlp_loss, int n_slices, const lfgc_peer_announce* announce /* nullable */,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* lfgc_train_step that LEAVES the MLP-gradient partial sums in the workspace instead of reducing them: *nslices_out (host
  * int, written at call time) rows of (lfgc_mlp_param_count + 1) floats, the last float of a row being that slice's

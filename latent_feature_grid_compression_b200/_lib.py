@@ -100,7 +100,7 @@ _SIGNATURES = {
                                            C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, C.c_size_t,
                                            C.POINTER(C.c_int32), _f]),
     'lfgc_train_step_accumulate': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64,
-                                             _f, C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, C.POINTER(PeerAnnounce),
+                                             _f, C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, C.c_int, C.POINTER(PeerAnnounce),
                                              _f, C.c_size_t, _f]),
     'lfgc_grid_step': (C.c_int, [C.POINTER(WaveletDesc), C.c_int, C.POINTER(GridStepArgs), _f]),
     'lfgc_grid_step_smem_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),

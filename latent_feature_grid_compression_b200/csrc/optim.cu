@@ -185,10 +185,17 @@ __global__ void __launch_bounds__(512) peer_sum_kernel(const __grid_constant__ P
 #endif
     const long long n4 = A.n >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 acc = __ldcv(reinterpret_cast<const float4*>(A.src[0]) + i);   // peer data changes every step: never from L1
-        for (int r = 1; r < A.n_srcs; ++r) {
-            const float4 v = __ldcv(reinterpret_cast<const float4*>(A.src[r]) + i);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        // peer data changes every step: never from L1.  Four sources' loads are in flight together (NVLink round trips
+        // overlap), the sum stays in rank order
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r0 = 0; r0 < A.n_srcs; r0 += 4) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + u < A.n_srcs) v[u] = __ldcv(reinterpret_cast<const float4*>(A.src[r0 + u]) + i);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + u < A.n_srcs) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
         }
         reinterpret_cast<float4*>(A.out)[i] = acc;
         if (A.zero) reinterpret_cast<float4*>(A.zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -201,6 +208,8 @@ __global__ void __launch_bounds__(512) peer_sum_kernel(const __grid_constant__ P
         atomicAdd(&g_peer_ns[0], t_bar - t_in);
         atomicAdd(&g_peer_ns[1], t_end - t_bar);
         atomicAdd(&g_peer_ns[2], 1ull);
+        g_peer_ns[4] = t_in;     // last launch: entry and exit of CTA 0
+        g_peer_ns[5] = t_end;
     }
 #endif
     if (tid == 0) {

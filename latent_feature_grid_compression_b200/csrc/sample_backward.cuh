@@ -32,6 +32,8 @@ struct BwdArgs {
     float* atomic_out = nullptr;  // lfgc_train_step_accumulate: [pcount + 1] running sums (MLP gradient | loss) the kernel
                                   // ADDS to; the tensor-core kernel does it with atomics from its flush (no workspace
                                   // slices, no reduction launch), the other kernels through the reduction kernel
+    int atomic_slices = 1;        // the tensor-core kernel spreads its CTAs over this many [pcount + 1] slices of atomic_out:
+                                  // 148 same-address reductions arriving together serialise in L2 (~3.5 us at one slice)
     // early announcement for lfgc_peer_sum (lfgc_peer_announce): the last CTA to finish stores *ann_epoch + 1 into slot
     // [ann_rank] of every rank's flag array
     int ann_n = 0, ann_rank = 0;
@@ -40,11 +42,15 @@ struct BwdArgs {
     int* ann_ticket = nullptr;
 };
 
-// stores the announcement of BwdArgs (one thread); used by the tensor-core kernel's last CTA and by announce_kernel
-__device__ __forceinline__ void announce_epoch(const BwdArgs& A) {
-    const int e = *reinterpret_cast<const volatile int*>(A.ann_epoch) + 1;
-    for (int r = 0; r < A.ann_n; ++r)
-        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(A.ann_flags[r] + A.ann_rank), "r"(e) : "memory");
+// stores the announcement of BwdArgs: called by the first ann_n lanes of ONE converged warp, lane r writes rank r's slot (the
+// release stores of the lanes travel in parallel; one thread storing them one after the other cost ~1 us per peer).  What
+// the peers go on to read was made visible at device scope -- this GPU's L2, which is where peer reads are served -- before
+// the caller decided to announce.
+__device__ __forceinline__ void announce_epoch(const BwdArgs& A, int lane) {
+    if (lane < A.ann_n) {
+        const int e = *reinterpret_cast<const volatile int*>(A.ann_epoch) + 1;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(A.ann_flags[lane] + A.ann_rank), "r"(e) : "memory");
+    }
 }
 void launch_announce(const BwdArgs& A, cudaStream_t st);
 

@@ -46,9 +46,15 @@
 
 #ifdef LFGC_PHASE_TIMING
 __device__ unsigned long long g_btc_cycles[16];
-#define BT_DECL long long _tl = clock64(); unsigned long long _tp[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0};
+__device__ unsigned long long g_btc_time[4];   // globaltimer: [0] entry (CTA 0), [1] latest exit of the last launch; [2], [3]: the launch before
+__device__ __forceinline__ unsigned long long btc_gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define BT_DECL if (threadIdx.x == 0 && blockIdx.x == 0) { g_btc_time[2] = g_btc_time[0]; g_btc_time[3] = g_btc_time[1]; g_btc_time[0] = btc_gtimer(); g_btc_time[1] = 0; } long long _tl = clock64(); unsigned long long _tp[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0};
 #define BT_MARK(i) { long long _n = clock64(); _tp[i] += (unsigned long long)(_n - _tl); _tl = _n; }
-#define BT_FLUSH() { if (threadIdx.x == 0) for (int _i = 0; _i < 16; ++_i) atomicAdd(&g_btc_cycles[_i], _tp[_i]); }
+#define BT_FLUSH() { if (threadIdx.x == 0) { for (int _i = 0; _i < 16; ++_i) atomicAdd(&g_btc_cycles[_i], _tp[_i]); atomicMax(&g_btc_time[1], btc_gtimer()); } }
 #else
 #define BT_DECL
 #define BT_MARK(i)
@@ -767,7 +773,7 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
     // sums themselves, added to with atomics (148 CTAs x 3.4 k reductions at the very end of the kernel cost less than the
     // reduction launch they replace in the data-parallel step)
     float* const aout = A.atomic_out;
-    float* dst = aout ? aout : A.partial + (size_t)blockIdx.x * A.pstride;
+    float* dst = aout ? aout + (size_t)(blockIdx.x % (unsigned)A.atomic_slices) * A.pstride : A.partial + (size_t)blockIdx.x * A.pstride;
     auto put = [&](int idx, float v) {
         if (aout) atomicAdd(dst + idx, v);
         else dst[idx] = v;
@@ -845,13 +851,18 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         // its ticket; the CTA that draws the last one knows all of this rank's sums are complete and tells the peers
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const int ticket = atomicAdd(A.ann_ticket, 1);
-            if (ticket == (int)gridDim.x - 1) {
-                *A.ann_ticket = 0;
-                __threadfence();
-                announce_epoch(A);
+        if (warp == 0) {
+            int last = 0;
+            if (lane == 0) {
+                const int ticket = atomicAdd(A.ann_ticket, 1);
+                if (ticket == (int)gridDim.x - 1) {
+                    *A.ann_ticket = 0;
+                    __threadfence();
+                    last = 1;
+                }
             }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) announce_epoch(A, lane);
         }
     }
     BT_MARK(10)  // flush
@@ -915,6 +926,15 @@ extern "C" int lfgc_btc_timing(unsigned long long* out16, int reset) {
     if (reset) {
         unsigned long long z[16] = {0};
         cudaMemcpyToSymbol(g_btc_cycles, z, sizeof(z));
+    }
+    return 0;
+}
+extern "C" int lfgc_btc_time(unsigned long long* out2, int reset) {
+    cudaDeviceSynchronize();
+    if (out2) cudaMemcpyFromSymbol(out2, g_btc_time, sizeof(unsigned long long) * 4);
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_btc_time, z, sizeof(z));
     }
     return 0;
 }

@@ -433,9 +433,10 @@ def train_step_partials(geom: Geometry, volume, n: int, seed: int, sample_offset
 
 def train_step_accumulate(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl,
                           mlp_flat, grad_grid_cl, grad_mlp_loss, workspace, step_dev=None, step_stride: int = 0,
-                          coords=None, targets=None, explicit_idx=None, announce=None):
+                          coords=None, targets=None, explicit_idx=None, announce=None, n_slices: int = 1):
     """``train_step`` that ADDS its MLP-gradient sums and loss sum to ``grad_mlp_loss`` (mlp_param_count + 1 floats, a
-    running sum the caller cleared) -- atomics from the tensor-core kernel's epilogue, no reduction launch
+    per row, ``n_slices`` rows whose SUM is the result: a running sum the caller cleared) -- atomics from the tensor-core
+    kernel's epilogue, its CTAs spread over the rows, no reduction launch
     (lfgc_train_step_accumulate).  ``announce``: a ``peer_announce(...)`` block; the kernel's last CTA then stores this
     rank's epoch flags for ``peer_sum(..., announced=True)``."""
     lib = L.load()
@@ -446,15 +447,15 @@ def train_step_accumulate(geom: Geometry, volume, n: int, seed: int, sample_offs
         _req(targets, 'targets')
     if explicit_idx is not None:
         _req(explicit_idx, 'explicit_idx', torch.int64)
-    if grad_mlp_loss.numel() < geom.mlp_param_count + 1:
+    if grad_mlp_loss.numel() < n_slices * (geom.mlp_param_count + 1):
         raise L.LfgcError('train_step_accumulate: grad_mlp_loss holds %d floats, %d needed'
-                          % (grad_mlp_loss.numel(), geom.mlp_param_count + 1))
+                          % (grad_mlp_loss.numel(), n_slices * (geom.mlp_param_count + 1)))
     shape3 = L.int3(volume.shape) if volume is not None else None
     L.check(lib.lfgc_train_step_accumulate(ct.byref(geom.model_desc), _p(volume), shape3, int(n), int(seed),
                                            int(sample_offset), _p(step_dev), int(step_stride), _p(explicit_idx),
                                            _p(coords), _p(targets), float(loss_scale), _p(_req(grid_cl, 'grid_cl')),
                                            _p(_req(mlp_flat, 'mlp')), _p(_req(grad_grid_cl, 'grad_grid_cl')),
-                                           _p(_req(grad_mlp_loss, 'grad_mlp_loss')),
+                                           _p(_req(grad_mlp_loss, 'grad_mlp_loss')), int(n_slices),
                                            ct.byref(announce) if announce is not None else None,
                                            _p(_req(workspace, 'workspace')), workspace.numel() * 4, _stream()),
             'lfgc_train_step_accumulate')

@@ -126,13 +126,16 @@ class FastTrainer:
         # run all-reduces ONE message (the adjoint is linear: reducing the grid gradient replaces reducing the coefficient
         # gradients, 0.23 MB instead of 0.45 MB at C16/G15)
         n_grid = self.grid_cl.numel()
-        self._n_red = (n_grid + self.n_mlp_elems + 1 + 3) // 4 * 4
         self._p2p = None
         import os
         mode = os.environ.get('LFGC_ALLREDUCE', 'p2p')
         gstep_ok = (os.environ.get('LFGC_GRID_STEP', '1') != '0' and self.var_cfg is None and not self.mask_params
                     and all(s is None for s in model.mask_specs()) and self.weight_l1 == 0.0
                     and ops.grid_step_supported(self.geom))
+        # message of the data-parallel step: [grid gradient | K rows of (MLP gradient, loss)]; K > 1 only where the per-sample
+        # kernel adds its sums with atomics (peer-sum path): its CTAs are spread over the rows
+        self._acc_slices = 8 if (self.world > 1 and mode == 'p2p' and gstep_ok and self.world <= L.MAX_PEERS) else 1
+        self._n_red = (n_grid + self._acc_slices * (self.n_mlp_elems + 1) + 3) // 4 * 4
         if self.world > 1 and mode == 'p2p' and gstep_ok and self.world <= L.MAX_PEERS:
             # No collective: the two parity copies of the buffer live in torch symmetric memory, lfgc_peer_sum reads
             # every rank's copy over NVLink behind its own in-kernel barrier (flags at the end of the allocation).
@@ -238,7 +241,7 @@ class FastTrainer:
         n_grid = self.grid_cl.numel()
         self.red = self._red2[par % len(self._red2)]
         self.grad_grid = self.red[:n_grid].view_as(self.grid_cl)
-        self.red_mlp = self.red[n_grid:n_grid + self.n_mlp_elems + 1]
+        self.red_mlp = self.red[n_grid:n_grid + self._acc_slices * (self.n_mlp_elems + 1)]
 
     def grad_of(self, p):
         return self._grad_view[id(p)]
@@ -441,7 +444,8 @@ class FastTrainer:
         # earlier, like the grid-gradient section): no reduction launch between it and the peer sum
         # ... and its last CTA stores this rank's epoch flags, so they cross NVLink during the launch gap
         ops.train_step_accumulate(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl, self.mlp_flat,
-                                  self.grad_grid, self.red_mlp, self.workspace, announce=self._p2p['announce'], **kw)
+                                  self.grad_grid, self.red_mlp, self.workspace, announce=self._p2p['announce'],
+                                  n_slices=self._acc_slices, **kw)
         # lfgc_peer_sum: this step's buffers of all ranks -> one local sum (barrier inside the kernel); the accumulator it
         # clears is the OTHER parity's (its last readers finished before they announced this epoch)
         P = self._p2p
@@ -450,7 +454,7 @@ class FastTrainer:
         ops.peer_sum(P['peers'][par], P['flags'], P['rank'], P['epoch'], P['summed'], zero=self._red2[par ^ 1],
                      announced=True)
         common['zero_grid'] = None
-        ops.grid_step(geom, [P['summed'][:n_grid]], [P['summed'][n_grid:]], 1, pcount + 1, pcount, **common)
+        ops.grid_step(geom, [P['summed'][:n_grid]], [P['summed'][n_grid:]], self._acc_slices, pcount + 1, pcount, **common)
 
     def capture(self, host_fed=False):
         """Warm up eagerly (counts launches), then record the step into a CUDA graph; the optimiser state the
@@ -579,11 +583,17 @@ class FastTrainer:
     def set_lr(self, lr: float):
         self.lr_dev.fill_(float(lr))
 
+    def _summed_loss(self):
+        """Global loss sum of the last peer-summed step: the last float of every row of the message's MLP section."""
+        n_grid, row = self.grid_cl.numel(), self.n_mlp_elems + 1
+        rows = self._p2p['summed'][n_grid:n_grid + self._acc_slices * row].view(self._acc_slices, row)
+        return rows[:, -1].sum()
+
     def last_loss(self) -> float:
         """Mean squared error of the last step's batch (device -> host read): the local batch, or -- peer-sum data
         parallelism, where the loss travels in the summed message -- the global one."""
         if self._p2p is not None:
-            return float(self._p2p['summed'][self.grid_cl.numel() + self.n_mlp_elems].item()) / (self.batch * self.world)
+            return float(self._summed_loss().item()) / (self.batch * self.world)
         return float(self.loss_sum.item()) / self.batch
 
     def complete_loss(self) -> float:
@@ -595,7 +605,7 @@ class FastTrainer:
             raise L.LfgcError('complete_loss() is defined for the MSE (+ SmallifyLoss) objective only')
         with torch.no_grad():
             if self._p2p is not None:   # already summed over the ranks (identical on every rank)
-                t = self._p2p['summed'][self.grid_cl.numel() + self.n_mlp_elems].double() / float(self.batch * self.world)
+                t = self._summed_loss().double() / float(self.batch * self.world)
             else:
                 t = self.loss_sum.double() / float(self.batch * self.world)
             if self.world > 1 and self._p2p is None:

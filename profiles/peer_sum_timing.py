@@ -43,6 +43,20 @@ if timed:
 k = max(int(buf[2]), 1)
 print('rank %d: step %.2f us; peer_sum CTA 0: barrier wait %.2f us, remote reads + sum %.2f us (%d launches)' % (
     rank, 1e3 * e0.elapsed_time(e1) / n, buf[0] / k / 1e3, buf[1] / k / 1e3, k), flush=True)
+# timeline of the last of a few queued steps (timing build): per-sample kernel entry/exit, peer-sum entry/exit, step period
+if timed:
+    lib.lfgc_btc_time.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    torch.cuda.synchronize(); dist.barrier()
+    for rep in range(3):
+        for _ in range(8):
+            tr.step()
+        torch.cuda.synchronize()
+        bt = (ctypes.c_ulonglong * 4)(); lib.lfgc_btc_time(bt, 0)
+        pb = (ctypes.c_ulonglong * 8)(); lib.lfgc_peer_timing(pb, 0)
+        us = lambda a, b: (int(a) - int(b)) / 1e3
+        print('rank %d: period %.2f us = per-sample kernel %.2f + gap %.2f + peer sum %.2f + rest (grid step, 3 launches) %.2f'
+              % (rank, us(bt[0], bt[2]), us(bt[1], bt[0]), us(pb[4], bt[1]), us(pb[5], pb[4]),
+                 us(bt[0], bt[2]) - us(bt[1], bt[0]) - us(pb[4], bt[1]) - us(pb[5], pb[4])), flush=True)
 # the per-sample kernel alone: gradient accumulators in ordinary device memory vs in the symmetric-memory message buffer
 from latent_feature_grid_compression_b200 import ops  # noqa: E402
 geom = tr.geom

@@ -304,12 +304,14 @@ def test_train_step_accumulate_adds_the_same_sums(n, tc, monkeypatch):
     loss = torch.zeros(1, device='cuda')
     ops.train_step(geom, vol, n, 0, 0, 1.0 / n, grid_cl, mlp, gg, gm, loss, ws, explicit_idx=idx)
     gg2 = torch.zeros_like(grid_cl)
-    acc = torch.zeros(geom.mlp_param_count + 1, device='cuda')
+    K = 1 if n == 1000 else 8    # rows the CTAs are spread over (the result is the sum of the rows)
+    acc = torch.zeros(K * (geom.mlp_param_count + 1), device='cuda')
     for rep in (1, 2):     # a running sum: the second call doubles it
-        ops.train_step_accumulate(geom, vol, n, 0, 0, 1.0 / n, grid_cl, mlp, gg2, acc, ws, explicit_idx=idx)
+        ops.train_step_accumulate(geom, vol, n, 0, 0, 1.0 / n, grid_cl, mlp, gg2, acc, ws, explicit_idx=idx, n_slices=K)
         torch.cuda.synchronize()
-        assert float((acc[:-1] - rep * gm).abs().max()) <= 3e-6 * rep * float(gm.abs().max())
-        assert abs(float(acc[-1]) - rep * float(loss)) <= 1e-5 * rep * float(loss)
+        tot = acc.view(K, -1).sum(0)
+        assert float((tot[:-1] - rep * gm).abs().max()) <= 3e-6 * rep * float(gm.abs().max())
+        assert abs(float(tot[-1]) - rep * float(loss)) <= 1e-5 * rep * float(loss)
         assert float((gg2 - rep * gg).abs().max()) <= 3e-6 * rep * float(gg.abs().max())
 
 
