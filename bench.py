@@ -530,7 +530,8 @@ def measure_config(name, volume, rank, world, dev, pk, opt_steps=300, with_recon
             # the fused per-sample kernel ALONE (its MLP-gradient partial sums stay in the workspace; their reduction is a
             # separate launch / part of lfgc_grid_step)
             ops.train_step_partials(geom, volume, n, 1234, 0, 1.0 / n, trainer.grid_cl, trainer.mlp_flat,
-                                    trainer.grad_grid, trainer.workspace, step_dev=trainer.step_dev, step_stride=n)
+                                    trainer.grad_grid, trainer.workspace, step_dev=trainer.step_dev, step_stride=n,
+                                    tc_panels=getattr(trainer, '_tc_panels', None))   # as the trainer launches it
             if i >= 5:
                 ke[i - 5][1].record()
         torch.cuda.synchronize()
@@ -689,7 +690,8 @@ def run_native(args):
             # the fused per-sample kernel ALONE (its MLP-gradient partial sums stay in the workspace; their reduction is a
             # separate launch / part of lfgc_grid_step)
             ops.train_step_partials(geom, volume, n, 1234, 0, 1.0 / n, trainer.grid_cl, trainer.mlp_flat,
-                                    trainer.grad_grid, trainer.workspace, step_dev=trainer.step_dev, step_stride=n)
+                                    trainer.grad_grid, trainer.workspace, step_dev=trainer.step_dev, step_stride=n,
+                                    tc_panels=getattr(trainer, '_tc_panels', None))   # as the trainer launches it
             if i >= 5:
                 ke[i - 5][1].record()
         torch.cuda.synchronize()

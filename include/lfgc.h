@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LFGC_ABI_VERSION 5 /* 5: lfgc_peer_announce; 4: + lfgc_train_step_accumulate; 3: lfgc_grid_step / lfgc_train_step_partials replace lfgc_step_glue */
+#define LFGC_ABI_VERSION 6 /* 6: tensor-core operand image (lfgc_tc_panel_*); 5: lfgc_peer_announce; 4: + lfgc_train_step_accumulate; 3: lfgc_grid_step / lfgc_train_step_partials replace lfgc_step_glue */
 #define LFGC_MAX_LEVELS 12 /* coefficient tensors per model (1 low-pass + up to 11 detail levels) */
 #define LFGC_MAX_TAPS 16   /* longest supported 1-D reconstruction filter */
 #define LFGC_MAX_LAYERS 8  /* hidden layers of the decoder MLP */
@@ -296,7 +296,18 @@ int lfgc_train_step_accumulate(const lfgc_model_desc* m, const float* volume, co
                                const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
                                float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl,
                                float* grad_mlp_loss, int n_slices, const lfgc_peer_announce* announce /* nullable */,
-                               void* workspace, size_t workspace_bytes, void* stream);
+                               const float* tc_panels /* nullable: lfgc_tc_panel_build */, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
+/* Weight operands of the tensor-core training kernel as a ready-made image in device memory (csrc/tc_panels.cuh): the
+ * tf32 hi / lo split of every MLP weight in the kernel's two shared-memory operand layouts plus the biases, so that the
+ * kernel's per-launch setup is a straight copy instead of a rebuild (12 k of 64 k cycles per launch at 32768 samples).
+ * lfgc_tc_panel_bytes: size of the image, 0 when the tensor-core kernel does not cover the model (nothing to pass then).
+ * lfgc_tc_panel_build: (re)builds the image from the packed parameter block `mlp` -- call it after the parameters changed
+ * outside lfgc_grid_step, which keeps the image current itself (lfgc_grid_step_args.panel_image).  Passing a stale image to
+ * lfgc_train_step_partials / _accumulate trains on stale weights: the owner of the parameters owns the image. */
+size_t lfgc_tc_panel_bytes(const lfgc_model_desc* m);
+int lfgc_tc_panel_build(const lfgc_model_desc* m, const float* mlp, float* image, void* stream);
 
 /* lfgc_train_step that LEAVES the MLP-gradient partial sums in the workspace instead of reducing them: *nslices_out (host
  * int, written at call time) rows of (lfgc_mlp_param_count + 1) floats, the last float of a row being that slice's
@@ -306,7 +317,8 @@ int lfgc_train_step_partials(const lfgc_model_desc* m, const float* volume, cons
                              uint64_t sample_offset, const int32_t* step_dev, uint64_t step_stride,
                              const int64_t* explicit_idx, const float* explicit_coords, const float* explicit_gt,
                              float loss_scale, const float* grid_cl, const float* mlp, float* grad_grid_cl,
-                             void* workspace, size_t workspace_bytes, int32_t* nslices_out, void* stream);
+                             const float* tc_panels /* nullable: lfgc_tc_panel_build */, void* workspace,
+                             size_t workspace_bytes, int32_t* nslices_out, void* stream);
 
 /* Everything of one optimiser step that is not per-sample, for mask-free models, in ONE launch: [sum over the
  * data-parallel ranks' gradient buffers, read from peer memory] -> reduction of the MLP-gradient partial sums (+ loss) ->
@@ -340,6 +352,10 @@ typedef struct lfgc_grid_step_args {
      * the coarser levels go through the per-channel shared-memory kernel: three dependent launches. */
     float* scratch;
     size_t scratch_bytes;
+    /* Optional: the tensor-core operand image of the model whose MLP block this step updates (lfgc_tc_panel_bytes > 0);
+     * the thread that applies Adam to a parameter also stores its hi / lo parts at their operand positions. */
+    const lfgc_model_desc* panel_model;
+    float* panel_image;
 } lfgc_grid_step_args;
 int lfgc_grid_step(const lfgc_wavelet_desc* w, int Cp, const lfgc_grid_step_args* a, void* stream);
 /* dynamic shared memory lfgc_grid_step needs for this pyramid; 0 = not supported (does not fit: use the separate kernels) */

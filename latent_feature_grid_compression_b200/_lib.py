@@ -18,7 +18,7 @@ MAX_PEERS = 16
 
 MASK_IDENTITY, MASK_DIRECT, MASK_VARIATIONAL, MASK_STE_SIGMOID, MASK_BERNOULLI = range(5)
 F_CLAMP = 1
-ABI_VERSION = 5   # include/lfgc.h LFGC_ABI_VERSION this binding was written against
+ABI_VERSION = 6   # include/lfgc.h LFGC_ABI_VERSION this binding was written against
 
 _ERRORS = {-1: 'LFGC_E_INVALID', -2: 'LFGC_E_UNSUPPORTED', -3: 'LFGC_E_CUDA', -4: 'LFGC_E_WORKSPACE'}
 
@@ -49,7 +49,8 @@ class GridStepArgs(C.Structure):
                 ('grid_cl', _f), ('p', _f), ('g', _f), ('m', _f), ('v', _f), ('coeff_off', _i64 * MAX_LEVELS),
                 ('mlp_off', _i64), ('loss_out', _f), ('lr', _f), ('step_count', _f), ('beta1', C.c_double),
                 ('beta2', C.c_double), ('eps', C.c_double), ('grad_scale', C.c_double), ('weight_l2', C.c_double),
-                ('scratch', _f), ('scratch_bytes', C.c_size_t)]
+                ('scratch', _f), ('scratch_bytes', C.c_size_t), ('panel_model', C.POINTER(ModelDesc)),
+                ('panel_image', _f)]
 
 
 class PeerAnnounce(C.Structure):
@@ -97,11 +98,13 @@ _SIGNATURES = {
     'lfgc_add_l2_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_add_l1_grad': (C.c_int, [_f, _f, _i64, C.c_float, _f]),
     'lfgc_train_step_partials': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64, _f,
-                                           C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, C.c_size_t,
+                                           C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, _f, C.c_size_t,
                                            C.POINTER(C.c_int32), _f]),
+    'lfgc_tc_panel_bytes': (C.c_size_t, [C.POINTER(ModelDesc)]),
+    'lfgc_tc_panel_build': (C.c_int, [C.POINTER(ModelDesc), _f, _f, _f]),
     'lfgc_train_step_accumulate': (C.c_int, [C.POINTER(ModelDesc), _f, C.POINTER(C.c_int32), _i64, C.c_uint64, C.c_uint64,
                                              _f, C.c_uint64, _f, _f, _f, C.c_float, _f, _f, _f, _f, C.c_int, C.POINTER(PeerAnnounce),
-                                             _f, C.c_size_t, _f]),
+                                             _f, _f, C.c_size_t, _f]),
     'lfgc_grid_step': (C.c_int, [C.POINTER(WaveletDesc), C.c_int, C.POINTER(GridStepArgs), _f]),
     'lfgc_grid_step_smem_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),
     'lfgc_grid_step_scratch_bytes': (C.c_size_t, [C.POINTER(WaveletDesc)]),

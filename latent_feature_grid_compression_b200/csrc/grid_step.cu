@@ -26,6 +26,7 @@
 // Models whose per-channel pyramid does not fit in shared memory (G > ~22) or with live mask layers keep the separate
 // kernels (FastTrainer falls back; lfgc_grid_step_smem_bytes() == 0 says so).
 #include "wavelet_lines.cuh"
+#include "tc_panels.cuh"
 
 #include <stdlib.h>
 
@@ -69,6 +70,8 @@ struct Args {
     AdamCoef c;
     float w2x2;                       // 2 * weight_l2
     int n_mlp_ctas;
+    unsigned char* panel_image;       // tensor-core weight operands kept current with the MLP parameters (tc_panels.cuh), nullable
+    TcPanelMap pm;
 };
 
 // Shared-memory (or, in the host test, heap) partitions of one channel
@@ -305,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) grid_step_kernel(const __grid_con
                 A.m[i] = mi;
                 A.v[i] = vi;
                 A.g[i] = t;
+                if (A.panel_image) tc_panel_store(A.panel_image, A.pm, j, pi);   // hi / lo parts at their operand positions
             } else if (A.loss_out) {
                 A.loss_out[0] = t;
             }
@@ -473,6 +477,19 @@ static int gstep_fill(gstep::Args& A, const lfgc_wavelet_desc* w, int Cp, const 
     A.c = make_adam_coef(a->beta1, a->beta2, a->eps, a->grad_scale);
     A.w2x2 = (float)(2.0 * a->weight_l2);
     A.n_mlp_ctas = a->pcount > 0 ? (a->pcount + 1 + 63) / 64 : 0;   // 64 parameters per CTA (see the kernel)
+    A.panel_image = nullptr;
+    if (a->panel_image && a->panel_model) {
+        SampleParams P;
+        const int prc = fill_sample_params(a->panel_model, 0, P);
+        if (prc) return prc;
+        A.pm = make_tc_panel_map(P);
+        if (A.pm.total_bytes > 0) {
+            const int pc = (P.in0 * P.H + P.H) + (P.L - 1) * (P.H * P.H + P.H) + P.H + 1;   // packed MLP block
+            if (pc != a->pcount)
+                return fail(LFGC_E_INVALID, "grid_step: panel_model has %d MLP parameters, pcount = %d", pc, a->pcount);
+            A.panel_image = reinterpret_cast<unsigned char*>(a->panel_image);
+        }
+    }
     return LFGC_OK;
 }
 

@@ -513,12 +513,15 @@ static int train_step_impl(const lfgc_model_desc* m, const float* volume, const 
                            const float* mlp, float* grad_grid_cl, float* grad_mlp, float* loss_sum, int accumulate_mlp,
                            void* workspace, size_t workspace_bytes, void* stream, int32_t* nslices_out = nullptr,
                            float* atomic_out = nullptr, const lfgc_peer_announce* announce = nullptr,
-                           int atomic_slices = 1) {
+                           int atomic_slices = 1, const float* tc_panels = nullptr) {
     BwdArgs A;
     A.defer_reduce = nslices_out ? 1 : 0;
     A.nslices = 0;
     A.atomic_out = atomic_out;
     A.atomic_slices = atomic_slices;
+    if (tc_panels && (reinterpret_cast<uintptr_t>(tc_panels) & 15))
+        return fail(LFGC_E_INVALID, "train_step: the panel image must be 16-byte aligned");
+    A.panel_image = reinterpret_cast<const unsigned char*>(tc_panels);
     if (announce) {
         if (!atomic_out || announce->n_peers < 1 || announce->n_peers > LFGC_MAX_PEERS || announce->rank < 0 ||
             announce->rank >= announce->n_peers || !announce->epoch || !announce->ticket)
@@ -600,13 +603,13 @@ extern "C" int lfgc_train_step_partials(const lfgc_model_desc* m, const float* v
                                         uint64_t seed, uint64_t sample_offset, const int32_t* step_dev,
                                         uint64_t step_stride, const int64_t* explicit_idx, const float* explicit_coords,
                                         const float* explicit_gt, float loss_scale, const float* grid_cl, const float* mlp,
-                                        float* grad_grid_cl, void* workspace, size_t workspace_bytes,
-                                        int32_t* nslices_out, void* stream) {
+                                        float* grad_grid_cl, const float* tc_panels, void* workspace,
+                                        size_t workspace_bytes, int32_t* nslices_out, void* stream) {
     if (!nslices_out) return fail(LFGC_E_INVALID, "train_step_partials: nslices_out is null");
     if (n == 0) return fail(LFGC_E_INVALID, "train_step_partials: n must be positive (nothing would be written)");
     return train_step_impl(m, volume, R, n, seed, sample_offset, step_dev, step_stride, explicit_idx, explicit_coords,
                            explicit_gt, loss_scale, nullptr, nullptr, grid_cl, mlp, grad_grid_cl, nullptr, nullptr, 0,
-                           workspace, workspace_bytes, stream, nslices_out);
+                           workspace, workspace_bytes, stream, nslices_out, nullptr, nullptr, 1, tc_panels);
 }
 
 extern "C" int lfgc_train_step_accumulate(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,
@@ -614,14 +617,14 @@ extern "C" int lfgc_train_step_accumulate(const lfgc_model_desc* m, const float*
                                           uint64_t step_stride, const int64_t* explicit_idx, const float* explicit_coords,
                                           const float* explicit_gt, float loss_scale, const float* grid_cl,
                                           const float* mlp, float* grad_grid_cl, float* grad_mlp_loss, int n_slices,
-                                          const lfgc_peer_announce* announce, void* workspace, size_t workspace_bytes,
-                                          void* stream) {
+                                          const lfgc_peer_announce* announce, const float* tc_panels, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
     if (!grad_mlp_loss) return fail(LFGC_E_INVALID, "train_step_accumulate: grad_mlp_loss is null");
     if (n_slices < 1 || n_slices > 1024) return fail(LFGC_E_INVALID, "train_step_accumulate: n_slices = %d", n_slices);
     if (n == 0 && announce) return fail(LFGC_E_INVALID, "train_step_accumulate: n must be positive with an announcement");
     return train_step_impl(m, volume, R, n, seed, sample_offset, step_dev, step_stride, explicit_idx, explicit_coords,
                            explicit_gt, loss_scale, nullptr, nullptr, grid_cl, mlp, grad_grid_cl, nullptr, nullptr, 1,
-                           workspace, workspace_bytes, stream, nullptr, grad_mlp_loss, announce, n_slices);
+                           workspace, workspace_bytes, stream, nullptr, grad_mlp_loss, announce, n_slices, tc_panels);
 }
 
 extern "C" int lfgc_train_step_weighted(const lfgc_model_desc* m, const float* volume, const int32_t R[3], int64_t n,

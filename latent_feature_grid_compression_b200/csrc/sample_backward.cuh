@@ -32,6 +32,7 @@ struct BwdArgs {
     float* atomic_out = nullptr;  // lfgc_train_step_accumulate: [pcount + 1] running sums (MLP gradient | loss) the kernel
                                   // ADDS to; the tensor-core kernel does it with atomics from its flush (no workspace
                                   // slices, no reduction launch), the other kernels through the reduction kernel
+    const unsigned char* panel_image = nullptr;   // tensor-core kernel: ready-made weight operands (tc_panels.cuh), nullable
     int atomic_slices = 1;        // the tensor-core kernel spreads its CTAs over this many [pcount + 1] slices of atomic_out:
                                   // 148 same-address reductions arriving together serialise in L2 (~3.5 us at one slice)
     // early announcement for lfgc_peer_sum (lfgc_peer_announce): the last CTA to finish stores *ann_epoch + 1 into slot

@@ -41,6 +41,7 @@
 //
 // Layer-0 columns are permuted as in the forward kernel: k = [features (Cp) | xyz | Fourier | zero pad to K0p].
 #include "sample_backward.cuh"
+#include "tc_panels.cuh"
 
 #include <stdlib.h>
 
@@ -389,32 +390,53 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    const bool have_image = A.panel_image != nullptr;
     {
         // zero what must read as zero / finite: the second column group of the MN-major activation block (only the ones
-        // column and the layer-0 columns >= 32 are ever written there) and the weight panels (pad rows / columns)
+        // column and the layer-0 columns >= 32 are ever written there) and, when they are built here, the weight panels
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int e = threadIdx.x; e < kBlkMN / 16; e += NT) {
             reinterpret_cast<float4*>(Hm + kBlkMN)[e] = z4;
             reinterpret_cast<float4*>(Hm + 3 * kBlkMN)[e] = z4;
         }
-        for (int e = threadIdx.x; e < (Lo.total - Lo.Wf) / 16; e += NT) reinterpret_cast<float4*>(smem + Lo.Wf)[e] = z4;
-        // the packed parameter block, staged through shared memory with independent loads (one L2 round trip)
-        float* stage = reinterpret_cast<float*>(DmHi);
-        if ((reinterpret_cast<uintptr_t>(A.mlp) & 15) == 0) {
-            const int n4 = A.pcount >> 2;
-            for (int e4 = threadIdx.x; e4 < n4; e4 += NT)
-                reinterpret_cast<float4*>(stage)[e4] = __ldg(reinterpret_cast<const float4*>(A.mlp) + e4);
-            if ((int)threadIdx.x < (A.pcount & 3)) stage[4 * n4 + threadIdx.x] = __ldg(A.mlp + 4 * n4 + threadIdx.x);
+        if (have_image) {
+            // ready-made operands (tc_panels.cuh, kept current by the optimiser step): two straight 128-bit copies, all
+            // loads of a thread in flight together
+            const float4* hsrc = reinterpret_cast<const float4*>(A.panel_image);
+            float4* hdst = reinterpret_cast<float4*>(smem + Lo.bias);
+            for (int e = threadIdx.x; e < kTcHdrCopy / 16; e += NT) hdst[e] = __ldg(hsrc + e);
+            const float4* psrc = reinterpret_cast<const float4*>(A.panel_image + kTcHdrBytes);
+            float4* pdst = reinterpret_cast<float4*>(smem + Lo.Wf);
+            const int n16 = (Lo.total - Lo.Wf) / 16;
+            for (int base = threadIdx.x; base < n16; base += 8 * NT) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (base + u * NT < n16) v[u] = __ldg(psrc + base + u * NT);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (base + u * NT < n16) pdst[base + u * NT] = v[u];
+            }
         } else {
-            for (int e = threadIdx.x; e < A.pcount; e += NT) stage[e] = __ldg(A.mlp + e);
+            for (int e = threadIdx.x; e < (Lo.total - Lo.Wf) / 16; e += NT) reinterpret_cast<float4*>(smem + Lo.Wf)[e] = z4;
+            // the packed parameter block, staged through shared memory with independent loads (one L2 round trip)
+            float* stage = reinterpret_cast<float*>(DmHi);
+            if ((reinterpret_cast<uintptr_t>(A.mlp) & 15) == 0) {
+                const int n4 = A.pcount >> 2;
+                for (int e4 = threadIdx.x; e4 < n4; e4 += NT)
+                    reinterpret_cast<float4*>(stage)[e4] = __ldg(reinterpret_cast<const float4*>(A.mlp) + e4);
+                if ((int)threadIdx.x < (A.pcount & 3)) stage[4 * n4 + threadIdx.x] = __ldg(A.mlp + 4 * n4 + threadIdx.x);
+            } else {
+                for (int e = threadIdx.x; e < A.pcount; e += NT) stage[e] = __ldg(A.mlp + e);
+            }
         }
     }
     __syncthreads();
     BT_MARK(12)  // setup: zero fill, parameter staging, TMEM allocation
-    {
+    // ones column (column 31 of group 1 of the hi block): bias gradient row of every dW accumulator
+    for (int r = threadIdx.x; r < TILE; r += NT) *reinterpret_cast<float*>(Hm + kBlkMN + mn_off(r, 31)) = 1.0f;
+    if (!have_image) {
         const float* stage = reinterpret_cast<const float*>(DmHi);
-        // ones column (column 31 of group 1 of the hi block): bias gradient row of every dW accumulator
-        for (int r = threadIdx.x; r < TILE; r += NT) *reinterpret_cast<float*>(Hm + kBlkMN + mn_off(r, 31)) = 1.0f;
         for (int l = 0; l < L; ++l) {
             const int K = l == 0 ? in0 : H;
             const float* W = stage + mlp_w_off(l, in0, H);
@@ -918,6 +940,36 @@ int launch_backward_tc(BwdArgs& A, int fused, float* grad_mlp, int accumulate, v
 }
 
 }  // namespace lfgc
+
+namespace lfgc {
+__global__ void tc_panel_build_kernel(const float* __restrict__ mlp, unsigned char* __restrict__ img, const TcPanelMap M,
+                                      int pcount) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pcount) tc_panel_store(img, M, i, mlp[i]);
+}
+}  // namespace lfgc
+
+extern "C" size_t lfgc_tc_panel_bytes(const lfgc_model_desc* m) {
+    lfgc::SampleParams P;
+    if (!m || lfgc::fill_sample_params(m, 0, P)) return 0;
+    return (size_t)lfgc::make_tc_panel_map(P).total_bytes;
+}
+
+extern "C" int lfgc_tc_panel_build(const lfgc_model_desc* m, const float* mlp, float* image, void* stream) {
+    using namespace lfgc;
+    SampleParams P;
+    if (!m || !mlp || !image) return fail(LFGC_E_INVALID, "tc_panel_build: null pointer");
+    const int rc = fill_sample_params(m, 0, P);
+    if (rc) return rc;
+    const TcPanelMap M = make_tc_panel_map(P);
+    if (M.total_bytes == 0) return fail(LFGC_E_UNSUPPORTED, "tc_panel_build: the tensor-core kernel does not cover this model");
+    if (reinterpret_cast<uintptr_t>(image) & 15) return fail(LFGC_E_INVALID, "tc_panel_build: the image must be 16-byte aligned");
+    const int pcount = (int)lfgc_mlp_param_count(m);
+    LFGC_CUDA_OK(cudaMemsetAsync(image, 0, (size_t)M.total_bytes, (cudaStream_t)stream));
+    tc_panel_build_kernel<<<(pcount + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mlp, reinterpret_cast<unsigned char*>(image), M, pcount);
+    LFGC_LAUNCH_OK();
+    return LFGC_OK;
+}
 
 #ifdef LFGC_PHASE_TIMING
 extern "C" int lfgc_btc_timing(unsigned long long* out16, int reset) {

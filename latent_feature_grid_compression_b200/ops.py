@@ -409,7 +409,7 @@ def adam_reg(p, g, m, v, lr_dev, step_dev, l2_range, weight_l2, l1_range, weight
 
 def train_step_partials(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl,
                         mlp_flat, grad_grid_cl, workspace, step_dev=None, step_stride: int = 0, coords=None,
-                        targets=None, explicit_idx=None) -> int:
+                        targets=None, explicit_idx=None, tc_panels=None) -> int:
     """``train_step`` that leaves the MLP-gradient partial sums (and the loss partials) in ``workspace`` for
     ``grid_step`` to reduce; returns the number of partial rows (lfgc_train_step_partials)."""
     lib = L.load()
@@ -426,14 +426,14 @@ def train_step_partials(geom: Geometry, volume, n: int, seed: int, sample_offset
                                          int(sample_offset), _p(step_dev), int(step_stride), _p(explicit_idx),
                                          _p(coords), _p(targets), float(loss_scale), _p(_req(grid_cl, 'grid_cl')),
                                          _p(_req(mlp_flat, 'mlp')), _p(_req(grad_grid_cl, 'grad_grid_cl')),
-                                         _p(_req(workspace, 'workspace')), workspace.numel() * 4, ct.byref(ns),
-                                         _stream()), 'lfgc_train_step_partials')
+                                         _p(tc_panels), _p(_req(workspace, 'workspace')), workspace.numel() * 4,
+                                         ct.byref(ns), _stream()), 'lfgc_train_step_partials')
     return int(ns.value)
 
 
 def train_step_accumulate(geom: Geometry, volume, n: int, seed: int, sample_offset: int, loss_scale: float, grid_cl,
                           mlp_flat, grad_grid_cl, grad_mlp_loss, workspace, step_dev=None, step_stride: int = 0,
-                          coords=None, targets=None, explicit_idx=None, announce=None, n_slices: int = 1):
+                          coords=None, targets=None, explicit_idx=None, announce=None, n_slices: int = 1, tc_panels=None):
     """``train_step`` that ADDS its MLP-gradient sums and loss sum to ``grad_mlp_loss`` (mlp_param_count + 1 floats, a
     per row, ``n_slices`` rows whose SUM is the result: a running sum the caller cleared) -- atomics from the tensor-core
     kernel's epilogue, its CTAs spread over the rows, no reduction launch
@@ -456,7 +456,7 @@ def train_step_accumulate(geom: Geometry, volume, n: int, seed: int, sample_offs
                                            _p(coords), _p(targets), float(loss_scale), _p(_req(grid_cl, 'grid_cl')),
                                            _p(_req(mlp_flat, 'mlp')), _p(_req(grad_grid_cl, 'grad_grid_cl')),
                                            _p(_req(grad_mlp_loss, 'grad_mlp_loss')), int(n_slices),
-                                           ct.byref(announce) if announce is not None else None,
+                                           ct.byref(announce) if announce is not None else None, _p(tc_panels),
                                            _p(_req(workspace, 'workspace')), workspace.numel() * 4, _stream()),
             'lfgc_train_step_accumulate')
 
@@ -500,11 +500,12 @@ def grid_step_scratch_floats(geom: Geometry) -> int:
 
 def grid_step(geom: Geometry, grad_grids, mlp_partials, nslices: int, pstride: int, pcount: int, grid_cl, p, g, m, v,
               coeff_offs, mlp_off: int, lr_dev, step_dev, zero_grid=None, loss_out=None, beta1=0.9, beta2=0.999,
-              eps=1e-8, grad_scale=1.0, weight_l2=0.0, scratch=None):
+              eps=1e-8, grad_scale=1.0, weight_l2=0.0, scratch=None, tc_panels=None):
     """Everything of one optimiser step that is not per-sample, one launch (lfgc_grid_step): partial reduction +
     synthesis adjoint + Adam + synthesis of the updated coefficients.  ``grad_grids`` / ``mlp_partials``: lists (one
     entry per gradient source: this rank, or every data-parallel rank in rank order) of tensors or raw device
-    addresses.  ``scratch`` (grid_step_scratch_floats) enables the split path: finest level on the whole GPU."""
+    addresses.  ``scratch`` (grid_step_scratch_floats) enables the split path: finest level on the whole GPU.
+    ``tc_panels`` (tc_panel_image): kept current with the MLP parameters this step updates."""
     lib = L.load()
     _req(step_dev, 'step', torch.int32)
     a = L.GridStepArgs()
@@ -528,7 +529,24 @@ def grid_step(geom: Geometry, grad_grids, mlp_partials, nslices: int, pstride: i
     if scratch is not None:
         a.scratch = _p(_req(scratch, 'scratch'))
         a.scratch_bytes = scratch.numel() * 4
+    if tc_panels is not None:
+        a.panel_model = ct.pointer(geom.model_desc)
+        a.panel_image = _p(_req(tc_panels, 'tc_panels'))
     L.check(lib.lfgc_grid_step(ct.byref(geom.wavelet_desc), geom.Cp, ct.byref(a), _stream()), 'lfgc_grid_step')
+
+
+def tc_panel_image(geom: Geometry, mlp_flat, out=None):
+    """Operand image of the tensor-core training kernel for the packed MLP block ``mlp_flat`` (lfgc_tc_panel_build); None
+    when the tensor-core kernel does not cover the model.  ``out``: rebuild into an existing image."""
+    lib = L.load()
+    nbytes = int(lib.lfgc_tc_panel_bytes(ct.byref(geom.model_desc)))
+    if nbytes == 0:
+        return None
+    if out is None:
+        out = torch.zeros((nbytes + 3) // 4, device=mlp_flat.device, dtype=torch.float32)
+    L.check(lib.lfgc_tc_panel_build(ct.byref(geom.model_desc), _p(_req(mlp_flat, 'mlp')), _p(_req(out, 'image')), _stream()),
+            'lfgc_tc_panel_build')
+    return out
 
 
 def add_l2_grad(g, p, weight: float):

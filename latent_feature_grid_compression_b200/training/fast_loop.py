@@ -160,6 +160,7 @@ class FastTrainer:
         else:
             self._red2 = [torch.zeros(self._n_red, device=self.device, dtype=torch.float32)]
         self._side = None
+        self._tc_panels = None
         self._par = 0                        # parity of the next step (only the p2p path has two buffers)
         self._set_red(0)
         self.scratch = torch.empty(max(self.geom.decode_scratch_bytes // 4, 4), device=self.device)
@@ -411,6 +412,8 @@ class FastTrainer:
         ops.decode_fwd(self.geom, coeffs, [None] * len(coeffs), scratch=self.scratch, out=self.grid_cl)
         for r in self._red2:
             r.zero_()
+        # operand image of the tensor-core kernel: lfgc_grid_step keeps it current from here on
+        self._tc_panels = ops.tc_panel_image(self.geom, self.mlp_flat, out=self._tc_panels)
         self._gstep_primed = True
 
     def _step_body_gstep(self, host_fed, in_coords, in_targets):
@@ -427,10 +430,10 @@ class FastTrainer:
         common = dict(grid_cl=self.grid_cl, p=self.flat_p, g=self.flat_g, m=self.flat_m, v=self.flat_v,
                       coeff_offs=self._coeff_offs, mlp_off=self.mlp_off, lr_dev=self.lr_dev, step_dev=self.step_dev,
                       zero_grid=self.grad_grid, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
-                      weight_l2=self.weight_l2, scratch=self._gstep_scratch)
+                      weight_l2=self.weight_l2, scratch=self._gstep_scratch, tc_panels=self._tc_panels)
         if self.world == 1:
             ns = ops.train_step_partials(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl,
-                                         self.mlp_flat, self.grad_grid, self.workspace, **kw)
+                                         self.mlp_flat, self.grad_grid, self.workspace, tc_panels=self._tc_panels, **kw)
             ops.grid_step(geom, [self.grad_grid], [self.workspace], ns, pcount + 1, pcount, loss_out=self.loss_sum,
                           **common)
             return
@@ -445,7 +448,7 @@ class FastTrainer:
         # ... and its last CTA stores this rank's epoch flags, so they cross NVLink during the launch gap
         ops.train_step_accumulate(geom, self.volume, self.batch, self.seed, offset, scale, self.grid_cl, self.mlp_flat,
                                   self.grad_grid, self.red_mlp, self.workspace, announce=self._p2p['announce'],
-                                  n_slices=self._acc_slices, **kw)
+                                  n_slices=self._acc_slices, tc_panels=self._tc_panels, **kw)
         # lfgc_peer_sum: this step's buffers of all ranks -> one local sum (barrier inside the kernel); the accumulator it
         # clears is the OTHER parity's (its last readers finished before they announced this epoch)
         P = self._p2p

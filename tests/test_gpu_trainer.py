@@ -195,6 +195,12 @@ def test_grid_step_path_equals_separate_kernels(wavelet, G, C, w2, split, monkey
     assert float(tb.grad_grid.abs().max()) == 0.0
     # the parameters the model exposes are the updated ones (views into the flat buffer)
     assert b.feature_grid[0].data_ptr() == tb.flat_p.data_ptr()
+    # the tensor-core operand image the step keeps current (csrc/tc_panels.cuh) is bit-identical to one rebuilt from the
+    # updated parameters
+    assert tb._tc_panels is not None
+    rebuilt = ops.tc_panel_image(tb.geom, tb.mlp_flat)
+    torch.cuda.synchronize()
+    assert torch.equal(rebuilt.view(torch.int32), tb._tc_panels.view(torch.int32))
 
 
 def test_grid_step_falls_back_when_the_pyramid_does_not_fit_or_masks_are_live():

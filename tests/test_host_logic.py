@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, sym), sym
     assert set(declared) == set(_lib.EXPORTED_SYMBOLS)
     loaded = _lib.load()
-    assert loaded.lfgc_abi_version() == _lib.ABI_VERSION == 5
+    assert loaded.lfgc_abi_version() == _lib.ABI_VERSION == 6
     assert loaded.lfgc_last_error() is not None
 
 
