@@ -405,18 +405,14 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             const float4* hsrc = reinterpret_cast<const float4*>(A.panel_image);
             float4* hdst = reinterpret_cast<float4*>(smem + Lo.bias);
             for (int e = threadIdx.x; e < kTcHdrCopy / 16; e += NT) hdst[e] = __ldg(hsrc + e);
-            const float4* psrc = reinterpret_cast<const float4*>(A.panel_image + kTcHdrBytes);
-            float4* pdst = reinterpret_cast<float4*>(smem + Lo.Wf);
+            // the panels are first needed by the MMAs after the first tile's input stage: asynchronous copies (LDGSTS),
+            // waited for just before that stage's closing barrier
+            const unsigned char* psrc = A.panel_image + kTcHdrBytes;
+            const uint32_t pdst = smem_u32(smem + Lo.Wf);
             const int n16 = (Lo.total - Lo.Wf) / 16;
-            for (int base = threadIdx.x; base < n16; base += 8 * NT) {
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (base + u * NT < n16) v[u] = __ldg(psrc + base + u * NT);
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (base + u * NT < n16) pdst[base + u * NT] = v[u];
-            }
+            for (int e = threadIdx.x; e < n16; e += NT)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pdst + 16u * (uint32_t)e), "l"(psrc + 16 * (size_t)e) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
         } else {
             for (int e = threadIdx.x; e < (Lo.total - Lo.Wf) / 16; e += NT) reinterpret_cast<float4*>(smem + Lo.Wf)[e] = z4;
             // the packed parameter block, staged through shared memory with independent loads (one L2 round trip)
@@ -576,6 +572,10 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             }
         }
         tmem_st_wait();
+        if (first_tile && have_image) {   // the weight panels have landed; make them visible to the tensor core's reads
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         BT_MARK(1)  // input stage
         __syncthreads();

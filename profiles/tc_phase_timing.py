@@ -13,16 +13,19 @@ vol = torch.rand(255, 255, 255, device='cuda') * 2 - 1
 ws = torch.empty(geom.backward_workspace_bytes // 4, device='cuda')
 os.environ['LFGC_BACKWARD_TC'] = '1'
 names = ['setup', 'input', 'barrier', 'mma issue', 'mma wait', 'fwd epilogue', 'output+loss', 'bwd staging', 'dz', 'scatter', 'flush (reduction)', 'dW wait', 'setup: fill+stage', 'setup: panels', 'flush: lo halves', 'flush: dW rows']
+panels = ops.tc_panel_image(geom, mlp)
 for tps in ('2',):
     os.environ['LFGC_TC_TPS'] = tps
-    for n in (32768, 262144):
+    for n in (32768, 32768.5, 262144):
+        img = panels if n != int(n) else None     # n = 32768.5: the same launch with the ready-made operand image
+        n = int(n)
         gg = torch.zeros((*geom.G, geom.Cp), device='cuda'); gm = torch.empty(geom.mlp_param_count, device='cuda'); ls = torch.zeros(1, device='cuda')
-        for _ in range(3): ops.train_step(geom, vol, n, 7, 0, 1.0 / n, grid, mlp, gg, gm, ls, ws)
+        for _ in range(3): ops.train_step_partials(geom, vol, n, 7, 0, 1.0 / n, grid, mlp, gg, ws, tc_panels=img)
         lib.lfgc_btc_timing(None, 1)
         reps = 10
-        for _ in range(reps): ops.train_step(geom, vol, n, 7, 0, 1.0 / n, grid, mlp, gg, gm, ls, ws)
+        for _ in range(reps): ops.train_step_partials(geom, vol, n, 7, 0, 1.0 / n, grid, mlp, gg, ws, tc_panels=img)
         buf = (ctypes.c_ulonglong * 16)(); lib.lfgc_btc_timing(buf, 1)
         ctas = min(148, (n + 127) // 128)
         tot = sum(buf[:16])
-        print('tps=%s n=%d: cycles per CTA (thread 0) per launch: %.0f  (tiles per CTA %.2f)' % (tps, n, tot / reps / ctas, n / 128 / ctas))
+        print('tps=%s n=%d%s: cycles per CTA (thread 0) per launch: %.0f  (tiles per CTA %.2f)' % (tps, n, ' (operand image)' if img is not None else '', tot / reps / ctas, n / 128 / ctas))
         for i, nm in enumerate(names): print('  %-14s %9.0f %5.1f%%' % (nm, buf[i] / reps / ctas, 100.0 * buf[i] / tot))
