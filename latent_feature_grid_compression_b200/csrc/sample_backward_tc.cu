@@ -371,15 +371,6 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
         }
     };
     auto issue_gather = [&]() { gather_pair(q); };
-    // The first tile's loads go out before the one-time setup below: the Philox draw, the volume read and the 16 gathers are
-    // three dependent memory round trips that now overlap the ~7 k cycles of parameter staging.
-    if ((int64_t)blockIdx.x * TILE < A.n) {
-        const int64_t sg0 = (int64_t)blockIdx.x * TILE + s;
-        load_position(sg0, sg0 < A.n, cx, cy, cz, aux);
-        make_corners(P, cx, cy, cz, Kc);
-        issue_gather();
-    }
-
     // ---- one-time setup ------------------------------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barA), "r"(1));
@@ -427,6 +418,16 @@ __global__ void __launch_bounds__(TILE * TPS, 1) backward_tc_kernel(const __grid
             }
         }
     }
+    // The first tile's loads go out before the rest of the setup (the Philox draw, the volume read and the 16 gathers are
+    // three dependent memory round trips) but AFTER its light part above, which covers the latency of the step-counter load
+    // the Philox counter depends on.
+    if ((int64_t)blockIdx.x * TILE < A.n) {
+        const int64_t sg0 = (int64_t)blockIdx.x * TILE + s;
+        load_position(sg0, sg0 < A.n, cx, cy, cz, aux);
+        make_corners(P, cx, cy, cz, Kc);
+        issue_gather();
+    }
+
     __syncthreads();
     BT_MARK(12)  // setup: zero fill, parameter staging, TMEM allocation
     // ones column (column 31 of group 1 of the hi block): bias gradient row of every dW accumulator
