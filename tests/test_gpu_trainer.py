@@ -217,3 +217,36 @@ def test_grid_step_falls_back_when_the_pyramid_does_not_fit_or_masks_are_live():
     assert not t2._gstep
     t2.step()
     torch.cuda.synchronize()
+
+
+def test_grid_step_path_notices_parameters_changed_from_outside():
+    """The grid-step path carries the decoded grid and the tensor-core operand image from step to step; in-place torch
+    writes to the parameters between steps must refresh both (FastTrainer._run's version check / refresh())."""
+    from latent_feature_grid_compression_b200 import ops
+    from latent_feature_grid_compression_b200.model.model_utils import setup_model
+    from latent_feature_grid_compression_b200.training.fast_loop import FastTrainer
+    torch.manual_seed(3)
+    model = setup_model(3, 32, 1, 4, 'fourier', 2, '', 0.1, 0.9, 'db2', 16, 15, '').cuda().train()
+    tr = FastTrainer(model, _volume(), 4096, lr=0.008, seed=1)
+    assert tr._gstep
+    for _ in range(3):
+        tr.step()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(0.5)
+    before = tr.flat_p.clone()
+    calls = []
+    prime = tr._prime_gstep
+    tr._prime_gstep = lambda: (calls.append(1), prime())[1]
+    tr.step()
+    tr.step()
+    torch.cuda.synchronize()
+    assert len(calls) == 1      # refreshed once, for the step after the outside write, and not again
+    # two Adam steps move a parameter by at most ~2 lr: the steps started from the halved parameters
+    assert float((tr.flat_p - before).abs().max()) <= 0.05
+    rebuilt = ops.tc_panel_image(tr.geom, tr.mlp_flat)
+    fresh = ops.decode_fwd(tr.geom, [p.data for p in tr.coeff_params], [None] * len(tr.coeff_params))
+    torch.cuda.synchronize()
+    assert torch.equal(rebuilt.view(torch.int32), tr._tc_panels.view(torch.int32))
+    assert float((fresh - tr.grid_cl).abs().max()) <= 2e-6 * float(fresh.abs().max())
