@@ -76,6 +76,7 @@ class FastTrainer:
         self.mlp_params = model._mlp_params()
         self.var_params = self.var_model._params() if self.var_model is not None else []
         every = self.coeff_params + self.mask_params + self.mlp_params + self.var_params
+        self._every_param = every
         # sections start on 16-byte boundaries (the kernels use 128-bit loads where the alignment allows)
         def pad4(n):
             return (n + 3) // 4 * 4
@@ -415,7 +416,7 @@ class FastTrainer:
         # operand image of the tensor-core kernel: lfgc_grid_step keeps it current from here on
         self._tc_panels = ops.tc_panel_image(self.geom, self.mlp_flat, out=self._tc_panels)
         self._gstep_primed = True
-        self._flat_version = self.flat_p._version
+        self._flat_version = self._param_version()
 
     def _step_body_gstep(self, host_fed, in_coords, in_targets):
         """Two launches per optimiser step: the fused per-sample kernel (partial sums left in the workspace) and
@@ -515,17 +516,23 @@ class FastTrainer:
         if self._p2p is not None:
             self._par ^= 1
 
+    def _param_version(self):
+        """Changes whenever a torch in-place operation wrote to a parameter or to the flat buffer (the kernels write through
+        raw pointers and leave the counters alone)."""
+        return self.flat_p._version + sum(p._version for p in self._every_param)
+
     def refresh(self):
         """Call after changing parameters OUTSIDE the trainer (the grid-step path carries two things derived from them from
         step to step: the decoded grid and the tensor-core operand image).  In-place torch operations on the parameters
-        are noticed by themselves (version counter of the flat buffer); raw writes through ``.data`` are not."""
+        are noticed by themselves (version counters of the parameters and of the flat buffer); raw writes through ``.data``
+        are not."""
         if self._gstep:
             self._prime_gstep()
 
     def _run(self, host_fed):
         if (host_fed, 0) not in self._graphs:
             self.capture(host_fed)
-        if self._gstep and self.flat_p._version != self._flat_version:
+        if self._gstep and self._param_version() != self._flat_version:
             self._prime_gstep()     # somebody wrote to the parameters with torch operations since the last step
         self._set_red(self._par)
         g = self._graphs[(host_fed, self._par)]
