@@ -108,6 +108,14 @@ def test_reconstruction_full_size_slabs_and_idempotence():
     parts = [field_from_net(ds, m, True, slab=slab_bounds(255, r, 8), to_cpu=False) for r in range(8)]
     assert torch.equal(torch.cat(parts, 0), full)                                    # 8 z-slabs == whole volume
     assert float(full.max()) <= 1.0 and float(full.min()) >= -1.0
+    # result delivered into pinned host memory (chunked, copies overlapped with the compute): the same values
+    host = torch.empty(255, 255, 255).pin_memory()
+    assert field_from_net(ds, m, True, host_out=host) is host
+    assert torch.equal(host, full.cpu())
+    b, e = slab_bounds(255, 3, 8)
+    part = torch.empty(e - b, 255, 255).pin_memory()
+    field_from_net(ds, m, True, slab=(b, e), host_out=part)
+    assert torch.equal(part, full[b:e].cpu())
     # same values as the per-point API on an arbitrary subset of voxels
     from latent_feature_grid_compression_b200.visualization.OutputToVTK import axis_tables
     ax = axis_tables(ds, 32)
