@@ -556,33 +556,55 @@ class FastTrainer:
         self._in_targets.copy_(targets.view(self.batch), non_blocking=True)
         self._run(True)
 
-    def step_host_pipelined(self, coords, targets):
-        """``step_host`` with the transfers taken off the critical path: the H2D copies of step i run on a copy stream
-        into one of two staging buffer pairs while step i-1 computes, and every step's loss is copied to pinned host
-        memory on the compute stream.  Returns the mean squared error of the PREVIOUS call's step (None on the first
-        call); ``flush_host_pipeline()`` returns the last one.  Same arithmetic as ``step_host``."""
+    def step_host_pipelined(self, coords, targets=None):
+        """``step_host`` with the transfers taken off the critical path: the H2D copy of step i runs on a copy stream
+        into one of two staging buffers while step i-1 computes, and every step's loss lands in pinned host memory.
+        Returns the mean squared error of the PREVIOUS call's step (None on the first call); ``flush_host_pipeline()``
+        returns the last one.  Same arithmetic as ``step_host``.
+
+        The loop is host-bound (a dozen CUDA API calls per 60 us step), so the calls are kept few: ``coords`` may be ONE
+        pinned buffer of 4 * batch floats, [positions (batch x 3) | targets (batch)] (then ``targets`` is None) -- or a
+        positions / targets pair that lies back to back in one allocation, which is detected -- for a single H2D copy;
+        and the step's loss is written by the kernel straight into pinned host memory (mapped into the device's address
+        space), so there is no D2H copy call at all."""
+        n = self.batch
         if self._pipe is None:
+            stage = [torch.zeros(4 * n, device=self.device) for _ in range(2)]
             self._pipe = dict(
-                coords=[torch.zeros((self.batch, 3), device=self.device) for _ in range(2)],
-                targets=[torch.zeros(self.batch, device=self.device) for _ in range(2)],
+                stage=stage,
+                coords=[t[:3 * n].view(n, 3) for t in stage], targets=[t[3 * n:] for t in stage],
                 loss=[torch.zeros(1).pin_memory() for _ in range(2)],
                 ready=[torch.cuda.Event() for _ in range(2)], consumed=[torch.cuda.Event() for _ in range(2)],
                 done=[torch.cuda.Event() for _ in range(2)], stream=torch.cuda.Stream(), i=0)
+            keep = self.loss_sum
             for b in range(2):
+                self.loss_sum = self._pipe['loss'][b]    # captured as the step's loss destination: host memory, device-visible
                 self.capture(('pipe', b))
+            self.loss_sum = keep
         P = self._pipe
         b = P['i'] & 1
         cur = torch.cuda.current_stream()
+        if targets is None:
+            packed = coords.view(-1)
+        elif (targets.data_ptr() == coords.data_ptr() + 12 * n and coords.is_contiguous() and targets.is_contiguous()
+              and coords.untyped_storage().data_ptr() == targets.untyped_storage().data_ptr()):
+            packed = torch.empty(0, dtype=torch.float32).set_(coords.untyped_storage(), coords.storage_offset(), (4 * n,))
+        else:
+            packed = None
         if P['i'] >= 2:
-            P['stream'].wait_event(P['consumed'][b])      # the step that read this buffer pair has run
+            P['stream'].wait_event(P['consumed'][b])      # the step that read this staging buffer has run
         with torch.cuda.stream(P['stream']):
-            P['coords'][b].copy_(coords.view(self.batch, 3), non_blocking=True)
-            P['targets'][b].copy_(targets.view(self.batch), non_blocking=True)
+            if packed is not None:
+                P['stage'][b].copy_(packed, non_blocking=True)
+            else:
+                P['coords'][b].copy_(coords.view(n, 3), non_blocking=True)
+                P['targets'][b].copy_(targets.view(n), non_blocking=True)
             P['ready'][b].record()
         cur.wait_event(P['ready'][b])
         self._run(('pipe', b))
         P['consumed'][b].record(cur)
-        P['loss'][b].copy_(self.loss_sum, non_blocking=True)
+        if self._p2p is not None:   # peer-sum data parallelism: the loss travels in the summed message (global sum)
+            P['loss'][b].copy_((self._summed_loss() / self.world).reshape(1), non_blocking=True)
         P['done'][b].record(cur)
         prev = None
         if P['i'] >= 1:
