@@ -574,8 +574,8 @@ class FastTrainer:
                 stage=stage,
                 coords=[t[:3 * n].view(n, 3) for t in stage], targets=[t[3 * n:] for t in stage],
                 loss=[torch.zeros(1).pin_memory() for _ in range(2)],
-                ready=[torch.cuda.Event() for _ in range(2)], consumed=[torch.cuda.Event() for _ in range(2)],
-                done=[torch.cuda.Event() for _ in range(2)], stream=torch.cuda.Stream(), i=0)
+                ready=[torch.cuda.Event() for _ in range(2)], done=[torch.cuda.Event() for _ in range(2)],
+                stream=torch.cuda.Stream(), i=0)
             keep = self.loss_sum
             for b in range(2):
                 self.loss_sum = self._pipe['loss'][b]    # captured as the step's loss destination: host memory, device-visible
@@ -592,7 +592,7 @@ class FastTrainer:
         else:
             packed = None
         if P['i'] >= 2:
-            P['stream'].wait_event(P['consumed'][b])      # the step that read this staging buffer has run
+            P['stream'].wait_event(P['done'][b])          # the step that read this staging buffer has run
         with torch.cuda.stream(P['stream']):
             if packed is not None:
                 P['stage'][b].copy_(packed, non_blocking=True)
@@ -602,7 +602,6 @@ class FastTrainer:
             P['ready'][b].record()
         cur.wait_event(P['ready'][b])
         self._run(('pipe', b))
-        P['consumed'][b].record(cur)
         if self._p2p is not None:   # peer-sum data parallelism: the loss travels in the summed message (global sum)
             P['loss'][b].copy_((self._summed_loss() / self.world).reshape(1), non_blocking=True)
         P['done'][b].record(cur)
