@@ -82,6 +82,9 @@ typedef struct lfgc_wavelet_desc {
 } lfgc_wavelet_desc;
 
 int lfgc_abi_version(void);
+/* sizeof(lfgc_wavelet_desc), sizeof(lfgc_model_desc), sizeof(lfgc_peer_announce), sizeof(lfgc_grid_step_args) into out[0..n);
+ * returns how many there are.  Bindings compare their own struct layouts with these when they load the library. */
+int lfgc_struct_sizes(size_t* out, int n);
 const char* lfgc_last_error(void);
 /* number of SMs of the current device (grid sizing); negative on error */
 int lfgc_sm_count(void);

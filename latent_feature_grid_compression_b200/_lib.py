@@ -60,6 +60,7 @@ class PeerAnnounce(C.Structure):
 
 _SIGNATURES = {
     'lfgc_abi_version': (C.c_int, []),
+    'lfgc_struct_sizes': (C.c_int, [C.POINTER(C.c_size_t), C.c_int]),
     'lfgc_last_error': (C.c_char_p, []),
     'lfgc_sm_count': (C.c_int, []),
     'lfgc_launch_count': (C.c_longlong, []),
@@ -135,6 +136,12 @@ def load():
         fn.argtypes = args
     if lib.lfgc_abi_version() != ABI_VERSION:
         raise LfgcError('liblfgc.so ABI version mismatch; rebuild')
+    sizes = (C.c_size_t * 4)()
+    n = lib.lfgc_struct_sizes(sizes, 4)
+    mine = [C.sizeof(WaveletDesc), C.sizeof(ModelDesc), C.sizeof(PeerAnnounce), C.sizeof(GridStepArgs)]
+    if n != len(mine) or [int(v) for v in sizes] != mine:
+        raise LfgcError('struct layouts of this binding %s differ from the library\'s %s (include/lfgc.h changed?)'
+                        % (mine, [int(v) for v in sizes[:n]]))
     _lib = lib
     return lib
 

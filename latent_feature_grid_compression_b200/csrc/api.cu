@@ -73,6 +73,15 @@ int max_smem_optin() {
 }  // namespace lfgc
 
 extern "C" int lfgc_abi_version(void) { return LFGC_ABI_VERSION; }
+
+// sizes of the structs that cross the ABI, in declaration order of include/lfgc.h: a binding checks its own layouts against
+// these at load time (a silent mismatch would corrupt arguments)
+extern "C" int lfgc_struct_sizes(size_t* out, int n) {
+    const size_t sz[] = {sizeof(lfgc_wavelet_desc), sizeof(lfgc_model_desc), sizeof(lfgc_peer_announce), sizeof(lfgc_grid_step_args)};
+    const int have = (int)(sizeof(sz) / sizeof(sz[0]));
+    for (int i = 0; i < n && i < have; ++i) out[i] = sz[i];
+    return have;
+}
 extern "C" const char* lfgc_last_error(void) { return lfgc::last_error_buffer(); }
 extern "C" int lfgc_sm_count(void) { return lfgc::sm_count(); }
 extern "C" long long lfgc_launch_count(void) { return lfgc::launch_count(); }

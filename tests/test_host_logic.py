@@ -29,6 +29,12 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == set(_lib.EXPORTED_SYMBOLS)
     loaded = _lib.load()
     assert loaded.lfgc_abi_version() == _lib.ABI_VERSION == 6
+    # the ctypes mirrors of the ABI structs have the library's sizes (checked again at every load)
+    import ctypes as _ct
+    sizes = (_ct.c_size_t * 4)()
+    assert loaded.lfgc_struct_sizes(sizes, 4) == 4
+    assert [int(v) for v in sizes] == [_ct.sizeof(_lib.WaveletDesc), _ct.sizeof(_lib.ModelDesc),
+                                       _ct.sizeof(_lib.PeerAnnounce), _ct.sizeof(_lib.GridStepArgs)]
     assert loaded.lfgc_last_error() is not None
 
 
